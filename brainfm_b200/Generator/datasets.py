@@ -1,0 +1,658 @@
+"""BaseGen / BrainIDGen: the on-the-fly synthetic-data generator (mirror of Generator/datasets.py:25-757)
+computed by libbfm's sm_100a kernels.
+
+Same constructor, `__len__`, `__getitem__` 5-tuple, `names/mild_samples/all_samples` attributes, operator
+registries and random-draw order as the reference.  Differences that are deliberate:
+  * volumes are decoded once into a device-resident cache and cropped by indexing inside the gather kernels
+    (no per-sample host crop + H2D);
+  * the stock augmentation sequence ['gamma','bias_field','resample','noise'] runs as the fused batched chain
+    (bfm_gen_*); any other sequence, or a re-registered operator, runs op by op through augmentation_funcs;
+  * the two volume-sized N(0,1) fields are generated in-kernel (Philox) unless draws are injected.
+"""
+import ctypes as C
+import glob
+import os
+from collections import defaultdict
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .. import _lib, io as bio
+from ..draws import HostDraws
+from ..plan import Arena, band_host, fill_zoom_tab, zoom_newsize, zoom_tables_host
+from . import constants as K
+from .utils import (DeformDict, DeformPlan, _stream, fast_3D_interp_torch, make_affine_matrix, myzoom_torch,
+                    resolution_sampler)
+
+ct_brightness_group = {
+    'darker': [4, 5, 14, 15, 24, 31, 72],
+    'dark': [2, 7, 16, 77, 30],
+    'bright': [3, 8, 17, 18, 28, 10, 11, 12, 13, 26],
+    'brighter': [],
+}
+
+_STOCK_STEPS = ['gamma', 'bias_field', 'resample', 'noise']
+
+
+class BaseGen(Dataset):
+    """BaseGen dataset (Generator/datasets.py:25-681)."""
+
+    def __init__(self, gen_args, device='cuda', draws=None):
+        if not torch.cuda.is_available():
+            raise _lib.BfmError("brainfm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _lib.lib()
+        self.gen_args = gen_args
+        self.split = gen_args.split
+        self.synth_args = self.gen_args.generator
+        self.shape_gen_args = gen_args.pathology_shape_generator
+        self.real_image_args = gen_args.real_image_generator
+        self.synth_image_args = gen_args.synth_image_generator
+        self.augmentation_steps = vars(gen_args.augmentation_steps)
+        self.input_prob = vars(gen_args.modality_probs)
+        self.device = torch.device('cuda' if device in ('cpu', None) else device)
+        if self.device.type != 'cuda':
+            raise _lib.BfmError("device must be a CUDA device")
+        self.rng = draws or HostDraws()
+        self.cache = bio.DeviceVolumeCache(self.device)
+        self.arena = Arena(self.device)
+        self.write_bflog = None        # None: follow the task list; True/False: force
+        self.prepare_tasks()
+        self.prepare_paths()
+        self.prepare_grid()
+        self.prepare_one_hot()
+
+    def __len__(self):
+        return sum([len(self.names[i]) for i in range(len(self.names))])
+
+    # ---- bookkeeping (datasets.py:52-184) --------------------------------------------------------
+    def idx_to_path(self, idx):
+        cnt = 0
+        for i, l in enumerate(self.datasets_len):
+            if cnt <= idx < cnt + l:
+                name = self.names[i][idx - cnt]
+                age = self.ages[i][os.path.basename(name).split('.T1w')[0]] if len(self.ages) > 0 else None
+                return self.datasets[i], vars(self.input_prob[self.datasets[i]]), name, age
+            cnt += l
+        raise IndexError(idx)
+
+    def prepare_paths(self):
+        if len(self.gen_args.dataset_names) < 1:
+            datasets = []
+            for g in glob.glob(os.path.join(self.gen_args.data_root, '*' + 'T1w.nii')):
+                d = os.path.basename(g)
+                d = d[:d.find('.')]
+                if d not in datasets:
+                    datasets.append(d)
+        else:
+            datasets = self.gen_args.dataset_names
+        names = []
+        if 'age' in self.tasks:
+            self.split = self.split + '_age'
+        if self.gen_args.split_root is not None:
+            with open(os.path.join(self.gen_args.split_root, self.split + '.txt'), 'r') as f:
+                split_names = [s.strip() for s in f.readlines()]
+            for d in datasets:
+                names.append([n for n in split_names if os.path.basename(n).startswith(d)])
+        ages = []
+        if 'age' in self.tasks:
+            with open(os.path.join(self.gen_args.split_root, 'participants_age.txt'), 'r') as f:
+                rows = [line.strip().split(' ') for line in f.readlines()]
+            for d in datasets:
+                ages.append({n: float(a) for n, a in rows if n.startswith(d)})
+        self.ages = ages
+        self.names = names
+        self.datasets = datasets
+        self.datasets_num = len(datasets)
+        self.datasets_len = [len(n) for n in names]
+        self.pathology_type = None
+
+    def prepare_tasks(self):
+        self.tasks = [key for (key, value) in vars(self.gen_args.task).items() if value]
+        if 'bias_field' in self.tasks and 'segmentation' not in self.tasks:
+            self.tasks += ['segmentation']
+        self.t, self.adv_pde = None, None
+        if 'pathology' in self.tasks and self.synth_args.augment_pathology and self.synth_args.random_shape_prob < 1.:
+            from ..ShapeID.DiffEqs.pde import AdvDiffPDE
+            self.t = torch.from_numpy(np.arange(self.shape_gen_args.max_nt) * self.shape_gen_args.dt).to(self.device)
+            self.adv_pde = AdvDiffPDE(data_spacing=[1., 1., 1.], perf_pattern='adv', V_type='vector_div_free',
+                                      V_dict={}, BC=self.shape_gen_args.bc, dt=self.shape_gen_args.dt,
+                                      device=self.device)
+
+    def prepare_grid(self):
+        self.size = list(self.synth_args.size)
+        self.res_training_data = np.array([1.0, 1.0, 1.0])
+        self.c = torch.tensor((np.array(self.size) - 1) / 2, dtype=torch.float)
+
+    def prepare_one_hot(self):
+        if self.synth_args.left_hemis_only:
+            label_list = K.label_list_segmentation_brainseg_left
+        else:
+            label_list = K.label_list_segmentation_brainseg_with_extracerebral
+        n_labels = len(label_list)
+        lut = torch.zeros(10000, dtype=torch.long)
+        for l in range(n_labels):
+            lut[label_list[l]] = l
+        self.lut = lut.to(self.device)
+        self.onehotmatrix = torch.eye(n_labels, dtype=torch.float, device=self.device)
+        nn_ = K.n_neutral_labels_brainseg_with_extracerebral
+        nlat = int((n_labels - nn_) / 2.0)
+        self.vflip = np.concatenate([np.array(range(nn_)), np.array(range(nn_ + nlat, n_labels)),
+                                     np.array(range(nn_, nn_ + nlat))])
+
+    def get_info(self, t1):
+        stem = t1[:-7]
+        self.modalities = {'T1': t1, 'Gen': stem + 'generation_labels.nii',
+                           'segmentation': stem + self.gen_args.segment_prefix + '.nii',
+                           'distance': [stem + 'lp_dist_map.nii', stem + 'lw_dist_map.nii', stem + 'rp_dist_map.nii',
+                                        stem + 'rw_dist_map.nii'],
+                           'registration': [stem + 'mni_reg.x.nii', stem + 'mni_reg.y.nii', stem + 'mni_reg.z.nii']}
+        for key, suffix in (('T1_DM', 'T1w.defacingmask.nii'), ('T2', 'T2w.nii'), ('T2_DM', 'T2w.defacingmask.nii'),
+                            ('FLAIR', 'FLAIR.nii'), ('FLAIR_DM', 'FLAIR.defacingmask.nii'), ('CT', 'CT.nii'),
+                            ('CT_DM', 'CT.defacingmask.nii')):
+            if bio.exists(stem + suffix):
+                self.modalities[key] = stem + suffix
+        return self.modalities
+
+    # ---- random setup (datasets.py:466-493, 563-590) ---------------------------------------------
+    def read_input(self, idx):
+        dataset_name, input_prob, t1_path, age = self.idx_to_path(idx)
+        case_name = os.path.basename(t1_path).split('.T1w.nii')[0]
+        self.modalities = self.get_info(t1_path)
+        prob = self.rng.rand("input.mode")
+        input_mode = 'synth'
+        for m in ('T1', 'T2', 'FLAIR', 'CT'):
+            if prob < input_prob[m] and m in self.modalities:
+                input_mode = m
+                break
+        path = self.modalities['Gen' if input_mode == 'synth' else input_mode]
+        img = bio.load(path)
+        aff = img.affine
+        res = np.sqrt(np.sum(abs(aff[:-1, :-1]), axis=0))
+        return dataset_name, case_name, input_mode, img, aff, res, age
+
+    def get_setup_params(self):
+        a, rng = self.synth_args, self.rng
+        hemis = 'left' if a.left_hemis_only else 'both'
+        if a.low_res_only:
+            photo_mode = False
+        elif a.left_hemis_only:
+            photo_mode = True
+        else:
+            photo_mode = rng.rand("setup.photo") < a.photo_prob
+        pathol_mode = rng.rand("setup.pathol") < a.pathology_prob
+        pathol_random_shape = rng.rand("setup.rshape") < a.random_shape_prob
+        spac = 2.5 + 10 * rng.rand("setup.spac") if photo_mode else None
+        flip = rng.randn("setup.flip") < a.flip_prob if not a.left_hemis_only else False
+        if photo_mode:
+            resolution = np.array([self.res_training_data[0], spac, self.res_training_data[2]])
+            thickness = np.array([self.res_training_data[0], 0.1, self.res_training_data[2]])
+        else:
+            resolution, thickness = resolution_sampler(a.low_res_only, draws=rng)
+        return {'resolution': resolution, 'thickness': thickness, 'photo_mode': photo_mode, 'pathol_mode': pathol_mode,
+                'pathol_random_shape': pathol_random_shape, 'spac': spac, 'flip': flip, 'hemis': hemis}
+
+    # ---- deformation (datasets.py:187-303) --------------------------------------------------------
+    def random_affine_transform(self, shp):
+        a, rng = self.synth_args, self.rng
+        rotations = (2 * a.max_rotation * rng.rand3("aff.rot") - a.max_rotation) / 180.0 * np.pi
+        shears = (2 * a.max_shear * rng.rand3("aff.shear") - a.max_shear)
+        scalings = 1 + (2 * a.max_scaling * rng.rand3("aff.scale") - a.max_scaling)
+        scaling_factor_distances = np.prod(scalings) ** .33333333333
+        A = torch.tensor(make_affine_matrix(rotations, shears, scalings), dtype=torch.float)
+        c2 = torch.tensor((np.array(shp[0:3]) - 1) / 2, dtype=torch.float)
+        if a.random_shift:
+            max_shift = torch.tensor(np.array(shp[0:3]) - self.size, dtype=torch.float) / 2
+            max_shift[max_shift < 0] = 0
+            c2 = c2 + (2 * (max_shift * rng.torch_rand("aff.shift", 3, dtype=torch.float64)) - max_shift)
+        return scaling_factor_distances, A, c2
+
+    def random_nonlinear_transform(self, photo_mode, spac):
+        """Returns the SMALL random grid (host float32, [sx,sy,sz,3]); the full-resolution field F is never
+        materialised unless somebody reads deform_dict['F'] or the SVF integration is requested."""
+        a, rng = self.synth_args, self.rng
+        nonlin_scale = a.nonlin_scale_min + rng.rand1("nl.scale") * (a.nonlin_scale_max - a.nonlin_scale_min)
+        size_F_small = np.round(nonlin_scale * np.array(self.size)).astype(int).tolist()
+        if photo_mode:
+            size_F_small[1] = np.round(self.size[1] / spac).astype(int)
+        nonlin_std = a.nonlin_std_max * rng.rand("nl.std")
+        Fsmall = nonlin_std * rng.torch_randn("nl.field", [*size_F_small, 3])
+        return Fsmall
+
+    def _full_field(self, Fsmall, photo_mode):
+        F = myzoom_torch(Fsmall.to(self.device), np.array(self.size) / np.array(Fsmall.shape[:3]))
+        if photo_mode:
+            F[:, :, :, 1] = 0
+        return F
+
+    def _integrate_svf(self, F):
+        n = self.synth_args.n_steps_svf_integration
+        L = _lib.lib()
+        cur = (F * (1.0 / (2.0 ** n))).contiguous()
+        nxt = torch.empty_like(cur)
+        for _ in range(n):
+            _lib.check(L.bfm_svf_step(cur.data_ptr(), nxt.data_ptr(), *self.size, _stream()))
+            cur, nxt = nxt, cur
+        return cur
+
+    def generate_deformation(self, setups, shp):
+        scaling_factor_distances, A, c2 = self.random_affine_transform(shp)
+        Fsmall, F, Fneg = None, None, None
+        if self.synth_args.nonlinear_transform:
+            Fsmall = self.random_nonlinear_transform(setups['photo_mode'], setups['spac'])
+            if 'surface' in self.tasks:
+                full = self._full_field(Fsmall, setups['photo_mode'])
+                F, Fneg = self._integrate_svf(full), self._integrate_svf(-full)
+        plan = DeformPlan(self.size, shp, A.numpy(), c2.to(torch.float32).numpy(),
+                          None if (Fsmall is None or F is not None) else Fsmall.numpy(), setups['photo_mode'],
+                          self.device, F_full=F)
+        d = DeformDict({'scaling_factor_distances': scaling_factor_distances, 'A': A.to(self.device),
+                        'c2': c2.to(self.device), 'Fneg': Fneg, '_plan': plan, '_Fsmall': Fsmall})
+        if F is not None or Fsmall is None:
+            d['F'] = F
+        return d
+
+    def deform_grid(self, shp, A, c2, F):
+        """Reference-shaped entry point (datasets.py:264-303): F is a full-resolution field or None."""
+        plan = DeformPlan(self.size, shp, A.detach().cpu().numpy(), c2.detach().cpu().float().numpy(), None, False,
+                          self.device, F_full=None if F is None else F.contiguous().float())
+        xx2, yy2, zz2 = plan.coords()
+        return (xx2, yy2, zz2, *plan.bbox_host())
+
+    def get_left_hemis_mask(self, grid):
+        if self.synth_args.left_hemis_only:
+            raise NotImplementedError("left_hemis_only is not supported")
+        self.hemis_mask = None
+
+    # ---- targets (datasets.py:593-631) -------------------------------------------------------------
+    def read_and_deform_target(self, idx, exist_keys, task_name, input_mode, setups, deform_dict, linear_weights=None):
+        if task_name == 'pathology':
+            p_prob_path, augment, thres = None, False, 0.1
+            if self.pathology_type is None and setups['pathol_mode']:
+                if setups['pathol_random_shape']:
+                    p_prob_path, augment, thres = 'random_shape', False, self.shape_gen_args.pathol_thres
+                else:
+                    p_prob_path = self.rng.choice("pathol.path", K.pathology_prob_paths)
+                    augment, thres = self.synth_args.augment_pathology, self.shape_gen_args.pathol_thres
+            return K.processing_funcs[task_name](exist_keys, task_name, p_prob_path, setups, deform_dict, self.device,
+                                                 mask=self.hemis_mask, augment=augment, pde_func=self.adv_pde,
+                                                 t=self.t, shape_gen_args=self.shape_gen_args, thres=thres,
+                                                 draws=self.rng)
+        if task_name in self.modalities:
+            return K.processing_funcs[task_name](exist_keys, task_name, self.modalities[task_name], setups,
+                                                 deform_dict, self.device, mask=self.hemis_mask, cfg=self.gen_args,
+                                                 onehotmatrix=self.onehotmatrix, lut=self.lut, vflip=self.vflip)
+        return {task_name: 0.}
+
+    def update_gen_args(self, new_args):
+        for key, value in vars(new_args).items():
+            vars(self.gen_args.generator)[key] = value
+
+    # ---- contrast (datasets.py:430-464) ------------------------------------------------------------
+    def get_contrast(self, photo_mode):
+        rng = self.rng
+        mus = 25 + 200 * rng.torch_rand("gmm.mu", 256)
+        sigmas = 5 + 20 * rng.torch_rand("gmm.sigma", 256)
+        if rng.rand("gmm.ct") < self.synth_args.ct_prob:
+            for name, (base, span) in (('darker', (25, 10)), ('dark', (90, 20)), ('bright', (110, 20)),
+                                       ('brighter', (150, 50))):
+                v = base + span * rng.torch_rand("gmm.ct." + name, 1)[0]
+                for l in ct_brightness_group[name]:
+                    mus[l] = v
+        if photo_mode or rng.rand1("gmm.bg") < 0.5:
+            mus[0] = 0
+        v = 0.02 * torch.arange(50)
+        mus[100:150] = mus[1] * (1 - v) + mus[2] * v
+        mus[150:200] = mus[2] * (1 - v) + mus[3] * v
+        mus[200:250] = mus[3] * (1 - v) + mus[4] * v
+        mus[250] = mus[4]
+        sigmas[100:150] = torch.sqrt(sigmas[1] ** 2 * (1 - v) + sigmas[2] ** 2 * v)
+        sigmas[150:200] = torch.sqrt(sigmas[2] ** 2 * (1 - v) + sigmas[3] ** 2 * v)
+        sigmas[200:250] = torch.sqrt(sigmas[3] ** 2 * (1 - v) + sigmas[4] ** 2 * v)
+        sigmas[250] = sigmas[4]
+        return mus, sigmas
+
+    # ---- host-side plan of one synthetic sample (all scalar draws, reference order) ----------------
+    def _stock_chain(self, input_mode):
+        steps = self.augmentation_steps['synth'] if input_mode == 'synth' else self.augmentation_steps['real']
+        return (list(steps) == _STOCK_STEPS and all(K.augmentation_funcs.get(k) is K._STOCK_AUGMENTATION[k]
+                                                    for k in _STOCK_STEPS)
+                and not self.synth_args.bspline_zooming)
+
+    def _plan_synth(self, setups, target):
+        """Draws of generate_sample + the stock augmentation chain, in the reference's order
+        (datasets.py:357-428, utils.py:568-638)."""
+        cfg, rng, size = self.gen_args.generator, self.rng, self.size
+        p = {}
+        p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'])
+        p['eps_gmm'] = rng.field_randn("gmm.eps")
+        p['mix'] = None
+        if rng.rand("mix.u") < self.gen_args.mix_synth_prob:
+            v = rng.torch_rand("mix.v", 4)
+            v[2] = 0 if 'T2' not in self.modalities else v[2]
+            v[3] = 0 if 'FLAIR' not in self.modalities else v[3]
+            v /= torch.sum(v)
+            p['mix'] = v
+        # gamma
+        p['gamma'] = np.float32(np.exp(cfg.gamma_std * rng.randn1("gamma.n")))
+        # bias field
+        bf_scale = cfg.bf_scale_min + rng.rand1("bf.scale") * (cfg.bf_scale_max - cfg.bf_scale_min)
+        small = np.round(bf_scale * np.array(size)).astype(int).tolist()
+        if setups['photo_mode']:
+            small[1] = int(np.round(size[1] / setups['spac']))
+        std = torch.tensor(cfg.bf_std_min + (cfg.bf_std_max - cfg.bf_std_min) * rng.rand1("bf.std"), dtype=torch.float)
+        p['bfsmall'] = (std * rng.torch_randn("bf.field", small)).numpy()
+        # resample
+        res = self.res_training_data
+        stds = (0.85 + 0.3 * rng.rand("rs.u")) * np.log(5) / np.pi * setups['thickness'] / res
+        stds[setups['thickness'] <= res] = 0.0
+        p['stds'] = stds
+        p['new_size'] = (np.array(size) * res / setups['resolution']).astype(int)
+        p['factors'] = np.array(p['new_size']) / np.array(size)
+        # noise
+        u = rng.rand1("noise.u")
+        p['noise_std'] = np.float32(torch.tensor(cfg.noise_std_min + (cfg.noise_std_max - cfg.noise_std_min) * u,
+                                                 dtype=torch.float)[0].item())
+        p['eps_noise'] = rng.field_randn("noise.eps")
+        p['seed'] = rng.seed64()
+        return p
+
+    # ---- fused batched launch ----------------------------------------------------------------------
+    def _run_chain(self, jobs):
+        """jobs: list of dicts(plan=DeformPlan, flip, labels, p=<_plan_synth>, mix_targets, want_bflog,
+        want_residual).  Returns a list of sample dicts."""
+        B = len(jobs)
+        L = _lib.lib()
+        dev = self.device
+        size = self.size
+        N = int(np.prod(size))
+        arena = self.arena.begin()
+        descs = (_lib.GenSample * B)()
+        out = torch.empty((B, 1, *size), dtype=torch.float32, device=dev)
+        i_bf = torch.empty((B, *size), dtype=torch.float32, device=dev)
+        tmp = torch.empty((B, 2, N), dtype=torch.float32, device=dev)
+        keep = [out, i_bf, tmp]
+        results = []
+        for b, job in enumerate(jobs):
+            s, p, plan = descs[b], job['p'], job['plan']
+            s.d = plan.struct
+            lab = job['labels']
+            s.labels = lab.data_ptr()
+            s.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
+            s.mu = arena.put(p['mu'].numpy().astype(np.float32))
+            s.sigma = arena.put(p['sigma'].numpy().astype(np.float32))
+            if p['eps_gmm'] is not None:
+                e = p['eps_gmm'].to(dev).contiguous()
+                keep.append(e)
+                s.eps_gmm = e.data_ptr()
+            s.seed = int(p['seed'])
+            syn = job.get('syn')
+            if syn is None:
+                syn = torch.empty(plan.src, dtype=torch.float32, device=dev)
+            keep.append(syn)
+            s.syn = syn.data_ptr()
+            s.bbox = plan.bbox.data_ptr()
+            if p['mix'] is not None:
+                v = p['mix']
+                mt = job['mix_targets']
+                for q in range(4):
+                    s.mixw[q] = float(v[q])
+                for q, t in enumerate(mt):
+                    if t is not None:
+                        keep.append(t)
+                        s.mix[q] = t.data_ptr()
+            s.gamma = float(p['gamma'])
+            bfs = p['bfsmall']
+            s.bfsmall = arena.put(bfs.astype(np.float32))
+            for a in range(3):
+                s.bs[a] = int(bfs.shape[a])
+            fac = np.array(size) / np.array(bfs.shape)
+            assert tuple(zoom_newsize(bfs.shape, fac)) == tuple(size)
+            fill_zoom_tab(s.btab, arena, [zoom_tables_host(bfs.shape[a], fac[a], size[a]) for a in range(3)])
+            s.i_bf = i_bf[b].data_ptr()
+            sample = {}
+            if job['want_bflog']:
+                bfl = torch.empty((1, *size), dtype=torch.float32, device=dev)
+                s.bflog_out = bfl.data_ptr()
+                sample['bias_field_log'] = bfl
+            s.flip = 1 if job['flip'] else 0
+            # resolution degradation: banded passes in ascending factor order, identity axes folded away
+            new = [int(v) for v in p['new_size']]
+            order = sorted(range(3), key=lambda a: new[a] / size[a])
+            nb = 0
+            for a in order:
+                if new[a] == size[a] and p['stds'][a] == 0:
+                    s.zero_first[a] = 1
+                    continue
+                start, w, T = band_host(size[a], new[a], float(p['stds'][a]))
+                bd = s.band[nb]
+                bd.start, bd.w, bd.T = arena.put(start), arena.put(w), T
+                bd.n_in, bd.n_out, bd.axis = size[a], new[a], a
+                nb += 1
+            if nb == 0:
+                bd = s.band[0]
+                bd.start = arena.put(np.arange(size[2], dtype=np.int32))
+                bd.w = arena.put(np.ones(size[2], dtype=np.float32))
+                bd.T, bd.n_in, bd.n_out, bd.axis = 1, size[2], size[2], 2
+                nb = 1
+            s.n_band = nb
+            s.noise_std = float(p['noise_std'])
+            if p['eps_noise'] is not None:
+                e = p['eps_noise'].to(dev).contiguous()
+                keep.append(e)
+                s.eps_noise = e.data_ptr()
+            s.tmp[0] = tmp[b, 0].data_ptr()
+            s.tmp[1] = tmp[b, 1].data_ptr()
+            low = torch.empty(new, dtype=torch.float32, device=dev)
+            keep.append(low)
+            s.lowres = low.data_ptr()
+            for a in range(3):
+                s.new_size[a] = new[a]
+            up = 1 / p['factors']
+            assert tuple(zoom_newsize(new, up)) == tuple(size), (new, up)
+            fill_zoom_tab(s.utab, arena, [zoom_tables_host(new[a], up[a], size[a]) for a in range(3)])
+            s.maxval, _ = arena.reserve(16)
+            s.out = out[b].data_ptr()
+            if job['want_residual']:
+                r = torch.empty((1, *size), dtype=torch.float32, device=dev)
+                s.residual = r.data_ptr()
+                sample['high_res_residual'] = r
+            sample['input'] = out[b]
+            job['_lowres'] = low
+            job['_i_bf'] = i_bf[b]
+            results.append(sample)
+        d_dev = arena.put_struct_array(descs)
+        arena.commit()
+        _lib.check(L.bfm_gen_run(C.addressof(descs), d_dev, B, _stream()))
+        arena.mark_done()
+        self._keep = keep
+        # key order of the reference's sample dict (datasets.py:345-352)
+        ordered = []
+        for smp in results:
+            o = {}
+            for k in ('high_res_residual', 'input', 'bias_field_log'):
+                if k in smp:
+                    o[k] = smp[k]
+            ordered.append(o)
+        return ordered
+
+    def _labels(self):
+        return self.cache.get(self.modalities['Gen'], 'gen')
+
+    def _want_bflog(self, input_mode):
+        if self.write_bflog is not None:
+            return bool(self.write_bflog)
+        return 'bias_field' in self.tasks and input_mode != 'CT'
+
+    def _job(self, setups, deform_dict, target, p):
+        mt = None
+        if p['mix'] is not None:
+            mt = [target['T1'][0].contiguous(),
+                  target['T2'][0].contiguous() if 'T2' in self.modalities else None,
+                  target['FLAIR'][0].contiguous() if 'FLAIR' in self.modalities else None]
+        return dict(plan=deform_dict['_plan'], flip=setups['flip'], labels=self._labels(), p=p, mix_targets=mt,
+                    want_bflog=self._want_bflog('synth'), want_residual='super_resolution' in self.tasks)
+
+    # ---- reference-shaped sample generation ---------------------------------------------------------
+    def generate_sample(self, name, G, setups, deform_dict, res, target):
+        """GMM synthesis + augmentation of one sample (datasets.py:357-428)."""
+        if not self._stock_chain('synth'):
+            return self._generate_sample_opwise(setups, deform_dict, res, target)
+        p = self._plan_synth(setups, target)
+        sample = self._run_chain([self._job(setups, deform_dict, target, p)])[0]
+        target['pathology'] = 0.
+        target['pathology_prob'] = 0.
+        return target['pathology'], target['pathology_prob'], sample
+
+    def _generate_sample_opwise(self, setups, deform_dict, res, target):
+        """Op-by-op path through the registries (custom or reordered augmentation steps)."""
+        rng = self.rng
+        mus, sigmas = self.get_contrast(setups['photo_mode'])
+        xx2, yy2, zz2, x1, y1, z1, x2, y2, z2 = deform_dict['grid']
+        G = self._labels()[x1:x2, y1:y2, z1:z2].float()
+        G[G == 77] = 2
+        Gr = torch.round(G).long()
+        eps = rng.field_randn("gmm.eps")
+        eps = torch.randn(Gr.shape, dtype=torch.float, device=self.device) if eps is None else eps.to(self.device)
+        SYN = mus.to(self.device)[Gr] + sigmas.to(self.device)[Gr] * eps
+        SYN[SYN < 0] = 0
+        SYN = fast_3D_interp_torch(SYN.contiguous(), xx2, yy2, zz2)
+        if rng.rand("mix.u") < self.gen_args.mix_synth_prob:
+            v = rng.torch_rand("mix.v", 4)
+            v[2] = 0 if 'T2' not in self.modalities else v[2]
+            v[3] = 0 if 'FLAIR' not in self.modalities else v[3]
+            v /= torch.sum(v)
+            SYN = v[0] * SYN + v[1] * target['T1'][0]
+            if 'T2' in self.modalities:
+                SYN += v[2] * target['T2'][0]
+            if 'FLAIR' in self.modalities:
+                SYN += v[3] * target['FLAIR'][0]
+        target['pathology'] = 0.
+        target['pathology_prob'] = 0.
+        SYN[SYN < 0.] = 0.
+        return target['pathology'], target['pathology_prob'], self.augment_sample(None, SYN, setups, deform_dict, res,
+                                                                                  target)
+
+    def augment_sample(self, name, I_def, setups, deform_dict, res, target, pathol_direction=None, input_mode='synth'):
+        """Augmentation of an already deformed image through the operator registry (datasets.py:306-354)."""
+        sample = {}
+        if not isinstance(I_def, torch.Tensor):
+            raise NotImplementedError("real-image inputs go through read_and_deform; pass a deformed tensor")
+        if input_mode == 'CT':
+            I_def = torch.clamp(I_def, min=0., max=80.)
+        target['pathology'] = 0.
+        target['pathology_prob'] = 0.
+        aux_dict = {}
+        steps = self.augmentation_steps['synth'] if input_mode == 'synth' else self.augmentation_steps['real']
+        for func_name in steps:
+            I_def, aux_dict = K.augmentation_funcs[func_name](I=I_def, aux_dict=aux_dict, cfg=self.gen_args.generator,
+                                                             input_mode=input_mode, setups=setups, size=self.size,
+                                                             res=res, device=self.device, draws=self.rng)
+        if self.synth_args.bspline_zooming:
+            from .. import interpol
+            I_def = interpol.resize(I_def, shape=self.size, anchor='edge', interpolation=3, bound='dct2',
+                                    prefilter=True)
+        else:
+            I_def = myzoom_torch(I_def, 1 / aux_dict['factors'])
+        maxi = torch.max(I_def)
+        I_final = I_def / maxi
+        flip = setups['flip']
+        if 'super_resolution' in self.tasks:
+            SRresidual = aux_dict['high_res'] / maxi - I_final
+            sample.update({'high_res_residual': torch.flip(SRresidual, [0])[None] if flip else SRresidual[None]})
+        sample.update({'input': torch.flip(I_final, [0])[None] if flip else I_final[None]})
+        if 'bias_field' in self.tasks and input_mode != 'CT':
+            sample.update({'bias_field_log': torch.flip(aux_dict['BFlog'], [0])[None] if flip else aux_dict['BFlog'][None]})
+        return sample
+
+    def get_pathology_direction(self, input_mode, pathol_direction=None):
+        if pathol_direction is not None:
+            return pathol_direction
+        if input_mode in ['T1', 'CT']:
+            return False
+        if input_mode in ['T2', 'FLAIR']:
+            return True
+        return self.rng.choice("pathol.dir", [True, False])
+
+    # ---- __getitem__ (datasets.py:638-681) ----------------------------------------------------------
+    def _prologue(self, idx, default):
+        if torch.is_tensor(idx):
+            idx = idx.tolist()
+        dataset_name, case_name, input_mode, img, aff, res, age = self.read_input(idx)
+        setups = self.get_setup_params()
+        deform_dict = self.generate_deformation(setups, img.shape)
+        self.get_left_hemis_mask(None)
+        target = defaultdict(default)
+        target['name'] = case_name
+        for key in ('T1', 'T2', 'FLAIR'):
+            target.update(self.read_and_deform_target(idx, target.keys(), key, input_mode, setups, deform_dict))
+        for task_name in self.tasks:
+            if task_name in K.processing_funcs.keys() and task_name not in ['T1', 'T2', 'FLAIR']:
+                target.update(self.read_and_deform_target(idx, target.keys(), task_name, input_mode, setups,
+                                                          deform_dict))
+        return dataset_name, case_name, input_mode, img, res, age, setups, deform_dict, target
+
+    def _real_input(self, input_mode, setups, deform_dict, res, target):
+        from .utils import read_and_deform
+        I, _ = read_and_deform(self.modalities[input_mode], torch.float, deform_dict, self.device, None)
+        return self.augment_sample(None, I, setups, deform_dict, res, target,
+                                   pathol_direction=self.get_pathology_direction(input_mode), input_mode=input_mode)
+
+    def __getitem__(self, idx):
+        dataset_name, case_name, input_mode, img, res, age, setups, deform_dict, target = \
+            self._prologue(idx, lambda: None)
+        if input_mode == 'synth':
+            self.update_gen_args(self.synth_image_args)
+            target['pathology'], target['pathology_prob'], sample = \
+                self.generate_sample(case_name, img, setups, deform_dict, res, target)
+        else:
+            self.update_gen_args(self.real_image_args)
+            sample = self._real_input(input_mode, setups, deform_dict, res, target)
+        if setups['flip'] and isinstance(target['pathology'], torch.Tensor):
+            target['pathology'] = torch.flip(target['pathology'], [1])
+            target['pathology_prob'] = torch.flip(target['pathology_prob'], [1])
+        if age is not None:
+            target['age'] = age
+        self.last_setups, self.last_deform = setups, deform_dict
+        return self.datasets_num, dataset_name, input_mode, target, sample
+
+
+class BrainIDGen(BaseGen):
+    """Intra-subject augmentation: one deformation, `all_samples` contrasts; the first `mild_samples` use
+    mild_generator parameters, the rest severe_generator (Generator/datasets.py:687-757).  All samples of one
+    item run as ONE batched launch of the fused chain."""
+
+    def __init__(self, gen_args, device='cuda', draws=None):
+        super(BrainIDGen, self).__init__(gen_args, device, draws)
+        self.all_samples = gen_args.generator.all_samples
+        self.mild_samples = gen_args.generator.mild_samples
+        self.mild_generator_args = gen_args.mild_generator
+        self.severe_generator_args = gen_args.severe_generator
+
+    def __getitem__(self, idx):
+        dataset_name, case_name, input_mode, img, res, age, setups, deform_dict, target = \
+            self._prologue(idx, lambda: 1.)
+        samples, jobs = [], []
+        for i_sample in range(self.all_samples):
+            self.update_gen_args(self.mild_generator_args if i_sample < self.mild_samples
+                                 else self.severe_generator_args)
+            if input_mode == 'synth':
+                self.update_gen_args(self.synth_image_args)
+                if self._stock_chain('synth'):
+                    jobs.append(self._job(setups, deform_dict, target, self._plan_synth(setups, target)))
+                else:
+                    samples.append(self.generate_sample(case_name, img, setups, deform_dict, res, target)[2])
+            else:
+                self.update_gen_args(self.real_image_args)
+                samples.append(self._real_input(input_mode, setups, deform_dict, res, target))
+        if jobs:
+            samples = self._run_chain(jobs)
+            target['pathology'] = 0.
+            target['pathology_prob'] = 0.
+        if setups['flip'] and isinstance(target['pathology'], torch.Tensor):
+            target['pathology'] = torch.flip(target['pathology'], [1])
+            target['pathology_prob'] = torch.flip(target['pathology_prob'], [1])
+        if age is not None:
+            target['age'] = age
+        self.last_setups, self.last_deform = setups, deform_dict
+        return self.datasets_num, dataset_name, input_mode, target, samples

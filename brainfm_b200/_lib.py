@@ -1,0 +1,107 @@
+"""ctypes binding of libbfm.so (include/bfm.h).  There is NO fallback: if the CUDA library is missing
+or fails to load, importing a compute entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbfm.so")
+
+BFM_OK, BFM_E_INVALID, BFM_E_UNSUPPORTED, BFM_E_CUDA = 0, -1, -2, -3
+
+c_f = C.c_float
+c_i = C.c_int
+c_p = C.c_void_p
+c_i64 = C.c_int64
+c_u64 = C.c_uint64
+
+
+class ZoomTab(C.Structure):
+    _fields_ = [("lo", c_p * 3), ("hi", c_p * 3), ("wl", c_p * 3), ("wh", c_p * 3)]
+
+
+class Deform(C.Structure):
+    _fields_ = [("size", c_i * 3), ("src", c_i * 3), ("A", c_f * 9), ("c2", c_f * 3), ("ctr", c_f * 3),
+                ("fsmall", c_p), ("fs", c_i * 3), ("photo", c_i), ("ftab", ZoomTab), ("F_full", c_p)]
+
+
+class Band(C.Structure):
+    _fields_ = [("start", c_p), ("w", c_p), ("T", c_i), ("n_in", c_i), ("n_out", c_i), ("axis", c_i)]
+
+
+class GenSample(C.Structure):
+    _fields_ = [("d", Deform),
+                ("labels", c_p), ("label_is_u8", c_i), ("mu", c_p), ("sigma", c_p), ("eps_gmm", c_p),
+                ("seed", c_u64), ("syn", c_p), ("bbox", c_p),
+                ("mix", c_p * 3), ("mixw", c_f * 4),
+                ("gamma", c_f), ("bfsmall", c_p), ("bs", c_i * 3), ("btab", ZoomTab),
+                ("i_bf", c_p), ("bflog_out", c_p), ("flip", c_i),
+                ("band", Band * 3), ("n_band", c_i), ("zero_first", c_i * 3),
+                ("noise_std", c_f), ("eps_noise", c_p), ("tmp", c_p * 2), ("lowres", c_p), ("new_size", c_i * 3),
+                ("utab", ZoomTab), ("maxval", c_p), ("out", c_p), ("residual", c_p)]
+
+
+class BfmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_PROTOS = {
+    "bfm_abi_version": (c_i, []),
+    "bfm_last_error": (C.c_char_p, []),
+    "bfm_launch_count": (c_u64, []),
+    "bfm_trilerp_pull": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i64, c_f, c_p, c_p, c_p]),
+    "bfm_nearest_pull": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    "bfm_zoom_linear": (c_i, [c_p, c_i, c_i, c_i, c_i] + [c_p, c_p, c_p, c_p, c_i] * 3 + [c_p, c_p]),
+    "bfm_blur_axis": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    "bfm_band_axis": (c_i, [c_p, c_p, C.POINTER(c_i), c_i, c_i, c_p, c_p, c_i, c_f, c_p, c_u64, c_p]),
+    "bfm_minmax": (c_i, [c_p, c_i64, c_p, c_p]),
+    "bfm_shift_scale_flip": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p, c_f, c_i, c_p]),
+    "bfm_deform_grid": (c_i, [C.POINTER(Deform), c_p, c_p, c_p]),
+    "bfm_warp_volume": (c_i, [C.POINTER(Deform), c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
+    "bfm_label_warp_onehot": (c_i, [C.POINTER(Deform), c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
+    "bfm_svf_step": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "bfm_gen_bbox": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_gen_gmm": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_gen_warp": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_gen_resample": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_gen_finish": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_gen_run": (c_i, [c_p, c_p, c_i, c_p]),
+}
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def lib():
+    """The loaded library; raises BfmError when it has not been built (python -m brainfm_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BfmError("libbfm.so not found at %s -- build it with `python -m brainfm_b200.build`; "
+                           "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.bfm_abi_version() != 1:
+            raise BfmError("libbfm.so ABI mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc == BFM_OK:
+        return
+    msg = lib().bfm_last_error().decode("utf-8", "replace")
+    if rc == BFM_E_INVALID:
+        raise ValueError(msg)
+    if rc == BFM_E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise BfmError("libbfm: %s (code %d)" % (msg, rc))
+
+
+def launch_count():
+    return int(lib().bfm_launch_count())

@@ -1,0 +1,98 @@
+"""Random-draw sources of the generator.
+
+The reference draws from three global generators (numpy, python `random`, torch) in a fixed order
+(SURVEY.md 8a "RNG draw inventory").  Every draw site of this package goes through one of the two
+classes below so that the order is explicit and the draws can be injected:
+
+  HostDraws    -- production: the same global generators, called in the same order as the reference for
+                  every scalar / small tensor; the two volume-sized normal fields (GMM eps, noise eps)
+                  are NOT materialised: they are generated in-kernel by Philox4x32-10 keyed on a
+                  per-sample seed.
+  ReplayDraws  -- parity tests: replays a recorded list of (tag, value) pairs (the oracle's log),
+                  checking the tag of every draw, so any divergence in draw order fails loudly.
+"""
+import random as _pyrandom
+
+import numpy as np
+import torch
+
+
+class HostDraws:
+    replay = False
+
+    def rand(self, tag):
+        return np.random.rand()
+
+    def rand1(self, tag):
+        return np.random.rand(1)
+
+    def rand3(self, tag):
+        return np.random.rand(3)
+
+    def randn(self, tag):
+        return np.random.randn()
+
+    def randn1(self, tag):
+        return np.random.randn(1)[0]
+
+    def randint(self, tag, n):
+        return np.random.randint(n)
+
+    def choice(self, tag, seq):
+        return _pyrandom.choice(seq)
+
+    def torch_rand(self, tag, shape, dtype=torch.float32):
+        return torch.rand(shape, dtype=dtype)
+
+    def torch_randn(self, tag, shape):
+        return torch.randn(shape, dtype=torch.float32)
+
+    def field_randn(self, tag, shape=None):
+        """Volume-sized N(0,1) field: None => generated in-kernel (Philox)."""
+        return None
+
+    def seed64(self):
+        return int(np.random.randint(0, 2 ** 62))
+
+
+class ReplayDraws(HostDraws):
+    replay = True
+
+    def __init__(self, log):
+        self.log = list(log)
+        self.pos = 0
+
+    def _next(self, tag):
+        if self.pos >= len(self.log):
+            raise AssertionError("draw log exhausted at %r" % tag)
+        t, v = self.log[self.pos]
+        if t != tag:
+            raise AssertionError("draw order mismatch: wanted %r, log has %r (position %d)" % (tag, t, self.pos))
+        self.pos += 1
+        return v
+
+    def rand(self, tag):
+        return self._next(tag)
+
+    rand1 = rand3 = randn = randn1 = rand
+
+    def randint(self, tag, n):
+        return self._next(tag)
+
+    def choice(self, tag, seq):
+        return self._next(tag)
+
+    def torch_rand(self, tag, shape, dtype=torch.float32):
+        return self._next(tag).clone()
+
+    def torch_randn(self, tag, shape):
+        return self._next(tag).clone()
+
+    def field_randn(self, tag, shape=None):
+        return self._next(tag)
+
+    def seed64(self):
+        return 0
+
+    def done(self):
+        return self.pos == len(self.log)

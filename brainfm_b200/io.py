@@ -1,0 +1,128 @@
+"""Volume access for the generator: an in-memory registry, minimal NIfTI-1 / MGH readers (the reference
+uses nibabel, Generator/utils.py:266-270,300-304), and a device-resident cache so that a volume is decoded
+and uploaded once instead of once per sample."""
+import gzip
+import os
+import struct
+
+import numpy as np
+import torch
+
+_REGISTRY = {}
+
+
+class Volume:
+    """The slice of nibabel's image API the generator touches: .shape, .affine, .get_fdata()."""
+
+    def __init__(self, data, affine=None):
+        self._data = data
+        self.shape = tuple(data.shape)
+        self.affine = np.eye(4) if affine is None else affine
+
+    def get_fdata(self):
+        return np.asarray(self._data, dtype=np.float64)
+
+    @property
+    def dataobj(self):
+        return self._data
+
+
+def register_volume(path, array, affine=None):
+    _REGISTRY[path] = Volume(np.asarray(array), affine)
+
+
+def clear_registry():
+    _REGISTRY.clear()
+
+
+def exists(path):
+    return path in _REGISTRY or os.path.isfile(path)
+
+
+def _read_nifti(path):
+    op = gzip.open if path.endswith(".gz") else open
+    with op(path, "rb") as f:
+        raw = f.read()
+    le = struct.unpack("<i", raw[:4])[0] == 348
+    e = "<" if le else ">"
+    dim = struct.unpack(e + "8h", raw[40:56])
+    datatype = struct.unpack(e + "h", raw[70:72])[0]
+    vox_offset = int(struct.unpack(e + "f", raw[108:112])[0])
+    slope, inter = struct.unpack(e + "2f", raw[112:120])
+    dt = {2: "u1", 4: "i2", 8: "i4", 16: "f4", 64: "f8", 256: "i1", 512: "u2", 768: "u4"}[datatype]
+    shape = dim[1:1 + dim[0]]
+    data = np.frombuffer(raw, dtype=e + dt, count=int(np.prod(shape)), offset=vox_offset).reshape(shape, order="F")
+    if slope not in (0.0, 1.0) or inter != 0.0:
+        if slope != 0.0 and not np.isnan(slope):
+            data = data * slope + inter
+    sform = struct.unpack(e + "h", raw[254:256])[0]
+    aff = np.eye(4)
+    if sform > 0:
+        aff[:3] = np.array(struct.unpack(e + "12f", raw[280:328])).reshape(3, 4)
+    else:
+        pix = struct.unpack(e + "8f", raw[76:108])
+        aff[0, 0], aff[1, 1], aff[2, 2] = pix[1], pix[2], pix[3]
+    return Volume(data, aff)
+
+
+def _read_mgh(path):
+    op = gzip.open if path.endswith("z") else open
+    with op(path, "rb") as f:
+        raw = f.read()
+    _, w, h, d, nf, typ, _ = struct.unpack(">7i", raw[:28])
+    dt = {0: ">u1", 1: ">i4", 3: ">f4", 4: ">i2"}[typ]
+    data = np.frombuffer(raw, dtype=dt, count=w * h * d * nf, offset=284)
+    shape = (w, h, d) if nf == 1 else (w, h, d, nf)
+    return Volume(data.reshape(shape, order="F"))
+
+
+def load(path):
+    """nib.load replacement: registry first, then NIfTI / MGH files (with the reference's '.gz' retry,
+    Generator/utils.py:299-302)."""
+    if path in _REGISTRY:
+        return _REGISTRY[path]
+    for p in (path, path + ".gz"):
+        if os.path.isfile(p):
+            if p.endswith((".mgz", ".mgh")):
+                return _read_mgh(p)
+            return _read_nifti(p)
+    raise FileNotFoundError(path)
+
+
+class DeviceVolumeCache:
+    """path -> device tensor, decoded once.  kinds: 'f32' (images), 'i32' (segmentation labels),
+    'gen' (generation labels: uint8 when every value is an integer in [0,255], else float32)."""
+
+    def __init__(self, device, max_bytes=64 << 30):
+        self.device = device
+        self.max_bytes = max_bytes
+        self._d = {}
+        self._bytes = 0
+
+    def get(self, path, kind="f32"):
+        key = (path, kind)
+        t = self._d.get(key)
+        if t is not None:
+            return t
+        a = load(path).get_fdata()
+        a = np.squeeze(a)
+        if kind == "f32":
+            h = torch.from_numpy(np.ascontiguousarray(a.astype(float))).to(torch.float32)
+        elif kind == "i32":
+            h = torch.from_numpy(np.ascontiguousarray(a.astype(int))).to(torch.int32)
+        elif kind == "gen":
+            f = a.astype(np.float32)
+            if np.all(f == np.round(f)) and f.min() >= 0 and f.max() <= 255:
+                h = torch.from_numpy(np.ascontiguousarray(f.astype(np.uint8)))
+            else:
+                h = torch.from_numpy(np.ascontiguousarray(f))
+        else:
+            raise ValueError(kind)
+        t = h.to(self.device)
+        nbytes = t.numel() * t.element_size()
+        if self._bytes + nbytes > self.max_bytes:
+            self._d.clear()
+            self._bytes = 0
+        self._d[key] = t
+        self._bytes += nbytes
+        return t

@@ -1,0 +1,172 @@
+"""Host-side planning for the CUDA kernels: the per-axis index/weight tables the reference builds with
+float32 `torch.arange` (myzoom_torch, Generator/utils.py:205-236), the banded blur-o-downsample maps of
+resample_resolution (utils.py:74-94, 591-609), and a pinned-host/device arena that ships all of a batch's
+small arrays to the GPU in one asynchronous copy."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_ALIGN = 16
+
+
+def zoom_tables_host(n_in, factor, n_out):
+    """lo, hi (int32), wl, wh (float32) of one axis of myzoom_torch -- computed with the reference's own
+    float32 torch expressions (float32 arange is not float64-then-cast)."""
+    factor = float(factor)
+    delta = (1.0 - factor) / (2.0 * factor)
+    v = torch.arange(delta, delta + n_out / factor, 1 / factor, dtype=torch.float32)[:n_out]
+    v = v.clamp(min=0, max=n_in - 1)
+    lo = torch.floor(v).int()
+    hi = (lo + 1).clamp(max=n_in - 1)
+    wh = v - lo
+    wl = 1 - wh
+    return lo.numpy(), hi.numpy(), wl.numpy(), wh.numpy()
+
+
+def zoom_newsize(shape, factor):
+    return np.round(np.asarray(shape) * np.asarray(factor, dtype=np.float64)).astype(int)
+
+
+def gaussian_taps_host(sigma):
+    """make_gaussian_kernel (utils.py:74-81), same float32 torch expressions."""
+    sl = int(np.ceil(3 * sigma))
+    ts = torch.linspace(-sl, sl, 2 * sl + 1, dtype=torch.float32)
+    g = torch.exp((-(ts / sigma) ** 2 / 2))
+    return (g / g.sum()).numpy(), sl
+
+
+def resample_coords_host(n_in, n_out):
+    """Low-res sample positions along one axis: float64 np.arange then float32 (utils.py:595-605)."""
+    f = n_out / n_in
+    delta = (1.0 - f) / (2.0 * f)
+    return np.arange(delta, delta + n_out / f, 1 / f)[:n_out].astype(np.float32), f
+
+
+def band_host(n_in, n_out, sigma):
+    """Banded matrix of (zero-padded Gaussian correlation) followed by (masked 2-tap linear sampling)
+    along one axis.  Returns start[n_out] int32, w[n_out, T] float32, T."""
+    v, _ = resample_coords_host(n_in, n_out)
+    ok = (v > 0) & (v <= np.float32(n_in - 1))
+    fx = np.floor(v)
+    lo = fx.astype(np.int64)
+    hi = np.minimum(lo + 1, n_in - 1)
+    wh = (v - fx).astype(np.float32)
+    wl = (np.float32(1) - wh).astype(np.float32)
+    if sigma > 0:
+        g, half = gaussian_taps_host(sigma)
+        g = g.astype(np.float64)
+    else:
+        g, half = np.ones(1, dtype=np.float64), 0
+    L = 2 * half + 1
+    T = L + 1
+    W = np.zeros((n_out, T), dtype=np.float64)
+    W[:, :L] += wl.astype(np.float64)[:, None] * g[None, :]
+    shift = (hi - lo).astype(bool)
+    W[shift, 1:] += wh.astype(np.float64)[shift, None] * g[None, :]
+    W[~shift, :L] += wh.astype(np.float64)[~shift, None] * g[None, :]
+    W[~ok] = 0
+    start = (lo - half).astype(np.int32)
+    return start, W.astype(np.float32), T
+
+
+class Arena:
+    """A ring of pinned-host / device byte buffers.  All small per-batch arrays (tables, LUTs, small random
+    grids, the descriptor array) are packed into the host side and shipped with ONE async copy."""
+
+    def __init__(self, device, capacity=8 << 20, slots=3):
+        self.device = torch.device(device)
+        self.capacity = capacity
+        self.slots = []
+        for _ in range(slots):
+            host = torch.empty(capacity, dtype=torch.uint8).pin_memory()
+            dev = torch.empty(capacity, dtype=torch.uint8, device=self.device)
+            self.slots.append(dict(host=host, dev=dev, np=host.numpy(), event=None))
+        self.cur = -1
+        self.used = 0
+
+    def begin(self):
+        self.cur = (self.cur + 1) % len(self.slots)
+        s = self.slots[self.cur]
+        if s["event"] is not None:
+            s["event"].synchronize()
+        self.used = 0
+        self.base = s["dev"].data_ptr()
+        return self
+
+    def put(self, arr):
+        """Copy a numpy array into the host buffer; returns its DEVICE address."""
+        a = np.ascontiguousarray(arr)
+        n = a.nbytes
+        off = (self.used + _ALIGN - 1) // _ALIGN * _ALIGN
+        if off + n > self.capacity:
+            raise MemoryError("plan arena overflow (%d + %d > %d)" % (off, n, self.capacity))
+        self.slots[self.cur]["np"][off:off + n] = a.view(np.uint8).reshape(-1)
+        self.used = off + n
+        return self.base + off
+
+    def reserve(self, nbytes):
+        """Uninitialised device scratch inside the arena (bbox ints, max scalars); returns (address, offset)."""
+        off = (self.used + _ALIGN - 1) // _ALIGN * _ALIGN
+        if off + nbytes > self.capacity:
+            raise MemoryError("plan arena overflow")
+        self.used = off + nbytes
+        return self.base + off, off
+
+    def put_struct_array(self, arr):
+        n = C.sizeof(arr)
+        off = (self.used + _ALIGN - 1) // _ALIGN * _ALIGN
+        if off + n > self.capacity:
+            raise MemoryError("plan arena overflow")
+        C.memmove(self.slots[self.cur]["host"].data_ptr() + off, C.addressof(arr), n)
+        self.used = off + n
+        return self.base + off
+
+    def commit(self, stream=None):
+        s = self.slots[self.cur]
+        s["dev"][:self.used].copy_(s["host"][:self.used], non_blocking=True)
+
+    def mark_done(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.slots[self.cur]["event"] = ev
+
+    def view(self, off, count, dtype):
+        """Device tensor view of arena bytes [off, off+count*itemsize)."""
+        item = torch.empty((), dtype=dtype).element_size()
+        return self.slots[self.cur]["dev"][off:off + count * item].view(dtype)
+
+
+def fill_zoom_tab(tab, arena, tables):
+    for ax, (lo, hi, wl, wh) in enumerate(tables):
+        tab.lo[ax] = arena.put(lo.astype(np.int32))
+        tab.hi[ax] = arena.put(hi.astype(np.int32))
+        tab.wl[ax] = arena.put(wl.astype(np.float32))
+        tab.wh[ax] = arena.put(wh.astype(np.float32))
+
+
+def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None):
+    """Populate a _lib.Deform from host values (A, c2: float32 arrays as the reference's tensors)."""
+    for a in range(3):
+        d.size[a] = int(size[a])
+        d.src[a] = int(src[a])
+        d.c2[a] = float(np.float32(c2[a]))
+        d.ctr[a] = float(np.float32((size[a] - 1) / 2))
+    Af = np.asarray(A, dtype=np.float32).reshape(-1)
+    for q in range(9):
+        d.A[q] = float(Af[q])
+    d.photo = int(bool(photo))
+    d.F_full = F_full_ptr
+    if fsmall_host is None:
+        d.fsmall = None
+        return
+    fs = fsmall_host.shape[:3]
+    for a in range(3):
+        d.fs[a] = int(fs[a])
+    d.fsmall = arena.put(fsmall_host.astype(np.float32))
+    factor = np.array(size) / np.array(fs)
+    new = zoom_newsize(fs, factor)
+    assert tuple(new) == tuple(size), (new, size)
+    fill_zoom_tab(d.ftab, arena, [zoom_tables_host(fs[a], factor[a], int(new[a])) for a in range(3)])

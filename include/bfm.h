@@ -1,0 +1,196 @@
+/*
+ * libbfm -- C ABI of the B200 (sm_100a) synthetic-data generator kernels.
+ *
+ * Drop-in boundary for the hot path of jhuldr/BrainFM's on-the-fly generator.  The reference is
+ * pure Python/PyTorch and has no FFI of its own; each entry point below replaces the
+ * ATen op-chain of the reference function cited next to it and is bound from Python with ctypes
+ * (brainfm_b200/_lib.py; the binding a reference maintainer would add is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller allocates all outputs; no ownership is transferred; no global state;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous;
+ *   - return value: 0 = OK, negative = BFM_E_*; bfm_last_error() gives a thread-local message;
+ *   - volumes are row-major (X,Y,Z[,C]) with Z (or C) contiguous, like the reference's tensors.
+ */
+#ifndef BFM_H_
+#define BFM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFM_OK 0
+#define BFM_E_INVALID (-1)      /* bad argument (null pointer, non-positive size, unknown enum) */
+#define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
+#define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
+
+#define BFM_ABI_VERSION 1
+
+int bfm_abi_version(void);
+const char *bfm_last_error(void);
+/* number of kernels launched by this library in the calling process since load (bench.py gpu_launches) */
+uint64_t bfm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Op-level entry points (one reference function each)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fast_3D_interp_torch(X, II, JJ, KK, 'linear', default)            Generator/utils.py:140-192
+ * X: (nx,ny,nz,C) f32 channels-last; I,J,K: n coordinates; out: (n,C).
+ * Points failing  I>0 & J>0 & K>0 & I<=nx-1 & J<=ny-1 & K<=nz-1  get default_value.
+ * If default_dev != NULL the default is read from that device scalar (the 'max' mode). */
+int bfm_trilerp_pull(const float *X, int nx, int ny, int nz, int C,
+                     const float *I, const float *J, const float *K, int64_t n,
+                     float default_value, const float *default_dev, float *out, void *stream);
+
+/* fast_3D_interp_torch(X, II, JJ, KK, 'nearest')                    Generator/utils.py:124-138
+ * elem_size 1, 4 or 8 bytes per channel value; round-half-even then clamp; bit-exact gather. */
+int bfm_nearest_pull(const void *X, int elem_size, int nx, int ny, int nz, int C,
+                     const float *I, const float *J, const float *K, int64_t n, void *out, void *stream);
+
+/* myzoom_torch(X, factor)                                            Generator/utils.py:200-257
+ * X: (a,b,c,C) -> out (A,B,Cc,C).  lo/hi/wl/wh: per-axis index/weight tables built by the caller with
+ * the reference's own float32 arange expressions (lengths A, B, Cc).  Evaluated in the reference's
+ * pass order (axis 0, 1, 2) with separately rounded mul/add => bit-exact. */
+int bfm_zoom_linear(const float *X, int a, int b, int c, int C,
+                    const int *lo0, const int *hi0, const float *wl0, const float *wh0, int A,
+                    const int *lo1, const int *hi1, const float *wl1, const float *wh1, int B,
+                    const int *lo2, const int *hi2, const float *wl2, const float *wh2, int Cc,
+                    float *out, void *stream);
+
+/* gaussian_blur_3d: ONE axis of the separable zero-padded correlation   Generator/utils.py:83-94
+ * in/out: (nx,ny,nz) f32; taps: (2*half+1) normalised weights (device). */
+int bfm_blur_axis(const float *in, float *out, int nx, int ny, int nz, int axis,
+                  const float *taps, int half, void *stream);
+
+/* Banded linear map along one axis: out[i'] = sum_t w[i'*T+t] * in[start[i']+t] (taps outside
+ * [0,n) are skipped).  Used for blur o trilinear-downsample (resample_resolution,
+ * Generator/utils.py:591-609) with optional fused add_noise (utils.py:633-638) epilogue:
+ * out = max(0, out + noise_std*eps)  when noise_std >= 0 (eps == NULL => Philox(seed)). */
+int bfm_band_axis(const float *in, float *out, const int *in_shape, int axis, int n_out,
+                  const int *start, const float *w, int T,
+                  float noise_std, const float *eps, uint64_t seed, void *stream);
+
+/* global min / max of a float volume (device results, 2 floats: min, max)  torch.min/torch.max */
+int bfm_minmax(const float *x, int64_t n, float *minmax_dev, void *stream);
+
+/* out = (x - sub[0]) / div[0], optionally flipped along axis 0; sub/div are device scalars (NULL => 0 / 1).
+ * read_and_deform_image normalisation + flip                            Generator/utils.py:326-329 */
+int bfm_shift_scale_flip(const float *x, float *out, int nx, int64_t plane,
+                         const float *sub_dev, const float *div_dev, float post_scale, int flip, void *stream);
+
+/* deform_grid                                                         Generator/datasets.py:264-303
+ * Pass 1 (coords_out == NULL): reduces the clamped source coordinates of every output voxel to the
+ *   bounding box bbox_dev[6] = {lo0,lo1,lo2, hi0,hi1,hi2} (ints, hi exclusive = 1+ceil(max)).
+ * Pass 2 (coords_out != NULL): writes bbox-relative coordinates xx2,yy2,zz2 as 3 planes (3,sx,sy,sz).
+ * F is evaluated on the fly from Fsmall (fs0,fs1,fs2,3) through the myzoom tables; Fsmall == NULL
+ * means no nonlinear field.  F_full (optional, (sx,sy,sz,3)) overrides Fsmall (SVF-integrated field). */
+typedef struct bfm_zoom_tab {
+    const int *lo[3];
+    const int *hi[3];
+    const float *wl[3];
+    const float *wh[3];
+} bfm_zoom_tab;
+
+typedef struct bfm_deform {
+    int size[3];        /* output grid */
+    int src[3];         /* source volume shape */
+    float A[9];         /* row-major affine (float32 like the reference tensor) */
+    float c2[3];
+    float ctr[3];       /* (size-1)/2 in float32 */
+    const float *fsmall; /* (fs0,fs1,fs2,3) or NULL */
+    int fs[3];
+    int photo;          /* zero F[...,1] (datasets.py:211-212) */
+    bfm_zoom_tab ftab;
+    const float *F_full; /* optional full-resolution field (size,3) */
+} bfm_deform;
+
+int bfm_deform_grid(const bfm_deform *d_host, int *bbox_dev, float *coords_out, void *stream);
+
+/* read_and_deform (+ wrappers): trilinear warp of a full source volume through the deformation,
+ * reading only inside the bbox crop                                    Generator/utils.py:296-321
+ * value = nan_to_num(src) -> (v - mean)/scale.  default: 0, or the crop maximum when default_max != 0. */
+int bfm_warp_volume(const bfm_deform *d_host, const int *bbox_dev, const float *src,
+                    float mean, float scale, int default_max, float *scratch_max_dev,
+                    float *out, void *stream);
+
+/* read_and_deform_segmentation                                        Generator/utils.py:394-424
+ * labels: int32 source volume; lut: int32[lut_n]; out: (n_classes, size) f32 one-hot, channel-first,
+ * flipped along axis 0 and channel-permuted by vflip (int32[n_classes]) when flip != 0.
+ * label_out (optional): (size) int32 warped class index (unflipped). */
+int bfm_label_warp_onehot(const bfm_deform *d_host, const int *bbox_dev, const int32_t *labels,
+                          const int32_t *lut, int lut_n, int n_classes, const int32_t *vflip, int flip,
+                          float *onehot_out, int32_t *label_out, void *stream);
+
+/* random_nonlinear_transform SVF integration step                     Generator/datasets.py:214-223
+ * out = Fin + trilerp(Fin, id + Fin)  for a (sx,sy,sz,3) field. */
+int bfm_svf_step(const float *Fin, float *Fout, int sx, int sy, int sz, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused batched synthesis chain:  BaseGen.generate_sample + augment_sample with the stock steps
+ * ['gamma','bias_field','resample','noise']                       Generator/datasets.py:306-428
+ * One descriptor per sample (device-visible array); every launch covers the whole batch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bfm_band {
+    const int *start;   /* n_out */
+    const float *w;     /* n_out * T */
+    int T;
+    int n_in, n_out;
+    int axis;
+} bfm_band;
+
+typedef struct bfm_gen_sample {
+    bfm_deform d;
+    /* labels -> GMM image */
+    const void *labels;     /* full source volume */
+    int label_is_u8;        /* 1: uint8, 0: float32 (G==77 -> 2, round-half-even) */
+    const float *mu;        /* 256 */
+    const float *sigma;     /* 256 */
+    const float *eps_gmm;   /* injected N(0,1) draws shaped like the bbox crop, or NULL => Philox */
+    uint64_t seed;          /* Philox key (per sample) */
+    float *syn;             /* scratch, source-volume sized */
+    int *bbox;              /* 6 ints (device) */
+    /* optional mixing with real modalities (datasets.py:379-388): I = v0*I + v[m]*mix[m] */
+    const float *mix[3];
+    float mixw[4];
+    /* gamma + bias field */
+    float gamma;            /* exp(gamma_std*n), rounded to float32 like the reference pow */
+    const float *bfsmall;   /* (bs0,bs1,bs2) */
+    int bs[3];
+    bfm_zoom_tab btab;
+    float *i_bf;            /* (size) high_res image after bias */
+    float *bflog_out;       /* (size) flipped if flip, or NULL */
+    int flip;
+    /* resolution degradation: up to 3 banded passes, executed in the given order */
+    bfm_band band[3];
+    int n_band;
+    int zero_first[3];      /* strict `>0` mask of identity axes */
+    float noise_std;
+    const float *eps_noise; /* injected, low-res shaped, or NULL => Philox */
+    float *tmp[2];          /* ping-pong scratch, each >= prod(size) floats */
+    float *lowres;          /* (new_size) */
+    int new_size[3];
+    /* back to the training grid + normalise */
+    bfm_zoom_tab utab;      /* tables of myzoom_torch(lowres, 1/factors), lengths size[d] */
+    float *maxval;          /* device scalar */
+    float *out;             /* (size) 'input', flipped if flip */
+    float *residual;        /* optional 'high_res_residual' */
+} bfm_gen_sample;
+
+/* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,
+ * `s_host` the host copy (grid sizing only). */
+int bfm_gen_bbox(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+int bfm_gen_gmm(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+int bfm_gen_warp(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+int bfm_gen_resample(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+int bfm_gen_finish(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+/* all five stages back to back */
+int bfm_gen_run(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFM_H_ */
