@@ -1,0 +1,319 @@
+"""Benchmark of the generator hot path (BASELINE.json configs[1]):
+
+  BaseGen default chain -- GMM intensities + affine/nonlinear deformation + gamma + bias field + resolution
+  degradation (blur, downsample, noise, re-upsample, normalise) + the always-on T1 target warp --
+  batch 8 x 160^3 per step on each GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One JSON line on stdout (rank 0).  `value` = samples/s with all inputs resident in HBM (host-side random
+draws and table planning INCLUDED, overlapped with the GPU through the asynchronous stream); `e2e` = the same
+through the public API with host label/image buffers copied in and the generated volumes copied out every
+step; `roofline` = the dominant kernel (warp+gamma+bias) against the measured HBM peak; `cpu_baseline` = the
+oracle port of the reference's PyTorch-CPU generator on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+SIZE = 160
+BATCH = 8
+METRIC = "synthetic 160^3 samples/sec (BaseGen default chain, batch 8)"
+UNIT = "samples/s"
+
+
+def make_inputs(n_subjects):
+    from tests import _inputs as ti
+    shp = (SIZE, SIZE, SIZE)
+    subs = []
+    for s in range(n_subjects):
+        subs.append(dict(Gen=ti.brain_like_labels(shp, seed=7 + s), T1=ti.smooth_image(shp, 0.1 * s)))
+    return subs
+
+
+def bench_cfg():
+    from tests import _inputs as ti
+    cfg = ti.default_cfg((SIZE,) * 3)
+    for k in vars(cfg.task):
+        setattr(cfg.task, k, False)          # "tasks off": input (+ BFlog written) + the unconditional T1 target
+    return cfg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_generator(subs, threads):
+    from oracle import gen_oracle as go
+    torch.set_num_threads(threads)
+    gens = [go.GeneratorOracle(bench_cfg(), s) for s in subs]
+    return gens
+
+
+def time_oracle(gens, n_samples, seed=0):
+    from oracle import gen_oracle as go
+    go.seed_all(seed)
+    t0 = time.perf_counter()
+    for i in range(n_samples):
+        gens[i % len(gens)].sample()
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    gens = oracle_generator(make_inputs(2), threads)
+    t1 = time_oracle(gens, 1, seed=123)            # page-in / first-touch
+    t1 = time_oracle(gens, 1, seed=124)
+    budget = 150.0
+    per_step = int(max(1, min(BATCH, budget / max(t1, 1e-3) / (args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        time_oracle(gens, per_step)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        time_oracle(gens, per_step, seed=k)
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step / dt
+    sample = "%d of the %d samples of a step (160^3 each), %d steps" % (per_step, BATCH, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict():
+    return {"workload": "configs[1]: BaseGen default chain batch 8x160^3 (GMM + affine/nonlinear deform + gamma + "
+                        "bias + blur/downsample/noise/upsample/normalise + T1 target warp), tasks off, brain-like "
+                        "procedural 160^3 label maps, reference parameter ranges (default.yaml + train/brain_id.yaml)",
+            "batch": BATCH, "size": [SIZE] * 3, "source": [SIZE] * 3,
+            "l2": "working set per step (8 samples x ~100 MB of intermediates) exceeds the 126 MB L2; "
+                  "no explicit flush",
+            "rng": "host scalars: numpy/torch global generators in reference order; volume-sized normal fields: "
+                   "in-kernel Philox4x32-10"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_dataset(subs, device):
+    from brainfm_b200 import io as bio
+    from brainfm_b200.Generator import BaseGen
+    root = tempfile.mkdtemp(prefix="bfm_bench_")
+    names = []
+    for s, v in enumerate(subs):
+        stem = os.path.join(root, "HCP.sub%02d." % s)
+        bio.register_volume(stem + "T1w.nii", v["T1"])
+        bio.register_volume(stem + "generation_labels.nii", v["Gen"])
+        names.append(stem + "T1w.nii")
+    with open(os.path.join(root, "train.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    cfg = bench_cfg()
+    cfg.split_root = root
+    ds = BaseGen(cfg, device)
+    ds.write_bflog = True
+    return ds
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from brainfm_b200 import _lib
+    n_subjects = BATCH
+    subs = make_inputs(n_subjects)
+    ds = build_dataset(subs, device)
+    np.random.seed(1000 + rank)
+    torch.manual_seed(1000 + rank)
+    idxs = list(range(BATCH))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    for _ in range(args.warmup):
+        ds.generate_batch(idxs)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timers = {}
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ds.generate_batch(idxs, timers=timers)
+    e1.record()
+    barrier()
+    host_s = time.perf_counter() - t0
+    launches = _lib.launch_count() - l0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    el = torch.tensor([dev_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    total_ms = float(el.item())
+    value = world * args.steps * BATCH / (total_ms * 1e-3)
+
+    stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
+
+    # ---------------- algorithmic bytes of the dominant kernel (warp+gamma+bias) ----------------
+    # per sample: gather-read of the GMM image over the bbox crop (4*Nc) + write I_bf and BFlog (8*N)
+    N = SIZE ** 3
+    np.random.seed(1000 + rank)
+    torch.manual_seed(1000 + rank)
+    items = ds.generate_batch(idxs)
+    nc = []
+    ns = []
+    for j in ds._last_jobs:
+        bb = j["plan"].bbox_host()
+        nc.append((bb[3] - bb[0]) * (bb[4] - bb[1]) * (bb[5] - bb[2]))
+        ns.append(int(np.prod(j["p"]["new_size"])))
+    nc_mean, ns_mean = float(np.mean(nc)), float(np.mean(ns))
+    peak, peak_src = peaks()
+    warp_bytes = BATCH * (4 * nc_mean + 8 * N)
+    warp_ms = stage_ms.get("warp", float("nan"))
+    achieved = warp_bytes / (warp_ms * 1e-3) / 1e9
+    chain_bytes = 4 * nc_mean + 16 * N + 12 * ns_mean + (4 * nc_mean + 4 * N)      # + the T1 target warp
+    chain_gbs = chain_bytes * value / world / 1e9
+
+    # ---------------- end-to-end arm: host buffers in, host buffers out ----------------
+    from brainfm_b200 import io as bio
+    host_lab = [torch.from_numpy(s["Gen"].astype(np.uint8)).pin_memory() for s in subs]
+    host_t1 = [torch.from_numpy(s["T1"]).pin_memory() for s in subs]
+    host_out = torch.empty((BATCH, 1, SIZE, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_lab) + sum(t.numel() * 4 for t in host_t1)
+    d2h = host_out.numel() * 4
+
+    def e2e_step():
+        for s in range(BATCH):
+            ds.cache.get(ds.names[0][s][:-7] + "generation_labels.nii", "gen").copy_(host_lab[s], non_blocking=True)
+            ds.cache.get(ds.names[0][s], "f32").copy_(host_t1[s], non_blocking=True)
+        its = ds.generate_batch(idxs)
+        for s in range(BATCH):
+            host_out[s].copy_(its[s][4]["input"], non_blocking=True)
+        return its
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    el2 = torch.tensor([f0.elapsed_time(f1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el2, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * BATCH / (float(el2.item()) * 1e-3)
+
+    # ---------------- CPU baseline (oracle port), rank 0 at N=1 only ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        gens = oracle_generator(subs[:2], threads)
+        time_oracle(gens, 1, seed=5)
+        n = 12
+        dt = time_oracle(gens, n, seed=6)
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d samples of 160^3 (same label maps, same parameter ranges), torch %d threads" % (n, threads)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
+                "roofline": {"bound": "hbm", "kernel": "k_gen_warp (gather + gamma + bias, batch 8)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": warp_ms},
+                "chain": {"algorithmic_bytes_per_sample": chain_bytes, "achieved_gbs": chain_gbs,
+                          "frac_of_peak": chain_gbs / peak, "nc_over_n": nc_mean / N, "ns_over_n": ns_mean / N,
+                          "stage_ms_per_step": stage_ms, "host_wall_ms_per_step": 1e3 * host_s / args.steps},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -235,7 +235,7 @@ class BaseGen(Dataset):
             cur, nxt = nxt, cur
         return cur
 
-    def generate_deformation(self, setups, shp):
+    def generate_deformation(self, setups, shp, arena=None, lazy=False):
         scaling_factor_distances, A, c2 = self.random_affine_transform(shp)
         Fsmall, F, Fneg = None, None, None
         if self.synth_args.nonlinear_transform:
@@ -245,7 +245,7 @@ class BaseGen(Dataset):
                 F, Fneg = self._integrate_svf(full), self._integrate_svf(-full)
         plan = DeformPlan(self.size, shp, A.numpy(), c2.to(torch.float32).numpy(),
                           None if (Fsmall is None or F is not None) else Fsmall.numpy(), setups['photo_mode'],
-                          self.device, F_full=F)
+                          self.device, F_full=F, arena=arena, lazy=lazy)
         d = DeformDict({'scaling_factor_distances': scaling_factor_distances, 'A': A.to(self.device),
                         'c2': c2.to(self.device), 'Fneg': Fneg, '_plan': plan, '_Fsmall': Fsmall})
         if F is not None or Fsmall is None:
@@ -358,15 +358,12 @@ class BaseGen(Dataset):
         return p
 
     # ---- fused batched launch ----------------------------------------------------------------------
-    def _run_chain(self, jobs):
-        """jobs: list of dicts(plan=DeformPlan, flip, labels, p=<_plan_synth>, mix_targets, want_bflog,
-        want_residual).  Returns a list of sample dicts."""
+    def _build_descs(self, jobs, arena):
+        """Fill one bfm_gen_sample per job (tables and small grids go into the arena).
+        jobs: dicts(plan=DeformPlan, flip, labels, p=<_plan_synth>, want_bflog, want_residual)."""
         B = len(jobs)
-        L = _lib.lib()
-        dev = self.device
-        size = self.size
+        dev, size = self.device, self.size
         N = int(np.prod(size))
-        arena = self.arena.begin()
         descs = (_lib.GenSample * B)()
         out = torch.empty((B, 1, *size), dtype=torch.float32, device=dev)
         i_bf = torch.empty((B, *size), dtype=torch.float32, device=dev)
@@ -386,21 +383,13 @@ class BaseGen(Dataset):
                 keep.append(e)
                 s.eps_gmm = e.data_ptr()
             s.seed = int(p['seed'])
-            syn = job.get('syn')
-            if syn is None:
-                syn = torch.empty(plan.src, dtype=torch.float32, device=dev)
+            syn = torch.empty(plan.src, dtype=torch.float32, device=dev)
             keep.append(syn)
             s.syn = syn.data_ptr()
             s.bbox = plan.bbox.data_ptr()
             if p['mix'] is not None:
-                v = p['mix']
-                mt = job['mix_targets']
                 for q in range(4):
-                    s.mixw[q] = float(v[q])
-                for q, t in enumerate(mt):
-                    if t is not None:
-                        keep.append(t)
-                        s.mix[q] = t.data_ptr()
+                    s.mixw[q] = float(p['mix'][q])
             s.gamma = float(p['gamma'])
             bfs = p['bfsmall']
             s.bfsmall = arena.put(bfs.astype(np.float32))
@@ -458,23 +447,64 @@ class BaseGen(Dataset):
                 s.residual = r.data_ptr()
                 sample['high_res_residual'] = r
             sample['input'] = out[b]
-            job['_lowres'] = low
-            job['_i_bf'] = i_bf[b]
-            results.append(sample)
+            job['_lowres'], job['_i_bf'] = low, i_bf[b]
+            # key order of the reference's sample dict (datasets.py:345-352)
+            results.append({k: sample[k] for k in ('high_res_residual', 'input', 'bias_field_log') if k in sample})
+        self._keep = keep
+        return descs, results
+
+    def _run_chain(self, jobs, arena, targets_fn=None, timers=None):
+        """Planned jobs -> device.  Stage order: bbox (batched) -> targets_fn() (per-sample target kernels, which
+        need the bbox and may feed the mixing step) -> gmm -> warp -> resample -> finish (all batched)."""
+        L = _lib.lib()
+        B = len(jobs)
+        descs, results = self._build_descs(jobs, arena)
         d_dev = arena.put_struct_array(descs)
         arena.commit()
-        _lib.check(L.bfm_gen_run(C.addressof(descs), d_dev, B, _stream()))
+        h = C.addressof(descs)
+
+        def stage(name, fn, dptr):
+            if timers is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _lib.check(fn(h, dptr, B, _stream()))
+            if timers is not None:
+                e1.record()
+                timers.setdefault(name, []).append((e0, e1))
+
+        stage('bbox', L.bfm_gen_bbox, d_dev)
+        for job in jobs:
+            job['plan'].have_bbox = True
+        if targets_fn is not None:
+            if timers is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            targets_fn()
+            if timers is not None:
+                e1.record()
+                timers.setdefault('targets', []).append((e0, e1))
+            patched = False
+            for b, job in enumerate(jobs):
+                if job['p']['mix'] is None:
+                    continue
+                tg = job['target']
+                mt = [tg['T1'][0].contiguous(),
+                      tg['T2'][0].contiguous() if 'T2' in job['modalities'] else None,
+                      tg['FLAIR'][0].contiguous() if 'FLAIR' in job['modalities'] else None]
+                for q, t in enumerate(mt):
+                    if t is not None:
+                        self._keep.append(t)
+                        descs[b].mix[q] = t.data_ptr()
+                patched = True
+            if patched:
+                d_dev = arena.put_struct_array(descs)
+                arena.commit()
+        stage('gmm', L.bfm_gen_gmm, d_dev)
+        stage('warp', L.bfm_gen_warp, d_dev)
+        stage('resample', L.bfm_gen_resample, d_dev)
+        stage('finish', L.bfm_gen_finish, d_dev)
         arena.mark_done()
-        self._keep = keep
-        # key order of the reference's sample dict (datasets.py:345-352)
-        ordered = []
-        for smp in results:
-            o = {}
-            for k in ('high_res_residual', 'input', 'bias_field_log'):
-                if k in smp:
-                    o[k] = smp[k]
-            ordered.append(o)
-        return ordered
+        return results
 
     def _labels(self):
         return self.cache.get(self.modalities['Gen'], 'gen')
@@ -485,21 +515,19 @@ class BaseGen(Dataset):
         return 'bias_field' in self.tasks and input_mode != 'CT'
 
     def _job(self, setups, deform_dict, target, p):
-        mt = None
-        if p['mix'] is not None:
-            mt = [target['T1'][0].contiguous(),
-                  target['T2'][0].contiguous() if 'T2' in self.modalities else None,
-                  target['FLAIR'][0].contiguous() if 'FLAIR' in self.modalities else None]
-        return dict(plan=deform_dict['_plan'], flip=setups['flip'], labels=self._labels(), p=p, mix_targets=mt,
-                    want_bflog=self._want_bflog('synth'), want_residual='super_resolution' in self.tasks)
+        return dict(plan=deform_dict['_plan'], flip=setups['flip'], labels=self._labels(), p=p, target=target,
+                    modalities=dict(self.modalities), want_bflog=self._want_bflog('synth'),
+                    want_residual='super_resolution' in self.tasks)
 
     # ---- reference-shaped sample generation ---------------------------------------------------------
     def generate_sample(self, name, G, setups, deform_dict, res, target):
         """GMM synthesis + augmentation of one sample (datasets.py:357-428)."""
         if not self._stock_chain('synth'):
             return self._generate_sample_opwise(setups, deform_dict, res, target)
+        deform_dict['_plan'].compute_bbox()
         p = self._plan_synth(setups, target)
-        sample = self._run_chain([self._job(setups, deform_dict, target, p)])[0]
+        arena = self.arena.begin()
+        sample = self._run_chain([self._job(setups, deform_dict, target, p)], arena, targets_fn=lambda: None)[0]
         target['pathology'] = 0.
         target['pathology_prob'] = 0.
         return target['pathology'], target['pathology_prob'], sample
@@ -575,22 +603,32 @@ class BaseGen(Dataset):
         return self.rng.choice("pathol.dir", [True, False])
 
     # ---- __getitem__ (datasets.py:638-681) ----------------------------------------------------------
-    def _prologue(self, idx, default):
+    def _prologue_host(self, idx, arena):
+        """Host-only part of an item: input mode, setup and deformation draws (reference order)."""
         if torch.is_tensor(idx):
             idx = idx.tolist()
         dataset_name, case_name, input_mode, img, aff, res, age = self.read_input(idx)
         setups = self.get_setup_params()
-        deform_dict = self.generate_deformation(setups, img.shape)
+        deform_dict = self.generate_deformation(setups, img.shape, arena=arena, lazy=True)
         self.get_left_hemis_mask(None)
-        target = defaultdict(default)
-        target['name'] = case_name
+        return dict(idx=idx, dataset_name=dataset_name, case_name=case_name, input_mode=input_mode, img=img, res=res,
+                    age=age, setups=setups, deform=deform_dict, modalities=dict(self.modalities))
+
+    def _targets(self, ctx, default):
+        """Per-sample target kernels (needs the bounding box on the device)."""
+        self.modalities = ctx['modalities']
+        idx, input_mode, setups, deform_dict = ctx['idx'], ctx['input_mode'], ctx['setups'], ctx['deform']
+        target = ctx.get('target')
+        if target is None:
+            target = defaultdict(default)
+        target['name'] = ctx['case_name']
         for key in ('T1', 'T2', 'FLAIR'):
             target.update(self.read_and_deform_target(idx, target.keys(), key, input_mode, setups, deform_dict))
         for task_name in self.tasks:
             if task_name in K.processing_funcs.keys() and task_name not in ['T1', 'T2', 'FLAIR']:
                 target.update(self.read_and_deform_target(idx, target.keys(), task_name, input_mode, setups,
                                                           deform_dict))
-        return dataset_name, case_name, input_mode, img, res, age, setups, deform_dict, target
+        return target
 
     def _real_input(self, input_mode, setups, deform_dict, res, target):
         from .utils import read_and_deform
@@ -598,29 +636,98 @@ class BaseGen(Dataset):
         return self.augment_sample(None, I, setups, deform_dict, res, target,
                                    pathol_direction=self.get_pathology_direction(input_mode), input_mode=input_mode)
 
-    def __getitem__(self, idx):
-        dataset_name, case_name, input_mode, img, res, age, setups, deform_dict, target = \
-            self._prologue(idx, lambda: None)
-        if input_mode == 'synth':
-            self.update_gen_args(self.synth_image_args)
-            target['pathology'], target['pathology_prob'], sample = \
-                self.generate_sample(case_name, img, setups, deform_dict, res, target)
-        else:
-            self.update_gen_args(self.real_image_args)
-            sample = self._real_input(input_mode, setups, deform_dict, res, target)
+    def _finish_item(self, ctx, target, sample):
+        setups = ctx['setups']
         if setups['flip'] and isinstance(target['pathology'], torch.Tensor):
             target['pathology'] = torch.flip(target['pathology'], [1])
             target['pathology_prob'] = torch.flip(target['pathology_prob'], [1])
-        if age is not None:
-            target['age'] = age
-        self.last_setups, self.last_deform = setups, deform_dict
-        return self.datasets_num, dataset_name, input_mode, target, sample
+        if ctx['age'] is not None:
+            target['age'] = ctx['age']
+        self.last_setups, self.last_deform = setups, ctx['deform']
+        return self.datasets_num, ctx['dataset_name'], ctx['input_mode'], target, sample
+
+    def _fast_ok(self, input_mode):
+        return input_mode == 'synth' and self._stock_chain('synth') and 'pathology' not in self.tasks
+
+    def _gen_arg_sets(self):
+        """Parameter overrides applied before each sample of an item (datasets.py:668, 728-745)."""
+        return [[self.synth_image_args]]
+
+    _default_target = staticmethod(lambda: None)
+    _list_samples = False
+
+    def generate_batch(self, indices, timers=None):
+        """Several items in one go: all host draws first (reference order, item by item), then ONE batched launch
+        per stage of the fused chain.  Returns a list of __getitem__ tuples."""
+        arena = self.arena.begin()
+        ctxs, jobs, spans, slow = [], [], [], {}
+        for n, idx in enumerate(indices):
+            ctx = self._prologue_host(idx, arena)
+            ctxs.append(ctx)
+            if not self._fast_ok(ctx['input_mode']):
+                slow[n] = True
+                spans.append((0, 0))
+                continue
+            ctx['target'] = defaultdict(self._default_target)
+            first = len(jobs)
+            for arg_sets in self._gen_arg_sets():
+                for a in arg_sets:
+                    self.update_gen_args(a)
+                jobs.append(self._job(ctx['setups'], ctx['deform'], ctx['target'],
+                                      self._plan_synth(ctx['setups'], ctx['target'])))
+            spans.append((first, len(jobs)))
+
+        def run_targets():
+            for n, ctx in enumerate(ctxs):
+                if n not in slow:
+                    self._targets(ctx, self._default_target)
+
+        self._last_jobs = jobs
+        results = self._run_chain(jobs, arena, targets_fn=run_targets, timers=timers) if jobs else []
+        items = []
+        for n, ctx in enumerate(ctxs):
+            if n in slow:
+                items.append(self._slow_item(ctx))
+                continue
+            target = ctx['target']
+            target['pathology'] = 0.
+            target['pathology_prob'] = 0.
+            a, b = spans[n]
+            sample = results[a:b] if self._list_samples else results[a]
+            items.append(self._finish_item(ctx, target, sample))
+        return items
+
+    def _slow_item(self, ctx):
+        """Op-by-op path: real-image inputs, custom augmentation sequences, pathology."""
+        self.arena.commit()
+        ctx['deform']['_plan'].compute_bbox()
+        target = self._targets(ctx, self._default_target)
+        setups, deform_dict, res, input_mode = ctx['setups'], ctx['deform'], ctx['res'], ctx['input_mode']
+        samples = []
+        for arg_sets in self._gen_arg_sets():
+            for a in arg_sets[:-1]:
+                self.update_gen_args(a)
+            if input_mode == 'synth':
+                self.update_gen_args(self.synth_image_args)
+                target['pathology'], target['pathology_prob'], sample = \
+                    self.generate_sample(ctx['case_name'], ctx['img'], setups, deform_dict, res, target)
+            else:
+                self.update_gen_args(self.real_image_args)
+                sample = self._real_input(input_mode, setups, deform_dict, res, target)
+            samples.append(sample)
+        return self._finish_item(ctx, target, samples if self._list_samples else samples[0])
+
+    def __getitem__(self, idx):
+        return self.generate_batch([idx])[0]
 
 
 class BrainIDGen(BaseGen):
     """Intra-subject augmentation: one deformation, `all_samples` contrasts; the first `mild_samples` use
     mild_generator parameters, the rest severe_generator (Generator/datasets.py:687-757).  All samples of one
     item run as ONE batched launch of the fused chain."""
+
+    _default_target = staticmethod(lambda: 1.)
+    _list_samples = True
 
     def __init__(self, gen_args, device='cuda', draws=None):
         super(BrainIDGen, self).__init__(gen_args, device, draws)
@@ -629,30 +736,6 @@ class BrainIDGen(BaseGen):
         self.mild_generator_args = gen_args.mild_generator
         self.severe_generator_args = gen_args.severe_generator
 
-    def __getitem__(self, idx):
-        dataset_name, case_name, input_mode, img, res, age, setups, deform_dict, target = \
-            self._prologue(idx, lambda: 1.)
-        samples, jobs = [], []
-        for i_sample in range(self.all_samples):
-            self.update_gen_args(self.mild_generator_args if i_sample < self.mild_samples
-                                 else self.severe_generator_args)
-            if input_mode == 'synth':
-                self.update_gen_args(self.synth_image_args)
-                if self._stock_chain('synth'):
-                    jobs.append(self._job(setups, deform_dict, target, self._plan_synth(setups, target)))
-                else:
-                    samples.append(self.generate_sample(case_name, img, setups, deform_dict, res, target)[2])
-            else:
-                self.update_gen_args(self.real_image_args)
-                samples.append(self._real_input(input_mode, setups, deform_dict, res, target))
-        if jobs:
-            samples = self._run_chain(jobs)
-            target['pathology'] = 0.
-            target['pathology_prob'] = 0.
-        if setups['flip'] and isinstance(target['pathology'], torch.Tensor):
-            target['pathology'] = torch.flip(target['pathology'], [1])
-            target['pathology_prob'] = torch.flip(target['pathology_prob'], [1])
-        if age is not None:
-            target['age'] = age
-        self.last_setups, self.last_deform = setups, deform_dict
-        return self.datasets_num, dataset_name, input_mode, target, samples
+    def _gen_arg_sets(self):
+        return [[self.mild_generator_args if i < self.mild_samples else self.severe_generator_args,
+                 self.synth_image_args] for i in range(self.all_samples)]

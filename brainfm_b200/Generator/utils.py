@@ -188,7 +188,7 @@ class DeformPlan:
     """Device-side description of one random deformation: affine + small nonlinear grid + zoom tables +
     the bounding box of the deformed grid in the source volume.  Owns its device buffers."""
 
-    def __init__(self, size, src, A, c2, fsmall_host, photo, device, F_full=None):
+    def __init__(self, size, src, A, c2, fsmall_host, photo, device, F_full=None, arena=None, lazy=False):
         self.size = [int(v) for v in size]
         self.src = [int(v) for v in src[:3]]
         self.device = torch.device(device)
@@ -197,22 +197,37 @@ class DeformPlan:
         self.photo = bool(photo)
         self.F_full = F_full
         self.struct = _lib.Deform()
-        ar = _MiniArena()
-        fill_deform(self.struct, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo,
-                    F_full.data_ptr() if F_full is not None else None)
-        self._keep, addr = pack_to_device(ar.arrays, self.device) if ar.arrays else (None, [])
-        if fsmall_host is not None:
-            self.struct.fsmall = addr[0]
-            q = 1
-            for ax in range(3):
-                self.struct.ftab.lo[ax] = addr[q]
-                self.struct.ftab.hi[ax] = addr[q + 1]
-                self.struct.ftab.wl[ax] = addr[q + 2]
-                self.struct.ftab.wh[ax] = addr[q + 3]
-                q += 4
-        self.bbox = torch.empty(8, dtype=torch.int32, device=self.device)
+        fptr = F_full.data_ptr() if F_full is not None else None
+        if arena is not None:
+            # tables live in the caller's arena slot: valid until that slot is recycled
+            fill_deform(self.struct, arena, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr)
+            addr, off = arena.reserve(32)
+            self.bbox = arena.view(off, 8, torch.int32)
+        else:
+            ar = _MiniArena()
+            fill_deform(self.struct, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr)
+            self._keep, addr = pack_to_device(ar.arrays, self.device) if ar.arrays else (None, [])
+            if fsmall_host is not None:
+                self.struct.fsmall = addr[0]
+                q = 1
+                for ax in range(3):
+                    self.struct.ftab.lo[ax] = addr[q]
+                    self.struct.ftab.hi[ax] = addr[q + 1]
+                    self.struct.ftab.wl[ax] = addr[q + 2]
+                    self.struct.ftab.wh[ax] = addr[q + 3]
+                    q += 4
+            self.bbox = torch.empty(8, dtype=torch.int32, device=self.device)
         self._bbox_host = None
-        _lib.check(_lib.lib().bfm_deform_grid(C.byref(self.struct), self.bbox.data_ptr(), None, _stream()))
+        self.have_bbox = False
+        if not lazy:
+            if arena is not None:
+                arena.commit()
+            self.compute_bbox()
+
+    def compute_bbox(self):
+        if not self.have_bbox:
+            _lib.check(_lib.lib().bfm_deform_grid(C.byref(self.struct), self.bbox.data_ptr(), None, _stream()))
+            self.have_bbox = True
 
     def bbox_host(self):
         """[x1,y1,z1,x2,y2,z2] -- one 24-byte D2H, only when somebody asks (datasets.py:296-301)."""

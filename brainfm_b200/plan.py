@@ -86,6 +86,7 @@ class Arena:
             self.slots.append(dict(host=host, dev=dev, np=host.numpy(), event=None))
         self.cur = -1
         self.used = 0
+        self.committed = 0
 
     def begin(self):
         self.cur = (self.cur + 1) % len(self.slots)
@@ -93,6 +94,7 @@ class Arena:
         if s["event"] is not None:
             s["event"].synchronize()
         self.used = 0
+        self.committed = 0
         self.base = s["dev"].data_ptr()
         return self
 
@@ -125,8 +127,12 @@ class Arena:
         return self.base + off
 
     def commit(self, stream=None):
+        """Ship everything put() since the last commit (one async copy on the current stream)."""
         s = self.slots[self.cur]
-        s["dev"][:self.used].copy_(s["host"][:self.used], non_blocking=True)
+        if self.used > self.committed:
+            a = self.committed // _ALIGN * _ALIGN
+            s["dev"][a:self.used].copy_(s["host"][a:self.used], non_blocking=True)
+            self.committed = self.used
 
     def mark_done(self):
         ev = torch.cuda.Event()
