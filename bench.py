@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident arm only (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -254,6 +255,11 @@ def main():
     chain_bytes = 4 * nc_mean + 16 * N + 12 * ns_mean + (4 * nc_mean + 4 * N)      # + the T1 target warp
     chain_gbs = chain_bytes * value / world / 1e9
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "stage_ms_per_step": stage_ms,
+                              "host_wall_ms_per_step": 1e3 * host_s / args.steps}), flush=True)
+        return
     # ---------------- end-to-end arm: host buffers in, host buffers out ----------------
     from brainfm_b200 import io as bio
     host_lab = [torch.from_numpy(s["Gen"].astype(np.uint8)).pin_memory() for s in subs]
