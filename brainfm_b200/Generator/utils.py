@@ -39,16 +39,27 @@ def pack_to_device(arrays, device):
 
 
 class _MiniArena:
-    """Arena-compatible packer used when a single plan owns its tables (see plan.Arena for batches)."""
+    """plan.Arena-compatible packer for a single plan that owns its tables: device addresses are known up
+    front (fixed-capacity device buffer), the host image is uploaded once by finalize()."""
 
-    def __init__(self):
-        self.arrays = []
-        self.slots = []
+    def __init__(self, device, capacity=1 << 20):
+        self.host = np.zeros(capacity, dtype=np.uint8)
+        self.dev = torch.empty(capacity, dtype=torch.uint8, device=device)
+        self.base = self.dev.data_ptr()
+        self.used = 0
 
     def put(self, arr):
-        self.arrays.append(np.ascontiguousarray(arr))
-        self.slots.append(None)
-        return len(self.arrays) - 1          # placeholder index, patched in finalize()
+        a = np.ascontiguousarray(arr)
+        off = (self.used + 15) // 16 * 16
+        if off + a.nbytes > self.host.size:
+            raise MemoryError("deformation plan tables exceed the mini arena")
+        self.host[off:off + a.nbytes] = a.view(np.uint8).reshape(-1)
+        self.used = off + a.nbytes
+        return self.base + off
+
+    def finalize(self):
+        n = max(self.used, 16)
+        self.dev[:n].copy_(torch.from_numpy(self.host[:n]))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,18 +215,10 @@ class DeformPlan:
             addr, off = arena.reserve(32)
             self.bbox = arena.view(off, 8, torch.int32)
         else:
-            ar = _MiniArena()
+            ar = _MiniArena(self.device)
             fill_deform(self.struct, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr)
-            self._keep, addr = pack_to_device(ar.arrays, self.device) if ar.arrays else (None, [])
-            if fsmall_host is not None:
-                self.struct.fsmall = addr[0]
-                q = 1
-                for ax in range(3):
-                    self.struct.ftab.lo[ax] = addr[q]
-                    self.struct.ftab.hi[ax] = addr[q + 1]
-                    self.struct.ftab.wl[ax] = addr[q + 2]
-                    self.struct.ftab.wh[ax] = addr[q + 3]
-                    q += 4
+            ar.finalize()
+            self._keep = ar.dev
             self.bbox = torch.empty(8, dtype=torch.int32, device=self.device)
         self._bbox_host = None
         self.have_bbox = False
@@ -282,7 +285,7 @@ def read_image(file_name):
 
 
 def read_and_deform(file_name, dtype, deform_dict, device, mask, default_value_linear_mode=None,
-                    deform_mode='linear', mean=0., scale=1.):
+                    deform_mode='linear', mean=0., scale=1., minmax_out=None):
     """Crop-read + trilinear warp of one volume (Generator/utils.py:296-321), fused into one gather kernel
     over the device-resident volume (no host crop, no H2D per sample)."""
     if mask is not None:
@@ -301,18 +304,20 @@ def read_and_deform(file_name, dtype, deform_dict, device, mask, default_value_l
     scratch = torch.empty(1, dtype=torch.float32, device=plan.device)
     _lib.check(_lib.lib().bfm_warp_volume(C.byref(plan.struct), plan.bbox.data_ptr(), vol.data_ptr(), float(mean),
                                           float(scale), 1 if default_value_linear_mode == 'max' else 0,
-                                          scratch.data_ptr(), out.data_ptr(), _stream()))
+                                          scratch.data_ptr(), out.data_ptr(),
+                                          None if minmax_out is None else minmax_out.data_ptr(), _stream()))
     return out, res
 
 
-def _normalise_flip(x, flip, minmax=True, post=1.0):
+def _normalise_flip(x, flip, minmax=True, post=1.0, mm=None):
     L = _lib.lib()
     out = torch.empty_like(x)
     nx = x.shape[0]
     plane = x.numel() // nx
     if minmax:
-        mm = torch.empty(2, dtype=torch.float32, device=x.device)
-        _lib.check(L.bfm_minmax(x.data_ptr(), x.numel(), mm.data_ptr(), _stream()))
+        if mm is None:
+            mm = torch.empty(2, dtype=torch.float32, device=x.device)
+            _lib.check(L.bfm_minmax(x.data_ptr(), x.numel(), mm.data_ptr(), _stream()))
         _lib.check(L.bfm_shift_scale_flip(x.data_ptr(), out.data_ptr(), nx, plane, mm.data_ptr(), mm.data_ptr() + 4,
                                           1.0, 1 if flip else 0, _stream()))
     else:
@@ -323,8 +328,9 @@ def _normalise_flip(x, flip, minmax=True, post=1.0):
 
 def read_and_deform_image(exist_keys, task_name, file_name, setups, deform_dict, device, mask=None, **kwargs):
     """Warp, min-max normalise, flip (Generator/utils.py:324-343)."""
-    Idef, _ = read_and_deform(file_name, torch.float, deform_dict, device, mask)
-    Idef = _normalise_flip(Idef, setups['flip'])
+    mm = torch.empty(2, dtype=torch.float32, device=_plan_of(deform_dict).device)
+    Idef, _ = read_and_deform(file_name, torch.float, deform_dict, device, mask, minmax_out=mm)
+    Idef = _normalise_flip(Idef, setups['flip'], mm=mm)
     update_dict = {task_name: Idef[None]}
     dm = file_name[:-4] + '.defacingmask.nii'
     if bio.exists(dm):

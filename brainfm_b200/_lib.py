@@ -21,7 +21,8 @@ class ZoomTab(C.Structure):
 
 class Deform(C.Structure):
     _fields_ = [("size", c_i * 3), ("src", c_i * 3), ("A", c_f * 9), ("c2", c_f * 3), ("ctr", c_f * 3),
-                ("fsmall", c_p), ("fs", c_i * 3), ("photo", c_i), ("ftab", ZoomTab), ("F_full", c_p)]
+                ("fsmall", c_p), ("fs", c_i * 3), ("photo", c_i), ("ftab", ZoomTab), ("F_full", c_p),
+                ("cand", c_p * 3), ("ncand", c_i * 3)]
 
 
 class Band(C.Structure):
@@ -58,7 +59,7 @@ _PROTOS = {
     "bfm_minmax": (c_i, [c_p, c_i64, c_p, c_p]),
     "bfm_shift_scale_flip": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p, c_f, c_i, c_p]),
     "bfm_deform_grid": (c_i, [C.POINTER(Deform), c_p, c_p, c_p]),
-    "bfm_warp_volume": (c_i, [C.POINTER(Deform), c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
+    "bfm_warp_volume": (c_i, [C.POINTER(Deform), c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p, c_p]),
     "bfm_label_warp_onehot": (c_i, [C.POINTER(Deform), c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
     "bfm_svf_step": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "bfm_gen_bbox": (c_i, [c_p, c_p, c_i, c_p]),

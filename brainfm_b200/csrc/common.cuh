@@ -118,42 +118,136 @@ __device__ __forceinline__ void row_zoom_setup(const float *__restrict__ small, 
     }
 }
 
-struct RowCtx {
-    float xc, yc;     // centred output coordinates of the row
+// Loop-invariant deformation state, loaded once into registers.
+struct DefRegs {
+    float A[9], c2[3], mx, my, mz, ctr0, ctr1, ctr2;
+    int s0, s1, s2, photo;
+    const float *F_full, *fsmall;
 };
 
-// clamped source-space coordinates of voxel (i,j,k); smF = row table from row_zoom_setup (3 channels)
-__device__ __forceinline__ void voxel_coords(const bfm_deform &d, const float *smF, int i, int j, int k,
-                                             float &px, float &py, float &pz) {
-    float x1 = __fsub_rn((float)i, d.ctr[0]);
-    float y1 = __fsub_rn((float)j, d.ctr[1]);
-    float z1 = __fsub_rn((float)k, d.ctr[2]);
-    if (d.F_full) {
-        const float *f = d.F_full + (((int64_t)i * d.size[1] + j) * d.size[2] + k) * 3;
-        x1 = __fadd_rn(x1, f[0]);
-        y1 = __fadd_rn(y1, f[1]);
-        z1 = __fadd_rn(z1, f[2]);
-    } else if (d.fsmall) {
-        const int lo = d.ftab.lo[2][k] * 3, hi = d.ftab.hi[2][k] * 3;
-        const float wl = d.ftab.wl[2][k], wh = d.ftab.wh[2][k];
-        float f0 = lerp_rn(wl, smF[lo], wh, smF[hi]);
-        float f1 = d.photo ? 0.f : lerp_rn(wl, smF[lo + 1], wh, smF[hi + 1]);
-        float f2 = lerp_rn(wl, smF[lo + 2], wh, smF[hi + 2]);
-        x1 = __fadd_rn(x1, f0);
-        y1 = __fadd_rn(y1, f1);
-        z1 = __fadd_rn(z1, f2);
+__device__ __forceinline__ DefRegs load_def(const bfm_deform &d) {
+    DefRegs g;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) g.A[q] = d.A[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g.c2[q] = d.c2[q];
+    g.mx = (float)(d.src[0] - 1); g.my = (float)(d.src[1] - 1); g.mz = (float)(d.src[2] - 1);
+    g.ctr0 = d.ctr[0]; g.ctr1 = d.ctr[1]; g.ctr2 = d.ctr[2];
+    g.s0 = d.size[0]; g.s1 = d.size[1]; g.s2 = d.size[2];
+    g.photo = d.photo;
+    g.F_full = d.F_full;
+    g.fsmall = d.F_full ? nullptr : d.fsmall;
+    return g;
+}
+
+// ((A0*x + A1*y) + A2*z) + c, evaluated left to right with separately rounded ops (datasets.py:276-278),
+// then the clamp to the source volume (datasets.py:279-284).
+__device__ __forceinline__ void affine_clamp(const DefRegs &g, float x1, float y1, float z1, float &px, float &py,
+                                             float &pz) {
+    px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.A[0], x1), __fmul_rn(g.A[1], y1)), __fmul_rn(g.A[2], z1)), g.c2[0]);
+    py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.A[3], x1), __fmul_rn(g.A[4], y1)), __fmul_rn(g.A[5], z1)), g.c2[1]);
+    pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.A[6], x1), __fmul_rn(g.A[7], y1)), __fmul_rn(g.A[8], z1)), g.c2[2]);
+    px = px < 0.f ? 0.f : px; py = py < 0.f ? 0.f : py; pz = pz < 0.f ? 0.f : pz;
+    px = px > g.mx ? g.mx : px; py = py > g.my ? g.my : py; pz = pz > g.mz ? g.mz : pz;
+}
+
+// Row-blocked traversal of the output grid.  A warp owns R consecutive rows (i, j, 0..s2-1) starting at row0.
+// For every k-chunk the per-k table entries of the third zoom pass are loaded ONCE into registers
+// (`kfn(k)` lets the caller load its own k-dependent state) and reused for the R rows;
+// `fn(r, row, i, j, k, px, py, pz)` receives the clamped source coordinates.
+// smF: this warp's shared scratch, R * 3*fs2 floats (rows of the first two zoom passes).
+template <int R, typename KFn, typename VFn>
+__device__ __forceinline__ void deform_rows(const bfm_deform &d, const DefRegs &g, float *smF, int row0,
+                                            int n_rows, int lane, KFn kfn, VFn fn) {
+    const int fs2x3 = d.fs[2] * 3;
+    int ri[R], rj[R];
+    float xc[R], yc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = min(row0 + r, n_rows - 1);
+        ri[r] = row / g.s1;
+        rj[r] = row - ri[r] * g.s1;
+        xc[r] = __fsub_rn((float)ri[r], g.ctr0);
+        yc[r] = __fsub_rn((float)rj[r], g.ctr1);
+        if (g.fsmall) row_zoom_setup(g.fsmall, d.fs[1], d.fs[2], 3, d.ftab, ri[r], rj[r], smF + r * fs2x3, lane);
     }
-    // ((A0*x + A1*y) + A2*z) + c, evaluated left to right (datasets.py:276-278)
-    px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d.A[0], x1), __fmul_rn(d.A[1], y1)), __fmul_rn(d.A[2], z1)), d.c2[0]);
-    py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d.A[3], x1), __fmul_rn(d.A[4], y1)), __fmul_rn(d.A[5], z1)), d.c2[1]);
-    pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d.A[6], x1), __fmul_rn(d.A[7], y1)), __fmul_rn(d.A[8], z1)), d.c2[2]);
-    if (px < 0.f) px = 0.f;
-    if (py < 0.f) py = 0.f;
-    if (pz < 0.f) pz = 0.f;
-    const float mx = (float)(d.src[0] - 1), my = (float)(d.src[1] - 1), mz = (float)(d.src[2] - 1);
-    if (px > mx) px = mx;
-    if (py > my) py = my;
-    if (pz > mz) pz = mz;
+    __syncwarp();
+    const int nr = min(R, n_rows - row0);
+    for (int k = lane; k < g.s2; k += 32) {
+        int lo = 0, hi = 0;
+        float wl = 0.f, wh = 0.f;
+        if (g.fsmall) {
+            lo = __ldg(d.ftab.lo[2] + k) * 3; hi = __ldg(d.ftab.hi[2] + k) * 3;
+            wl = __ldg(d.ftab.wl[2] + k); wh = __ldg(d.ftab.wh[2] + k);
+        }
+        const float zc = __fsub_rn((float)k, g.ctr2);
+        kfn(k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r >= nr) break;
+            float x1 = xc[r], y1 = yc[r], z1 = zc;
+            if (g.F_full) {
+                const float *f = g.F_full + ((int64_t)(row0 + r) * g.s2 + k) * 3;
+                x1 = __fadd_rn(x1, f[0]); y1 = __fadd_rn(y1, f[1]); z1 = __fadd_rn(z1, f[2]);
+            } else if (g.fsmall) {
+                const float *sm = smF + r * fs2x3;
+                const float f0 = lerp_rn(wl, sm[lo], wh, sm[hi]);
+                const float f1 = g.photo ? 0.f : lerp_rn(wl, sm[lo + 1], wh, sm[hi + 1]);
+                const float f2 = lerp_rn(wl, sm[lo + 2], wh, sm[hi + 2]);
+                x1 = __fadd_rn(x1, f0); y1 = __fadd_rn(y1, f1); z1 = __fadd_rn(z1, f2);
+            }
+            float px, py, pz;
+            affine_clamp(g, x1, y1, z1, px, py, pz);
+            fn(r, row0 + r, ri[r], rj[r], k, px, py, pz);
+        }
+    }
+}
+
+// Bounding-box-relative trilinear taps with 32-bit element indices (volumes < 2^31 elements).
+struct BoxRegs {
+    float l0, l1, l2, h0, h1, h2;   // bbox origin and (crop extent - 1) as floats
+    int b0, b1, b2, c0, c1, c2;     // bbox origin, crop extent - 1
+    int n1n2, n2;                   // source strides
+};
+__device__ __forceinline__ BoxRegs load_box(const int *bb, int n1, int n2) {
+    BoxRegs q;
+    q.b0 = bb[0]; q.b1 = bb[1]; q.b2 = bb[2];
+    q.c0 = bb[3] - bb[0] - 1; q.c1 = bb[4] - bb[1] - 1; q.c2 = bb[5] - bb[2] - 1;
+    q.l0 = (float)q.b0; q.l1 = (float)q.b1; q.l2 = (float)q.b2;
+    q.h0 = (float)q.c0; q.h1 = (float)q.c1; q.h2 = (float)q.c2;
+    q.n1n2 = n1 * n2; q.n2 = n2;
+    return q;
+}
+struct Taps32 {
+    int base, dx, dy, dz;           // element index of the (lo,lo,lo) tap and the offsets to the hi taps
+    float ax0, ax1, ay0, ay1, az0, az1;
+    bool ok;
+};
+__device__ __forceinline__ Taps32 make_taps32(float px, float py, float pz, const BoxRegs &q) {
+    Taps32 t;
+    const float rx = __fsub_rn(px, q.l0), ry = __fsub_rn(py, q.l1), rz = __fsub_rn(pz, q.l2);
+    t.ok = (rx > 0.f) & (ry > 0.f) & (rz > 0.f) & (rx <= q.h0) & (ry <= q.h1) & (rz <= q.h2);
+    const float fx = floorf(rx), fy = floorf(ry), fz = floorf(rz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    t.ax1 = __fsub_rn(rx, fx); t.ax0 = __fsub_rn(1.f, t.ax1);
+    t.ay1 = __fsub_rn(ry, fy); t.ay0 = __fsub_rn(1.f, t.ay1);
+    t.az1 = __fsub_rn(rz, fz); t.az0 = __fsub_rn(1.f, t.az1);
+    t.base = (q.b0 + ix) * q.n1n2 + (q.b1 + iy) * q.n2 + (q.b2 + iz);
+    t.dx = ix < q.c0 ? q.n1n2 : 0;       // hi = min(lo+1, n-1)  (utils.py:148-149)
+    t.dy = iy < q.c1 ? q.n2 : 0;
+    t.dz = iz < q.c2 ? 1 : 0;
+    return t;
+}
+template <typename Fetch>
+__device__ __forceinline__ float trilerp32(const Taps32 &t, Fetch at) {
+    const int b = t.base;
+    float e00 = lerp_rn(at(b), t.ax0, at(b + t.dx), t.ax1);
+    float e01 = lerp_rn(at(b + t.dz), t.ax0, at(b + t.dx + t.dz), t.ax1);
+    float e10 = lerp_rn(at(b + t.dy), t.ax0, at(b + t.dx + t.dy), t.ax1);
+    float e11 = lerp_rn(at(b + t.dy + t.dz), t.ax0, at(b + t.dx + t.dy + t.dz), t.ax1);
+    float f0 = lerp_rn(e00, t.ay0, e10, t.ay1);
+    float f1 = lerp_rn(e01, t.ay0, e11, t.ay1);
+    return lerp_rn(f0, t.az0, f1, t.az1);
 }
 
 // Trilinear taps of a bbox-relative coordinate triple (fast_3D_interp_torch, utils.py:141-166).
@@ -192,6 +286,7 @@ __device__ __forceinline__ float trilerp(const Taps &t, Fetch at) {
     return lerp_rn(f0, t.az0, f1, t.az1);
 }
 
-constexpr int kRowWarps = 8;   // warps (= output rows) per block in the row-wise kernels
+constexpr int kRowWarps = 8;   // warps per block in the row-wise kernels
+constexpr int kRowsPerWarp = 4;   // output rows owned by one warp
 
 }  // namespace bfm

@@ -132,15 +132,25 @@ __global__ void k_minmax_init(int *mm) {
     mm[1] = f2ord(-INFINITY);
 }
 __global__ void k_minmax(const float *__restrict__ x, int64_t n, int *mm) {
+    __shared__ float red[8][2];
     float lo = INFINITY, hi = -INFINITY;
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n4 = ((uintptr_t)x & 15) == 0 ? n / 4 : 0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n4; p += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg((const float4 *)x + p);
+        lo = fminf(fminf(lo, v.x), fminf(fminf(v.y, v.z), v.w));
+        hi = fmaxf(fmaxf(hi, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+    }
+    for (int64_t p = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const float v = x[p];
         lo = fminf(lo, v);
         hi = fmaxf(hi, v);
     }
     lo = warp_min(lo);
     hi = warp_max(hi);
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = lo; red[threadIdx.x >> 5][1] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fminf(lo, red[w][0]); hi = fmaxf(hi, red[w][1]); }
         atomicMin(mm, f2ord(lo));
         atomicMax(mm + 1, f2ord(hi));
     }
@@ -178,26 +188,24 @@ __global__ void k_bbox_init(int *bb) {
     else if (threadIdx.x < 6) bb[threadIdx.x] = 0;
 }
 
-__device__ __forceinline__ void bbox_rows(const bfm_deform &d, int *bb_bits, float *smF) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *sm = smF + warp * (kMaxSmallZ * 3);
-    const int64_t row = (int64_t)blockIdx.x * kRowWarps + warp;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {0.f, 0.f, 0.f};
-    if (row < (int64_t)d.size[0] * d.size[1]) {
-        const int i = (int)(row / d.size[1]), j = (int)(row % d.size[1]);
-        if (d.fsmall && !d.F_full) {
-            row_zoom_setup(d.fsmall, d.fs[1], d.fs[2], 3, d.ftab, i, j, sm, lane);
-            __syncwarp();
-        }
-        for (int k = lane; k < d.size[2]; k += 32) {
-            float px, py, pz;
-            voxel_coords(d, sm, i, j, k, px, py, pz);
-            lo[0] = fminf(lo[0], px); hi[0] = fmaxf(hi[0], px);
-            lo[1] = fminf(lo[1], py); hi[1] = fmaxf(hi[1], py);
-            lo[2] = fminf(lo[2], pz); hi[2] = fmaxf(hi[2], pz);
-        }
-    }
+__global__ void __launch_bounds__(kRowWarps * 32)
+k_deform_bbox(const __grid_constant__ bfm_deform d, int *bb_bits, int fstride) {
+    extern __shared__ float smem[];
     __shared__ float red[kRowWarps][6];
+    const DefRegs g = load_def(d);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *smF = smem + warp * kRowsPerWarp * fstride;
+    const int n_rows = g.s0 * g.s1;
+    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {0.f, 0.f, 0.f};
+    if (row0 < n_rows) {
+        deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
+                                  [&](int, int, int, int, int, float px, float py, float pz) {
+                                      lo[0] = fminf(lo[0], px); hi[0] = fmaxf(hi[0], px);
+                                      lo[1] = fminf(lo[1], py); hi[1] = fmaxf(hi[1], py);
+                                      lo[2] = fminf(lo[2], pz); hi[2] = fmaxf(hi[2], pz);
+                                  });
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         lo[a] = warp_min(lo[a]);
@@ -221,11 +229,6 @@ __device__ __forceinline__ void bbox_rows(const bfm_deform &d, int *bb_bits, flo
     }
 }
 
-__global__ void __launch_bounds__(kRowWarps * 32) k_deform_bbox(const __grid_constant__ bfm_deform d, int *bb_bits) {
-    __shared__ float smF[kRowWarps * kMaxSmallZ * 3];
-    bbox_rows(d, bb_bits, smF);
-}
-
 __global__ void k_bbox_finish(int *bb) {
     // lo = floor(min), hi = 1 + ceil(max)   (datasets.py:288-293)
     if (threadIdx.x < 3) bb[threadIdx.x] = (int)floorf(__int_as_float(bb[threadIdx.x]));
@@ -233,33 +236,30 @@ __global__ void k_bbox_finish(int *bb) {
 }
 
 __global__ void __launch_bounds__(kRowWarps * 32)
-k_deform_coords(const __grid_constant__ bfm_deform d, const int *__restrict__ bb, float *__restrict__ out) {
-    __shared__ float smF[kRowWarps * kMaxSmallZ * 3];
+k_deform_coords(const __grid_constant__ bfm_deform d, const int *__restrict__ bb, float *__restrict__ out, int fstride) {
+    extern __shared__ float smem[];
+    const DefRegs g = load_def(d);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *sm = smF + warp * (kMaxSmallZ * 3);
-    const int64_t row = (int64_t)blockIdx.x * kRowWarps + warp;
-    if (row >= (int64_t)d.size[0] * d.size[1]) return;
-    const int i = (int)(row / d.size[1]), j = (int)(row % d.size[1]);
-    if (d.fsmall && !d.F_full) {
-        row_zoom_setup(d.fsmall, d.fs[1], d.fs[2], 3, d.ftab, i, j, sm, lane);
-        __syncwarp();
-    }
-    const int64_t N = (int64_t)d.size[0] * d.size[1] * d.size[2];
+    float *smF = smem + warp * kRowsPerWarp * fstride;
+    const int n_rows = g.s0 * g.s1;
+    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
+    if (row0 >= n_rows) return;
+    const int64_t N = (int64_t)n_rows * g.s2;
     const float l0 = (float)bb[0], l1 = (float)bb[1], l2 = (float)bb[2];
-    for (int k = lane; k < d.size[2]; k += 32) {
-        float px, py, pz;
-        voxel_coords(d, sm, i, j, k, px, py, pz);
-        const int64_t p = row * d.size[2] + k;
-        out[p] = __fsub_rn(px, l0);
-        out[N + p] = __fsub_rn(py, l1);
-        out[2 * N + p] = __fsub_rn(pz, l2);
-    }
+    deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
+                              [&](int, int row, int, int, int k, float px, float py, float pz) {
+                                  const int64_t p = (int64_t)row * g.s2 + k;
+                                  out[p] = __fsub_rn(px, l0);
+                                  out[N + p] = __fsub_rn(py, l1);
+                                  out[2 * N + p] = __fsub_rn(pz, l2);
+                              });
 }
 
 // crop maximum of (nan_to_num(src) - mean) / scale  (default_value_linear_mode == 'max')
 __global__ void k_crop_max_init(float *m) { *(int *)m = f2ord(-INFINITY); }
 __global__ void k_crop_max(const float *__restrict__ src, int n1, int n2, const int *__restrict__ bb, float mean,
                            float scale, float *m) {
+    __shared__ float red[8];
     const int c0 = bb[3] - bb[0], c1 = bb[4] - bb[1], c2 = bb[5] - bb[2];
     const int64_t total = (int64_t)c0 * c1 * c2;
     float hi = -INFINITY;
@@ -270,78 +270,96 @@ __global__ void k_crop_max(const float *__restrict__ src, int n1, int n2, const 
         hi = fmaxf(hi, v);
     }
     hi = warp_max(hi);
-    if ((threadIdx.x & 31) == 0) atomicMax((int *)m, f2ord(hi));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) hi = fmaxf(hi, red[w]);
+        atomicMax((int *)m, f2ord(hi));
+    }
 }
 __global__ void k_crop_max_decode(float *m) { *m = ord2f(*(int *)m); }
 
+// read_and_deform: warp of a full source volume; optional fused min/max of the result (for the
+// `Idef -= min; Idef /= max` normalisation of read_and_deform_image)
 __global__ void __launch_bounds__(kRowWarps * 32)
 k_warp_volume(const __grid_constant__ bfm_deform d, const int *__restrict__ bb, const float *__restrict__ src,
-              float mean, float scale, const float *__restrict__ dflt_dev, float *__restrict__ out) {
-    __shared__ float smF[kRowWarps * kMaxSmallZ * 3];
+              float mean, float scale, const float *__restrict__ dflt_dev, float *__restrict__ out, int *mm_ord,
+              int fstride) {
+    extern __shared__ float smem[];
+    __shared__ float red[kRowWarps][2];
+    const DefRegs g = load_def(d);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *sm = smF + warp * (kMaxSmallZ * 3);
-    const int64_t row = (int64_t)blockIdx.x * kRowWarps + warp;
-    if (row >= (int64_t)d.size[0] * d.size[1]) return;
-    const int i = (int)(row / d.size[1]), j = (int)(row % d.size[1]);
-    if (d.fsmall && !d.F_full) {
-        row_zoom_setup(d.fsmall, d.fs[1], d.fs[2], 3, d.ftab, i, j, sm, lane);
-        __syncwarp();
+    float *smF = smem + warp * kRowsPerWarp * fstride;
+    const int n_rows = g.s0 * g.s1;
+    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
+    float vlo = INFINITY, vhi = -INFINITY;
+    if (row0 < n_rows) {
+        const float dv = dflt_dev ? *dflt_dev : 0.f;
+        const BoxRegs box = load_box(bb, d.src[1], d.src[2]);
+        const bool plain = (mean == 0.f && scale == 1.f);
+        deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
+                                  [&](int, int row, int, int, int k, float px, float py, float pz) {
+                                      const Taps32 t = make_taps32(px, py, pz, box);
+                                      float v = dv;
+                                      if (t.ok) {
+                                          v = trilerp32(t, [&](int e) {
+                                              const float s = nan_to_num(__ldg(src + e));
+                                              return plain ? s : __fdiv_rn(__fsub_rn(s, mean), scale);
+                                          });
+                                      }
+                                      out[row * g.s2 + k] = v;
+                                      vlo = fminf(vlo, v);
+                                      vhi = fmaxf(vhi, v);
+                                  });
     }
-    const float dv = dflt_dev ? *dflt_dev : 0.f;
-    const int n1 = d.src[1], n2 = d.src[2];
-    const bool plain = (mean == 0.f && scale == 1.f);
-    for (int k = lane; k < d.size[2]; k += 32) {
-        float px, py, pz;
-        voxel_coords(d, sm, i, j, k, px, py, pz);
-        Taps t = make_taps(px, py, pz, bb);
-        float v = dv;
-        if (t.ok) {
-            v = trilerp(t, [&](int x, int y, int z) {
-                float s = nan_to_num(__ldg(src + ((int64_t)x * n1 + y) * n2 + z));
-                return plain ? s : __fdiv_rn(__fsub_rn(s, mean), scale);
-            });
+    if (mm_ord) {
+        vlo = warp_min(vlo);
+        vhi = warp_max(vhi);
+        if (lane == 0) { red[warp][0] = vlo; red[warp][1] = vhi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < kRowWarps; ++w) { vlo = fminf(vlo, red[w][0]); vhi = fmaxf(vhi, red[w][1]); }
+            atomicMin(mm_ord, f2ord(vlo));
+            atomicMax(mm_ord + 1, f2ord(vhi));
         }
-        out[row * d.size[2] + k] = v;
     }
 }
 
 __global__ void __launch_bounds__(kRowWarps * 32)
 k_label_warp(const __grid_constant__ bfm_deform d, const int *__restrict__ bb, const int32_t *__restrict__ labels,
              const int32_t *__restrict__ lut, int lut_n, int n_classes, const int32_t *__restrict__ vflip, int flip,
-             float *__restrict__ onehot, int32_t *__restrict__ label_out) {
-    __shared__ float smF[kRowWarps * kMaxSmallZ * 3];
+             float *__restrict__ onehot, int32_t *__restrict__ label_out, int fstride) {
+    extern __shared__ float smem[];
+    const DefRegs g = load_def(d);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *sm = smF + warp * (kMaxSmallZ * 3);
-    const int64_t row = (int64_t)blockIdx.x * kRowWarps + warp;
-    if (row >= (int64_t)d.size[0] * d.size[1]) return;
-    const int i = (int)(row / d.size[1]), j = (int)(row % d.size[1]);
-    if (d.fsmall && !d.F_full) {
-        row_zoom_setup(d.fsmall, d.fs[1], d.fs[2], 3, d.ftab, i, j, sm, lane);
-        __syncwarp();
-    }
+    float *smF = smem + warp * kRowsPerWarp * fstride;
+    const int n_rows = g.s0 * g.s1;
+    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
+    if (row0 >= n_rows) return;
     const int n1 = d.src[1], n2 = d.src[2];
-    const int cx = bb[3] - bb[0], cy = bb[4] - bb[1], cz = bb[5] - bb[2];
-    const int64_t N = (int64_t)d.size[0] * d.size[1] * d.size[2];
-    const int oi = flip ? d.size[0] - 1 - i : i;
-    for (int k = lane; k < d.size[2]; k += 32) {
-        float px, py, pz;
-        voxel_coords(d, sm, i, j, k, px, py, pz);
-        // nearest: round-half-even of the bbox-relative coordinate, clamped to the crop (utils.py:124-138)
-        int x = min(max(__float2int_rn(__fsub_rn(px, (float)bb[0])), 0), cx - 1) + bb[0];
-        int y = min(max(__float2int_rn(__fsub_rn(py, (float)bb[1])), 0), cy - 1) + bb[1];
-        int z = min(max(__float2int_rn(__fsub_rn(pz, (float)bb[2])), 0), cz - 1) + bb[2];
-        int32_t lab = __ldg(labels + ((int64_t)x * n1 + y) * n2 + z);
-        int32_t cls = (lab >= 0 && lab < lut_n) ? __ldg(lut + lab) : 0;
-        if (label_out) label_out[row * d.size[2] + k] = cls;
-        if (onehot) {
-            const int64_t p = ((int64_t)oi * d.size[1] + j) * d.size[2] + k;
-            // flipped output channel c holds input channel vflip[c]
-            for (int c = 0; c < n_classes; ++c) {
-                const int srcc = flip ? vflip[c] : c;
-                onehot[(int64_t)c * N + p] = (srcc == cls) ? 1.f : 0.f;
+    const int b0 = bb[0], b1 = bb[1], b2 = bb[2];
+    const int cx = bb[3] - b0, cy = bb[4] - b1, cz = bb[5] - b2;
+    const float l0 = (float)b0, l1 = (float)b1, l2 = (float)b2;
+    const int64_t N = (int64_t)n_rows * g.s2;
+    deform_rows<kRowsPerWarp>(
+        d, g, smF, row0, n_rows, lane, [](int) {},
+        [&](int, int row, int i, int j, int k, float px, float py, float pz) {
+            // nearest: round-half-even of the bbox-relative coordinate, clamped to the crop (utils.py:124-138)
+            const int x = min(max(__float2int_rn(__fsub_rn(px, l0)), 0), cx - 1) + b0;
+            const int y = min(max(__float2int_rn(__fsub_rn(py, l1)), 0), cy - 1) + b1;
+            const int z = min(max(__float2int_rn(__fsub_rn(pz, l2)), 0), cz - 1) + b2;
+            const int32_t lab = __ldg(labels + (x * n1 + y) * n2 + z);
+            const int32_t cls = (lab >= 0 && lab < lut_n) ? __ldg(lut + lab) : 0;
+            if (label_out) label_out[row * g.s2 + k] = cls;
+            if (onehot) {
+                const int64_t p = (int64_t)((flip ? g.s0 - 1 - i : i) * g.s1 + j) * g.s2 + k;
+                // flipped output channel c holds input channel vflip[c]
+                for (int c = 0; c < n_classes; ++c) {
+                    const int srcc = flip ? __ldg(vflip + c) : c;
+                    onehot[(int64_t)c * N + p] = (srcc == cls) ? 1.f : 0.f;
+                }
             }
-        }
-    }
+        });
 }
 
 __global__ void k_svf_step(const float *__restrict__ Fin, float *__restrict__ Fout, int sx, int sy, int sz) {
@@ -374,6 +392,9 @@ static inline int check_deform(const bfm_deform *d) {
         if (d->size[a] <= 0 || d->src[a] <= 0) return fail(BFM_E_INVALID, "%s", "non-positive size");
     if (d->fsmall && !d->F_full && (d->fs[2] > kMaxSmallZ || d->fs[2] <= 0))
         return fail(BFM_E_UNSUPPORTED, "%s", "small-grid z extent exceeds kMaxSmallZ");
+    if ((int64_t)d->src[0] * d->src[1] * d->src[2] >= (1LL << 31) ||
+        (int64_t)d->size[0] * d->size[1] * d->size[2] >= (1LL << 31))
+        return fail(BFM_E_UNSUPPORTED, "%s", "volumes of 2^31 voxels or more are not supported");
     return BFM_OK;
 }
 }  // namespace bfm
@@ -459,7 +480,7 @@ int bfm_minmax(const float *x, int64_t n, float *minmax_dev, void *stream) {
     BFM_REQUIRE(x && minmax_dev && n > 0, "bfm_minmax: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     k_minmax_init<<<1, 1, 0, s>>>((int *)minmax_dev);
-    k_minmax<<<grid_for(n), 256, 0, s>>>(x, n, (int *)minmax_dev);
+    k_minmax<<<148 * 4, 256, 0, s>>>(x, n, (int *)minmax_dev);
     k_minmax_decode<<<1, 1, 0, s>>>((int *)minmax_dev);
     g_launches.fetch_add(2);
     return check_launch("bfm_minmax");
@@ -474,26 +495,34 @@ int bfm_shift_scale_flip(const float *x, float *out, int nx, int64_t plane, cons
     return check_launch("bfm_shift_scale_flip");
 }
 
+static inline unsigned row_blocks(const bfm_deform *d) {
+    const int64_t rows = (int64_t)d->size[0] * d->size[1];
+    const int per = kRowWarps * kRowsPerWarp;
+    return (unsigned)((rows + per - 1) / per);
+}
+static inline int row_fstride(const bfm_deform *d) { return (d->fsmall && !d->F_full) ? d->fs[2] * 3 : 0; }
+static inline size_t row_smem(const bfm_deform *d) {
+    return (size_t)kRowWarps * kRowsPerWarp * row_fstride(d) * sizeof(float);
+}
+
 int bfm_deform_grid(const bfm_deform *d, int *bbox_dev, float *coords_out, void *stream) {
     int rc = check_deform(d);
     if (rc) return rc;
     BFM_REQUIRE(bbox_dev, "bfm_deform_grid: null bbox");
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t rows = (int64_t)d->size[0] * d->size[1];
-    const unsigned grid = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
     if (!coords_out) {
         k_bbox_init<<<1, 32, 0, s>>>(bbox_dev);
-        k_deform_bbox<<<grid, kRowWarps * 32, 0, s>>>(*d, bbox_dev);
+        k_deform_bbox<<<row_blocks(d), kRowWarps * 32, row_smem(d), s>>>(*d, bbox_dev, row_fstride(d));
         k_bbox_finish<<<1, 32, 0, s>>>(bbox_dev);
         g_launches.fetch_add(2);
         return check_launch("bfm_deform_grid(bbox)");
     }
-    k_deform_coords<<<grid, kRowWarps * 32, 0, s>>>(*d, bbox_dev, coords_out);
+    k_deform_coords<<<row_blocks(d), kRowWarps * 32, row_smem(d), s>>>(*d, bbox_dev, coords_out, row_fstride(d));
     return check_launch("bfm_deform_grid(coords)");
 }
 
 int bfm_warp_volume(const bfm_deform *d, const int *bbox_dev, const float *src, float mean, float scale,
-                    int default_max, float *scratch_max_dev, float *out, void *stream) {
+                    int default_max, float *scratch_max_dev, float *out, float *minmax_out_dev, void *stream) {
     int rc = check_deform(d);
     if (rc) return rc;
     BFM_REQUIRE(bbox_dev && src && out, "bfm_warp_volume: null pointer");
@@ -501,15 +530,21 @@ int bfm_warp_volume(const bfm_deform *d, const int *bbox_dev, const float *src, 
     cudaStream_t s = (cudaStream_t)stream;
     if (default_max) {
         k_crop_max_init<<<1, 1, 0, s>>>(scratch_max_dev);
-        k_crop_max<<<grid_for((int64_t)d->src[0] * d->src[1] * d->src[2]), 256, 0, s>>>(src, d->src[1], d->src[2],
-                                                                                       bbox_dev, mean, scale,
-                                                                                       scratch_max_dev);
+        k_crop_max<<<148 * 8, 256, 0, s>>>(src, d->src[1], d->src[2], bbox_dev, mean, scale, scratch_max_dev);
         k_crop_max_decode<<<1, 1, 0, s>>>(scratch_max_dev);
         g_launches.fetch_add(3);
     }
-    const int64_t rows = (int64_t)d->size[0] * d->size[1];
-    k_warp_volume<<<(unsigned)((rows + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, s>>>(
-        *d, bbox_dev, src, mean, scale, default_max ? scratch_max_dev : nullptr, out);
+    if (minmax_out_dev) {
+        k_minmax_init<<<1, 1, 0, s>>>((int *)minmax_out_dev);
+        g_launches.fetch_add(1);
+    }
+    k_warp_volume<<<row_blocks(d), kRowWarps * 32, row_smem(d), s>>>(
+        *d, bbox_dev, src, mean, scale, default_max ? scratch_max_dev : nullptr, out, (int *)minmax_out_dev,
+        row_fstride(d));
+    if (minmax_out_dev) {
+        k_minmax_decode<<<1, 1, 0, s>>>((int *)minmax_out_dev);
+        g_launches.fetch_add(1);
+    }
     return check_launch("bfm_warp_volume");
 }
 
@@ -520,9 +555,8 @@ int bfm_label_warp_onehot(const bfm_deform *d, const int *bbox_dev, const int32_
     if (rc) return rc;
     BFM_REQUIRE(bbox_dev && labels && lut && (onehot_out || label_out), "bfm_label_warp_onehot: null pointer");
     BFM_REQUIRE(!flip || vflip, "bfm_label_warp_onehot: flip needs vflip");
-    const int64_t rows = (int64_t)d->size[0] * d->size[1];
-    k_label_warp<<<(unsigned)((rows + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, (cudaStream_t)stream>>>(
-        *d, bbox_dev, labels, lut, lut_n, n_classes, vflip, flip, onehot_out, label_out);
+    k_label_warp<<<row_blocks(d), kRowWarps * 32, row_smem(d), (cudaStream_t)stream>>>(
+        *d, bbox_dev, labels, lut, lut_n, n_classes, vflip, flip, onehot_out, label_out, row_fstride(d));
     return check_launch("bfm_label_warp_onehot");
 }
 

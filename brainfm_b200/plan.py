@@ -26,6 +26,20 @@ def zoom_tables_host(n_in, factor, n_out):
     return lo.numpy(), hi.numpy(), wl.numpy(), wh.numpy()
 
 
+def zoom_candidates_host(n_in, factor, n_out):
+    """Output indices next to a kink of the piecewise-linear zoom weights along one axis: the ends, every
+    change of the lower source node, and the transitions into / out of the edge clamp.  Between two
+    consecutive candidates the interpolation weight is (up to rounding) affine in the index, so a field
+    zoomed this way is multilinear between candidates and attains its extrema on them."""
+    factor = float(factor)
+    delta = (1.0 - factor) / (2.0 * factor)
+    v = torch.arange(delta, delta + n_out / factor, 1 / factor, dtype=torch.float32)[:n_out].numpy()
+    seg = np.floor(np.clip(v, 0, n_in - 1)).astype(np.int64) * 4 + (v < 0) * 1 + (v > n_in - 1) * 2
+    k = np.nonzero(seg[1:] != seg[:-1])[0] + 1
+    cand = np.unique(np.concatenate([[0, n_out - 1], k, k - 1]))
+    return cand.astype(np.int32)
+
+
 def zoom_newsize(shape, factor):
     return np.round(np.asarray(shape) * np.asarray(factor, dtype=np.float64)).astype(int)
 
@@ -165,6 +179,13 @@ def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None)
         d.A[q] = float(Af[q])
     d.photo = int(bool(photo))
     d.F_full = F_full_ptr
+    if F_full_ptr is not None:
+        for a in range(3):
+            d.ncand[a] = 0
+    elif fsmall_host is None:
+        for a in range(3):
+            d.cand[a] = arena.put(np.array([0, size[a] - 1], dtype=np.int32))
+            d.ncand[a] = 2
     if fsmall_host is None:
         d.fsmall = None
         return
@@ -176,3 +197,8 @@ def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None)
     new = zoom_newsize(fs, factor)
     assert tuple(new) == tuple(size), (new, size)
     fill_zoom_tab(d.ftab, arena, [zoom_tables_host(fs[a], factor[a], int(new[a])) for a in range(3)])
+    if F_full_ptr is None:
+        for a in range(3):
+            c = zoom_candidates_host(fs[a], factor[a], int(new[a]))
+            d.cand[a] = arena.put(c)
+            d.ncand[a] = int(c.size)

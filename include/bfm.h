@@ -106,16 +106,22 @@ typedef struct bfm_deform {
     int photo;          /* zero F[...,1] (datasets.py:211-212) */
     bfm_zoom_tab ftab;
     const float *F_full; /* optional full-resolution field (size,3) */
+    /* voxels next to the node boundaries of the small grid, per axis (sorted, device); the bounding box of
+       the fused chain is evaluated on their product first (bfm_gen_bbox).  ncand[0] == 0: always full scan. */
+    const int *cand[3];
+    int ncand[3];
 } bfm_deform;
 
 int bfm_deform_grid(const bfm_deform *d_host, int *bbox_dev, float *coords_out, void *stream);
 
 /* read_and_deform (+ wrappers): trilinear warp of a full source volume through the deformation,
  * reading only inside the bbox crop                                    Generator/utils.py:296-321
- * value = nan_to_num(src) -> (v - mean)/scale.  default: 0, or the crop maximum when default_max != 0. */
+ * value = nan_to_num(src) -> (v - mean)/scale.  default: 0, or the crop maximum when default_max != 0.
+ * minmax_out_dev (optional, 2 floats): min and max of the warped volume, reduced in the same kernel
+ * (read_and_deform_image's `Idef -= min; Idef /= max`, utils.py:326-327). */
 int bfm_warp_volume(const bfm_deform *d_host, const int *bbox_dev, const float *src,
                     float mean, float scale, int default_max, float *scratch_max_dev,
-                    float *out, void *stream);
+                    float *out, float *minmax_out_dev, void *stream);
 
 /* read_and_deform_segmentation                                        Generator/utils.py:394-424
  * labels: int32 source volume; lut: int32[lut_n]; out: (n_classes, size) f32 one-hot, channel-first,

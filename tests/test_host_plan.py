@@ -64,3 +64,29 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert declared == set(_lib.exported_symbols())
     assert L.bfm_abi_version() == 1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_bbox_candidates_bound_the_full_scan(seed):
+    """The candidate-voxel bounding box (bfm_gen_bbox) relies on: extrema of the clamped source coordinates
+    over ALL voxels lie within 2*delta of the extrema over the candidate voxels (delta = 1e-3)."""
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    size = [48, 40, 56]
+    src = [64, 64, 64]
+    fs = [int(rng.randint(2, 6)) for _ in range(3)]
+    Fsmall = float(rng.rand() * 4) * torch.randn(*fs, 3)
+    F = go.zoom_linear(Fsmall, np.array(size) / np.array(fs))
+    rot = (rng.rand(3) * 30 - 15) / 180 * np.pi
+    A = torch.tensor(go.affine_matrix(rot, rng.rand(3) * 0.4 - 0.2, 1 + rng.rand(3) * 0.4 - 0.2), dtype=torch.float32)
+    c2 = torch.tensor((np.array(src) - 1) / 2, dtype=torch.float32)
+    _, centred = go.centred_grid(size)
+    p = [centred[d] + F[..., d] for d in range(3)]
+    cands = [torch.from_numpy(plan.zoom_candidates_host(fs[a], size[a] / fs[a], size[a]).astype(np.int64))
+             for a in range(3)]
+    for r in range(3):
+        v = A[r, 0] * p[0] + A[r, 1] * p[1] + A[r, 2] * p[2] + c2[r]
+        v = v.clamp(0, src[r] - 1)
+        sub = v[cands[0]][:, cands[1]][:, :, cands[2]]
+        assert 0 <= float(sub.min() - v.min()) <= 2e-3
+        assert 0 <= float(v.max() - sub.max()) <= 2e-3
