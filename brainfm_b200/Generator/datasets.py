@@ -504,6 +504,7 @@ class BaseGen(Dataset):
         stage('resample', L.bfm_gen_resample, d_dev)
         stage('finish', L.bfm_gen_finish, d_dev)
         arena.mark_done()
+        self._last_descs = (descs, d_dev, B)
         return results
 
     def _labels(self):

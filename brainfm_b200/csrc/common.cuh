@@ -88,7 +88,8 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream,
     float u2 = ((float)r.z + 0.5f) * S, u3 = (float)r.w * S;
     u0 = fminf(u0, 0.99999994f);
     u2 = fminf(u2, 0.99999994f);
-    float ra = sqrtf(-2.f * __logf(u0)), rb = sqrtf(-2.f * __logf(u2));
+    const float ta = -1.3862943611198906f * __log2f(u0), tb = -1.3862943611198906f * __log2f(u2);   // -2 ln u
+    float ra = ta * rsqrtf(ta), rb = tb * rsqrtf(tb);
     float sa, ca, sb, cb;
     __sincosf(6.283185307179586f * u1 - 3.14159265358979f, &sa, &ca);
     __sincosf(6.283185307179586f * u3 - 3.14159265358979f, &sb, &cb);
@@ -232,10 +233,12 @@ __device__ __forceinline__ Taps32 make_taps32(float px, float py, float pz, cons
     t.ax1 = __fsub_rn(rx, fx); t.ax0 = __fsub_rn(1.f, t.ax1);
     t.ay1 = __fsub_rn(ry, fy); t.ay0 = __fsub_rn(1.f, t.ay1);
     t.az1 = __fsub_rn(rz, fz); t.az0 = __fsub_rn(1.f, t.az1);
-    t.base = (q.b0 + ix) * q.n1n2 + (q.b1 + iy) * q.n2 + (q.b2 + iz);
-    t.dx = ix < q.c0 ? q.n1n2 : 0;       // hi = min(lo+1, n-1)  (utils.py:148-149)
-    t.dy = iy < q.c1 ? q.n2 : 0;
-    t.dz = iz < q.c2 ? 1 : 0;
+    // invalid points gather from the crop origin (always in range) and are masked by the caller: the loads
+    // stay unconditional, so the rows a warp owns can be in flight together
+    t.base = t.ok ? (q.b0 + ix) * q.n1n2 + (q.b1 + iy) * q.n2 + (q.b2 + iz) : q.b0 * q.n1n2 + q.b1 * q.n2 + q.b2;
+    t.dx = (t.ok && ix < q.c0) ? q.n1n2 : 0;       // hi = min(lo+1, n-1)  (utils.py:148-149)
+    t.dy = (t.ok && iy < q.c1) ? q.n2 : 0;
+    t.dz = (t.ok && iz < q.c2) ? 1 : 0;
     return t;
 }
 template <typename Fetch>
@@ -287,6 +290,9 @@ __device__ __forceinline__ float trilerp(const Taps &t, Fetch at) {
 }
 
 constexpr int kRowWarps = 8;   // warps per block in the row-wise kernels
-constexpr int kRowsPerWarp = 4;   // output rows owned by one warp
+#ifndef KROWS
+#define KROWS 4
+#endif
+constexpr int kRowsPerWarp = KROWS;   // output rows owned by one warp
 
 }  // namespace bfm

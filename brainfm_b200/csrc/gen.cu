@@ -177,12 +177,75 @@ __device__ __forceinline__ int label_index(float g) {
     return min(max(r, 0), 255);
 }
 
+// Vector path (n2 % 4 == 0): grid = (groups per x-plane / 256, n0, B); no integer division by runtime values
+// except one per thread.
+__global__ void __launch_bounds__(256) k_gen_gmm_planes(const bfm_gen_sample *__restrict__ S) {
+    __shared__ bfm_gen_sample sd;
+    __shared__ float lut[512];
+    const bfm_gen_sample *sp = S + blockIdx.z;
+    const int x = blockIdx.y;
+    {
+        const int *bb = sp->bbox;
+        if (x >= sp->d.src[0] || (sp->d.src[2] & 3) || x < bb[0] || x >= bb[3]) return;
+    }
+    stage_desc(&sd, sp);
+    const bfm_gen_sample &s = sd;
+    const int n1 = s.d.src[1], n2 = s.d.src[2];
+    const int n2v = n2 >> 2;
+    const int b1 = s.bbox[1], b2 = s.bbox[2], e1 = s.bbox[4], e2 = s.bbox[5], b0 = s.bbox[0];
+    // block covers 256 consecutive groups of this plane: skip if all of its rows are outside [b1, e1)
+    const int g0 = blockIdx.x * blockDim.x;
+    if (g0 >= n1 * n2v) return;
+    {
+        const int ya = g0 / n2v, yb = min(g0 + (int)blockDim.x - 1, n1 * n2v - 1) / n2v;
+        if (yb < b1 || ya >= e1) return;
+    }
+    for (int q = threadIdx.x; q < 512; q += blockDim.x) lut[q] = q < 256 ? __ldg(s.mu + q) : __ldg(s.sigma + q - 256);
+    __syncthreads();
+    const int gq = g0 + threadIdx.x;
+    if (gq >= n1 * n2v) return;
+    const int y = gq / n2v, z = (gq - y * n2v) << 2;
+    if (y < b1 || y >= e1 || z + 3 < b2 || z >= e2) return;
+    const int p0 = (x * n1 + y) * n2 + z;
+    float ev[4];
+    if (!s.eps_gmm) {
+        const float4 e = philox_normal4(s.seed, 0u, (uint64_t)(p0 >> 2));
+        ev[0] = e.x; ev[1] = e.y; ev[2] = e.z; ev[3] = e.w;
+    } else {
+        const int c1 = e1 - b1, c2 = e2 - b2;
+        const float *er = s.eps_gmm + ((x - b0) * c1 + (y - b1)) * c2 - b2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ev[q] = (z + q >= b2 && z + q < e2) ? __ldg(er + z + q) : 0.f;
+    }
+    int lab[4];
+    if (s.label_is_u8) {
+        const uint32_t w = __ldg((const uint32_t *)((const uint8_t *)s.labels + p0));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = (w >> (8 * q)) & 0xff;
+            lab[q] = (l == 77) ? 2 : l;
+        }
+    } else {
+        const float4 f = __ldg((const float4 *)((const float *)s.labels + p0));
+        lab[0] = label_index(f.x); lab[1] = label_index(f.y); lab[2] = label_index(f.z); lab[3] = label_index(f.w);
+    }
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float v = __fadd_rn(lut[lab[q]], __fmul_rn(lut[256 + lab[q]], ev[q]));
+        o[q] = v < 0.f ? 0.f : v;
+    }
+    // positions just outside the crop are never gathered; writing them keeps the store 128-bit
+    *(float4 *)(s.syn + p0) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void __launch_bounds__(256) k_gen_gmm(const bfm_gen_sample *__restrict__ S) {
     __shared__ bfm_gen_sample sd;
     __shared__ float lut[512];
     stage_desc(&sd, S + blockIdx.y);
     const bfm_gen_sample &s = sd;
     const int n0 = s.d.src[0], n1 = s.d.src[1], n2 = s.d.src[2];
+    if ((n2 & 3) == 0) return;                       // handled by k_gen_gmm_planes
     const int total = n0 * n1 * n2;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int blk0 = blockIdx.x * blockDim.x * 4;
@@ -259,10 +322,18 @@ __global__ void __launch_bounds__(256) k_gen_gmm(const bfm_gen_sample *__restric
 // 1e-5 parity tolerance (the reference's own CPU and CUDA pow differ at that level).
 __device__ __forceinline__ float fast_pow(float x, float g) { return exp2f(g * __log2f(x)); }
 
-__global__ void __launch_bounds__(kRowWarps * 32)
+#ifndef WARP_MINB
+#define WARP_MINB 3
+#endif
+template <bool MIX, bool BFL>
+__global__ void __launch_bounds__(kRowWarps * 32, WARP_MINB)
 k_gen_warp(const bfm_gen_sample *__restrict__ S, int fstride, int bstride) {
     extern __shared__ float smem[];
     __shared__ bfm_gen_sample sd;
+    {   // each instantiation handles the samples of its own kind
+        const bfm_gen_sample *sp = S + blockIdx.y;
+        if ((sp->mix[0] != nullptr) != MIX || (sp->bflog_out != nullptr) != BFL) return;
+    }
     stage_desc(&sd, S + blockIdx.y);
     const bfm_gen_sample &s = sd;
     const bfm_deform &d = s.d;
@@ -301,10 +372,10 @@ k_gen_warp(const bfm_gen_sample *__restrict__ S, int fstride, int bstride) {
         },
         [&](int r, int row, int i, int j, int k, float px, float py, float pz) {
             const Taps32 t = make_taps32(px, py, pz, box);
-            float v = 0.f;
-            if (t.ok) v = trilerp32(t, [&](int e) { return __ldg(syn + e); });
+            float v = trilerp32(t, [&](int e) { return __ldg(syn + e); });
+            v = t.ok ? v : 0.f;
             const int p = row * g.s2 + k;
-            if (mix0) {                                       // datasets.py:379-388
+            if (MIX) {                                        // datasets.py:379-388
                 v = __fadd_rn(__fmul_rn(mw0, v), __fmul_rn(mw1, mix0[p]));
                 if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[p]));
                 if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[p]));
@@ -317,7 +388,7 @@ k_gen_warp(const bfm_gen_sample *__restrict__ S, int fstride, int bstride) {
                 const float *sb = smB + r * bs2;
                 const float bl = lerp_rn(kwl, sb[klo], kwh, sb[khi]);
                 v *= exp2f(bl * 1.4426950408889634f);
-                if (bfl) bfl[((flip ? g.s0 - 1 - i : i) * g.s1 + j) * g.s2 + k] = bl;
+                if (BFL) bfl[((flip ? g.s0 - 1 - i : i) * g.s1 + j) * g.s2 + k] = bl;
             }
             i_bf[p] = v;
         });
@@ -428,11 +499,18 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_upsample(const bfm_gen_s
         __syncwarp();
         const int *__restrict__ lo = s.utab.lo[2], *__restrict__ hi2 = s.utab.hi[2];
         const float *__restrict__ wl = s.utab.wl[2], *__restrict__ wh = s.utab.wh[2];
-        const float mx = WRITE ? *s.maxval : 1.f;
+        // I / max(I) (datasets.py:342-343) as a multiplication by the reciprocal: <= 1 ulp from the division
+        const float rmx = WRITE ? __frcp_rn(*s.maxval) : 1.f;
         float *__restrict__ outp = s.out;
         float *__restrict__ resid = s.residual;
         const float *__restrict__ hr = s.i_bf;
-        const int flip = s.flip;
+        int obase[kRowsPerWarp];
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const int row = min(row0 + r, n_rows - 1);
+            const int i = row / s1, j = row - i * s1;
+            obase[r] = ((s.flip ? s0 - 1 - i : i) * s1 + j) * s2;
+        }
         for (int k = lane; k < s2; k += 32) {
             const int a = __ldg(lo + k), b = __ldg(hi2 + k);
             const float wa = __ldg(wl + k), wb = __ldg(wh + k);
@@ -442,12 +520,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_upsample(const bfm_gen_s
                 const float *row_sm = sm + r * max_lz;
                 const float v = lerp_rn(wa, row_sm[a], wb, row_sm[b]);
                 if (WRITE) {
-                    const int row = row0 + r;
-                    const int i = row / s1, j = row - i * s1;
-                    const int o = ((flip ? s0 - 1 - i : i) * s1 + j) * s2 + k;
-                    const float y = __fdiv_rn(v, mx);                                  // datasets.py:342-343
-                    outp[o] = y;
-                    if (resid) resid[o] = __fsub_rn(__fdiv_rn(hr[row * s2 + k], mx), y);   // datasets.py:345-347
+                    const float y = v * rmx;
+                    outp[obase[r] + k] = y;
+                    if (resid) resid[obase[r] + k] = __fsub_rn(hr[(row0 + r) * s2 + k] * rmx, y);   // datasets.py:345-347
                 } else {
                     hi = fmaxf(hi, v);
                 }
@@ -535,13 +610,30 @@ int bfm_gen_bbox(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
 int bfm_gen_gmm(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
     int rc = check_batch(h, d, B);
     if (rc) return rc;
-    int64_t groups = 0;
+    int64_t flat_groups = 0, plane_groups = 0;
+    int max_n0 = 0;
     for (int b = 0; b < B; ++b) {
-        int64_t n = ((int64_t)h[b].d.src[0] * h[b].d.src[1] * h[b].d.src[2] + 3) / 4;
-        groups = n > groups ? n : groups;
+        const int *n = h[b].d.src;
+        if (n[2] & 3) {
+            const int64_t g = ((int64_t)n[0] * n[1] * n[2] + 3) / 4;
+            flat_groups = g > flat_groups ? g : flat_groups;
+        } else {
+            const int64_t g = (int64_t)n[1] * (n[2] / 4);
+            plane_groups = g > plane_groups ? g : plane_groups;
+            max_n0 = n[0] > max_n0 ? n[0] : max_n0;
+        }
     }
-    k_gen_gmm<<<dim3((unsigned)((groups + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(d);
-    return check_launch("bfm_gen_gmm");
+    if (plane_groups > 0) {
+        if (max_n0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_gmm: grid too large");
+        k_gen_gmm_planes<<<dim3((unsigned)((plane_groups + 255) / 256), max_n0, B), 256, 0, (cudaStream_t)stream>>>(d);
+        rc = check_launch("bfm_gen_gmm");
+        if (rc) return rc;
+    }
+    if (flat_groups > 0) {
+        k_gen_gmm<<<dim3((unsigned)((flat_groups + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(d);
+        rc = check_launch("bfm_gen_gmm");
+    }
+    return rc;
 }
 
 int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
@@ -550,9 +642,24 @@ int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
     const int fstride = max_fstride(h, B), bstride = max_bstride(h, B);
     const size_t smem = (size_t)kRowWarps * kRowsPerWarp * (fstride + bstride) * sizeof(float);
     if (smem > 200 * 1024) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_warp: small grids too deep for shared memory");
-    if (smem > 40 * 1024) cudaFuncSetAttribute(k_gen_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_gen_warp<<<dim3(rows_grid(h), B), kRowWarps * 32, smem, (cudaStream_t)stream>>>(d, fstride, bstride);
-    return check_launch("bfm_gen_warp");
+    bool kinds[2][2] = {{false, false}, {false, false}};
+    for (int b = 0; b < B; ++b) kinds[h[b].mix[0] != nullptr][h[b].bflog_out != nullptr] = true;
+    const dim3 grid(rows_grid(h), B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define BFM_LAUNCH_WARP(M, L)                                                                                  \
+    if (kinds[M][L]) {                                                                                         \
+        if (smem > 40 * 1024)                                                                                  \
+            cudaFuncSetAttribute(k_gen_warp<M, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        k_gen_warp<M, L><<<grid, kRowWarps * 32, smem, st>>>(d, fstride, bstride);                             \
+        rc = check_launch("bfm_gen_warp");                                                                     \
+        if (rc) return rc;                                                                                     \
+    }
+    BFM_LAUNCH_WARP(false, false)
+    BFM_LAUNCH_WARP(false, true)
+    BFM_LAUNCH_WARP(true, false)
+    BFM_LAUNCH_WARP(true, true)
+#undef BFM_LAUNCH_WARP
+    return BFM_OK;
 }
 
 int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {

@@ -300,13 +300,11 @@ k_warp_volume(const __grid_constant__ bfm_deform d, const int *__restrict__ bb, 
         deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
                                   [&](int, int row, int, int, int k, float px, float py, float pz) {
                                       const Taps32 t = make_taps32(px, py, pz, box);
-                                      float v = dv;
-                                      if (t.ok) {
-                                          v = trilerp32(t, [&](int e) {
-                                              const float s = nan_to_num(__ldg(src + e));
-                                              return plain ? s : __fdiv_rn(__fsub_rn(s, mean), scale);
-                                          });
-                                      }
+                                      float v = trilerp32(t, [&](int e) {
+                                          const float s = nan_to_num(__ldg(src + e));
+                                          return plain ? s : __fdiv_rn(__fsub_rn(s, mean), scale);
+                                      });
+                                      v = t.ok ? v : dv;
                                       out[row * g.s2 + k] = v;
                                       vlo = fminf(vlo, v);
                                       vhi = fmaxf(vhi, v);

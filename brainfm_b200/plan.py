@@ -12,9 +12,23 @@ from . import _lib
 _ALIGN = 16
 
 
+_ZOOM_CACHE = {}
+_CAND_CACHE = {}
+
+
 def zoom_tables_host(n_in, factor, n_out):
     """lo, hi (int32), wl, wh (float32) of one axis of myzoom_torch -- computed with the reference's own
-    float32 torch expressions (float32 arange is not float64-then-cast)."""
+    float32 torch expressions (float32 arange is not float64-then-cast).  Memoised: the
+    tables only depend on (n_in, factor, n_out) and a generator sees a few hundred distinct keys."""
+    key = (int(n_in), float(factor), int(n_out))
+    hit = _ZOOM_CACHE.get(key)
+    if hit is None:
+        hit = _zoom_tables_host(*key)
+        _ZOOM_CACHE[key] = hit
+    return hit
+
+
+def _zoom_tables_host(n_in, factor, n_out):
     factor = float(factor)
     delta = (1.0 - factor) / (2.0 * factor)
     v = torch.arange(delta, delta + n_out / factor, 1 / factor, dtype=torch.float32)[:n_out]
@@ -23,10 +37,20 @@ def zoom_tables_host(n_in, factor, n_out):
     hi = (lo + 1).clamp(max=n_in - 1)
     wh = v - lo
     wl = 1 - wh
-    return lo.numpy(), hi.numpy(), wl.numpy(), wh.numpy()
+    return (lo.numpy().astype(np.int32), hi.numpy().astype(np.int32), wl.numpy().astype(np.float32),
+            wh.numpy().astype(np.float32))
 
 
 def zoom_candidates_host(n_in, factor, n_out):
+    key = (int(n_in), float(factor), int(n_out))
+    hit = _CAND_CACHE.get(key)
+    if hit is None:
+        hit = _zoom_candidates_host(*key)
+        _CAND_CACHE[key] = hit
+    return hit
+
+
+def _zoom_candidates_host(n_in, factor, n_out):
     """Output indices next to a kink of the piecewise-linear zoom weights along one axis: the ends, every
     change of the lower source node, and the transitions into / out of the edge clamp.  Between two
     consecutive candidates the interpolation weight is (up to rounding) affine in the index, so a field
@@ -161,10 +185,10 @@ class Arena:
 
 def fill_zoom_tab(tab, arena, tables):
     for ax, (lo, hi, wl, wh) in enumerate(tables):
-        tab.lo[ax] = arena.put(lo.astype(np.int32))
-        tab.hi[ax] = arena.put(hi.astype(np.int32))
-        tab.wl[ax] = arena.put(wl.astype(np.float32))
-        tab.wh[ax] = arena.put(wh.astype(np.float32))
+        tab.lo[ax] = arena.put(lo)
+        tab.hi[ax] = arena.put(hi)
+        tab.wl[ax] = arena.put(wl)
+        tab.wh[ax] = arena.put(wh)
 
 
 def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None):
