@@ -68,6 +68,9 @@ _PROTOS = {
     "bfm_gen_resample": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_finish": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_run": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_interpol": (c_i, [c_i, c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_i, c_i, c_i,
+                           c_i, c_i, c_i, c_i64, c_p]),
+    "bfm_spline_filter": (c_i, [c_p, c_i, c_i64, c_i, c_i64, c_i, C.POINTER(C.c_double), c_i, c_p]),
 }
 
 

@@ -196,6 +196,30 @@ int bfm_gen_finish(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, in
 /* all five stages back to back */
 int bfm_gen_run(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * utils/interpol (vendored torch-interpol 0.2.3): spline resampling, forward semantics
+ * ---------------------------------------------------------------------------------------------- */
+
+/* grid_pull / grid_push / grid_count / grid_grad                     utils/interpol/nd.py:81-288,
+ *                                                                    iso0.py:24-100, iso1.py:29-387
+ * Always 3-D (pad lower dimensions with singleton axes, order 0, coordinate 0).
+ * mode 0 pull: inp (Bi,C,X,Y,Z), grid (Bg,P,3) -> out (B,C,P)
+ * mode 1 push: inp (Bi,C,P) or NULL (= count), grid (Bg,P,3) -> out (B,C,X,Y,Z), PRE-ZEROED by the caller
+ * mode 2 grad: like pull, out (B,C,P,3)
+ * order[d] 0..7 (splines.py:30-160), bound[d] 0..6 = zero, replicate, dct1, dct2, dst1, dst2, dft
+ * (bounds.py:8-89), extrapolate 0 no / 1 yes / 2 hist (jit_utils.py:242-255).  Bi, Bg in {1, B}.
+ * iso: 1 when every (real) axis has order 0 (nearest = round-half-even, iso0.py:10-15), 2 when every axis has
+ * order 1 (iso1 gradient convention), 0 otherwise (generic nd path) -- the reference's own dispatch
+ * (pushpull.py:35-233). */
+int bfm_interpol(int mode, int is_double, const void *inp, const void *grid, void *out, const int *ishape,
+                 const int *order, const int *bound, int extrapolate, int iso, int B, int C, int Bi, int Bg,
+                 int64_t P, void *stream);
+
+/* spline_coeff: in-place recursive prefilter along one axis of a tensor viewed as (outer, n, inner)
+ * utils/interpol/coeff.py:35-316.  bound: 0 zero (=dct1), 1 replicate (=dct2), 2 dct1, 3 dct2, 6 dft. */
+int bfm_spline_filter(void *data, int is_double, int64_t outer, int n, int64_t inner, int bound,
+                      const double *poles_host, int npoles, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
