@@ -71,6 +71,13 @@ _PROTOS = {
     "bfm_interpol": (c_i, [c_i, c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_i, c_i, c_i,
                            c_i, c_i, c_i, c_i64, c_p]),
     "bfm_spline_filter": (c_i, [c_p, c_i, c_i64, c_i, c_i64, c_i, C.POINTER(C.c_double), c_i, c_p]),
+    "bfm_perlin3d": (c_i, [c_p, C.POINTER(c_i), C.POINTER(c_i), c_p, c_p]),
+    "bfm_threshold_mask": (c_i, [c_p, c_p, c_i64, C.c_double, c_p]),
+    "bfm_gradient3d": (c_i, [c_p, c_i, C.POINTER(c_i), c_i, C.POINTER(c_f), c_p, c_p]),
+    "bfm_curl3d": (c_i, [c_p, c_p, c_p, c_i, C.POINTER(c_i), c_f, c_p, c_p, c_p, c_p]),
+    "bfm_advect_rhs": (c_i, [c_p, c_i, c_p, c_p, c_p, C.POINTER(c_i), c_i, C.POINTER(c_f), c_p, c_p]),
+    "bfm_rk_combine": (c_i, [c_p, c_i, C.POINTER(c_p), C.POINTER(c_f), c_i, c_i64, c_p, c_i, c_p]),
+    "bfm_rk_error_sum": (c_i, [c_p, c_p, c_p, c_i, c_i64, C.c_double, C.c_double, c_p, c_p]),
 }
 
 

@@ -1,0 +1,282 @@
+// ShapeID kernels: Perlin noise, curl velocity, upwind advection RHS with Neumann boundary, Runge-Kutta stage
+// combinations and the dopri5 error ratio.
+//   generate_perlin_noise_3d     ShapeID/perlin3d.py:15-90   (numpy float64; reproduced bit for bit)
+//   stream_3D / gradient_c       ShapeID/misc.py:66-80, 198-259
+//   gradient_f / gradient_b      ShapeID/DiffEqs/pde.py:13-183
+//   AdvDiffPDE.forward (adv)     ShapeID/DiffEqs/pde.py:588-640, 301-328, 499-509
+//   _runge_kutta_step combos     ShapeID/DiffEqs/rk_common.py:22-61, misc.py:22-25
+//   _compute_error_ratio         ShapeID/DiffEqs/misc.py:146-157
+// numpy / ATen evaluate every `*` and `+` as a separately rounded operation, so the kernels use the
+// non-contracting intrinsics (__dmul_rn, __dadd_rn, __fmul_rn, __fadd_rn).
+#include "common.cuh"
+
+namespace bfm {
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dadd_rn(a, -b); }
+
+// t*t*t*(t*(t*6 - 15) + 10)   (perlin3d.py:11-12), numpy evaluation order
+__device__ __forceinline__ double fade(double t) {
+    return dmul(dmul(dmul(t, t), t), dadd(dmul(t, dsub(dmul(t, 6.0), 15.0)), 10.0));
+}
+
+// grad: (r0+1, r1+1, r2+1, 3) unit vectors (tileable copies already applied by the caller)
+__global__ void k_perlin3d(const double *__restrict__ grad, int s0, int s1, int s2, int r0, int r1, int r2,
+                           double d0, double d1, double d2, double *__restrict__ out) {
+    const int64_t total = (int64_t)s0 * s1 * s2;
+    const int q0 = s0 / r0, q1 = s1 / r1, q2 = s2 / r2;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % s2), j = (int)((p / s2) % s1), i = (int)(p / ((int64_t)s1 * s2));
+        // np.mgrid[0:res:delta] % 1  ->  fmod(i*delta, 1) (values are >= 0)
+        const double gx = fmod(dmul((double)i, d0), 1.0), gy = fmod(dmul((double)j, d1), 1.0),
+                     gz = fmod(dmul((double)k, d2), 1.0);
+        const int a = i / q0, b = j / q1, c = k / q2;
+        auto ramp = [&](int da, int db, int dc) {
+            const double *g = grad + ((((int64_t)(a + da) * (r1 + 1)) + (b + db)) * (r2 + 1) + (c + dc)) * 3;
+            // np.sum over the stacked last axis: (x + y) + z
+            return dadd(dadd(dmul(dsub(gx, (double)da), g[0]), dmul(dsub(gy, (double)db), g[1])),
+                        dmul(dsub(gz, (double)dc), g[2]));
+        };
+        const double n000 = ramp(0, 0, 0), n100 = ramp(1, 0, 0), n010 = ramp(0, 1, 0), n110 = ramp(1, 1, 0);
+        const double n001 = ramp(0, 0, 1), n101 = ramp(1, 0, 1), n011 = ramp(0, 1, 1), n111 = ramp(1, 1, 1);
+        const double t0 = fade(gx), t1 = fade(gy), t2 = fade(gz);
+        const double u0 = dsub(1.0, t0), u1 = dsub(1.0, t1), u2 = dsub(1.0, t2);
+        const double n00 = dadd(dmul(n000, u0), dmul(t0, n100));
+        const double n10 = dadd(dmul(n010, u0), dmul(t0, n110));
+        const double n01 = dadd(dmul(n001, u0), dmul(t0, n101));
+        const double n11 = dadd(dmul(n011, u0), dmul(t0, n111));
+        const double n0 = dadd(dmul(u1, n00), dmul(t1, n10));
+        const double n1 = dadd(dmul(u1, n01), dmul(t1, n11));
+        out[p] = dadd(dmul(u2, n0), dmul(t2, n1));
+    }
+}
+
+// noise *= (noise >= thr); mask = (noise >= thr)     (perlin3d.py:86-90)
+__global__ void k_threshold_mask(double *__restrict__ noise, double *__restrict__ mask, int64_t n, double thr) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const double m = noise[p] >= thr ? 1.0 : 0.0;
+        mask[p] = m;
+        noise[p] = dmul(noise[p], m);
+    }
+}
+
+// one-sided / central differences of gradient_c / gradient_f / gradient_b for a 3-D volume (spacing 1):
+// the difference is formed in the input precision and stored as float32, like `dX[...] = ...` in the reference.
+template <typename T>
+__device__ __forceinline__ float diff_axis(const T *__restrict__ X, int64_t p, int q, int n, int64_t st, int mode) {
+    T v;
+    if (mode == 0) {         // central (misc.py:243-245)
+        if (q == 0) v = X[p + st] - X[p];
+        else if (q == n - 1) v = X[p] - X[p - st];
+        else v = (X[p + st] - X[p - st]) / T(2);
+    } else if (mode == 1) {  // forward (pde.py:48-49)
+        v = q == n - 1 ? X[p] - X[p - st] : X[p + st] - X[p];
+    } else {                 // backward (pde.py:105-106)
+        v = q == 0 ? X[p + st] - X[p] : X[p] - X[p - st];
+    }
+    return (float)v;
+}
+
+template <typename T>
+__global__ void k_gradient3d(const T *__restrict__ X, int n0, int n1, int n2, int mode, float i0, float i1, float i2,
+                             float *__restrict__ out) {
+    const int64_t total = (int64_t)n0 * n1 * n2;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % n2), j = (int)((p / n2) % n1), i = (int)(p / ((int64_t)n1 * n2));
+        out[p * 3] = __fdiv_rn(diff_axis(X, p, i, n0, (int64_t)n1 * n2, mode), i0);
+        out[p * 3 + 1] = __fdiv_rn(diff_axis(X, p, j, n1, n2, mode), i1);
+        out[p * 3 + 2] = __fdiv_rn(diff_axis(X, p, k, n2, 1, mode), i2);
+    }
+}
+
+// stream_3D: V = curl(Phi_a, Phi_b, Phi_c) * multiplier   (misc.py:66-80, perlin3d.py:149-156)
+template <typename T>
+__global__ void k_curl3d(const T *__restrict__ A, const T *__restrict__ B, const T *__restrict__ Cc, int n0, int n1,
+                         int n2, float mult, float *__restrict__ Vx, float *__restrict__ Vy, float *__restrict__ Vz) {
+    const int64_t total = (int64_t)n0 * n1 * n2;
+    const int64_t s0 = (int64_t)n1 * n2, s1 = n2;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % n2), j = (int)((p / n2) % n1), i = (int)(p / s0);
+        const float a_y = diff_axis(A, p, j, n1, s1, 0), a_z = diff_axis(A, p, k, n2, 1, 0);
+        const float b_x = diff_axis(B, p, i, n0, s0, 0), b_z = diff_axis(B, p, k, n2, 1, 0);
+        const float c_x = diff_axis(Cc, p, i, n0, s0, 0), c_y = diff_axis(Cc, p, j, n1, s1, 0);
+        Vx[p] = __fmul_rn(__fsub_rn(c_y, b_z), mult);
+        Vy[p] = __fmul_rn(__fsub_rn(a_z, c_x), mult);
+        Vz[p] = __fmul_rn(__fsub_rn(b_x, a_y), mult);
+    }
+}
+
+// AdvDiffPDE.forward, perf_pattern 'adv', V_type 'vector_div_free':
+//   C <- ReplicationPad3d(1)(C[1:-1,1:-1,1:-1])  (neumann != 0), then
+//   out = -(Vx*Cx + Vy*Cy + Vz*Cz) with per-component upwinding (V > 0 -> backward difference)
+template <typename T>
+__global__ void k_advect_rhs(const T *__restrict__ C, const float *__restrict__ Vx, const float *__restrict__ Vy,
+                             const float *__restrict__ Vz, int n0, int n1, int n2, int neumann, float sp0, float sp1,
+                             float sp2, float *__restrict__ out) {
+    const int64_t total = (int64_t)n0 * n1 * n2;
+    const int64_t s0 = (int64_t)n1 * n2, s1 = n2;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(p % n2), j = (int)((p / n2) % n1), i = (int)(p / s0);
+        auto at = [&](int a, int b, int c) -> T {
+            if (neumann) {
+                a = min(max(a, 1), n0 - 2); b = min(max(b, 1), n1 - 2); c = min(max(c, 1), n2 - 2);
+            }
+            return C[(int64_t)a * s0 + (int64_t)b * s1 + c];
+        };
+        const T c0 = at(i, j, k);
+        auto updiff = [&](float v, int q, int n, int da, int db, int dc) -> float {
+            // gradient_f / gradient_b of the padded volume, stored as float32
+            float df, db_;
+            if (q == n - 1) df = (float)(c0 - at(i - da, j - db, k - dc));
+            else df = (float)(at(i + da, j + db, k + dc) - c0);
+            if (q == 0) db_ = (float)(at(i + da, j + db, k + dc) - c0);
+            else db_ = (float)(c0 - at(i - da, j - db, k - dc));
+            return v > 0.f ? db_ : df;     // dXf*(1-flag) + dXb*flag with flag in {0,1}
+        };
+        const float vx = Vx[p], vy = Vy[p], vz = Vz[p];
+        const float cx = __fdiv_rn(updiff(vx, i, n0, 1, 0, 0), sp0), cy = __fdiv_rn(updiff(vy, j, n1, 0, 1, 0), sp1),
+                    cz = __fdiv_rn(updiff(vz, k, n2, 0, 0, 1), sp2);
+        out[p] = -__fadd_rn(__fadd_rn(__fmul_rn(vx, cx), __fmul_rn(vy, cy)), __fmul_rn(vz, cz));
+    }
+}
+
+// out = y0 + sum_j coef[j] * k_j : the float32 partial sums of _scaled_dot_product, added to the state in the
+// state's precision (rk_common.py:47-48).  y0 == NULL: out = the float32 sum itself (error estimate).
+struct RkArgs {
+    const float *k[8];
+    float coef[8];
+    int n_terms;
+};
+template <typename T, typename TO>
+__global__ void k_rk_combine(const T *__restrict__ y0, RkArgs a, int64_t n, TO *__restrict__ out) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        float acc = __fmul_rn(a.coef[0], a.k[0][p]);
+#pragma unroll 1
+        for (int j = 1; j < a.n_terms; ++j) acc = __fadd_rn(acc, __fmul_rn(a.coef[j], a.k[j][p]));
+        out[p] = y0 ? (TO)(y0[p] + (T)acc) : (TO)acc;
+    }
+}
+
+// sum over voxels of (err / (atol + rtol*max(|y0|,|y1|)))^2 in float64 (misc.py:146-157); result[0] += sum
+template <typename T>
+__global__ void k_rk_error_sum(const float *__restrict__ err, const T *__restrict__ y0, const T *__restrict__ y1,
+                               int64_t n, double rtol, double atol, double *__restrict__ result) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        // tolerance in the state's precision, ratio promoted like torch (float32 state stays float32)
+        const T tol = (T)atol + (T)rtol * max(abs(y0[p]), abs(y1[p]));
+        const T r = (T)err[p] / tol;
+        s += (double)(r * r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        atomicAdd(result, s);
+    }
+}
+
+static inline unsigned g1d(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = 148LL * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+}  // namespace bfm
+
+using namespace bfm;
+
+extern "C" {
+
+int bfm_perlin3d(const double *grad, const int *shape, const int *res, double *out, void *stream) {
+    BFM_REQUIRE(grad && shape && res && out, "bfm_perlin3d: null pointer");
+    for (int d = 0; d < 3; ++d) {
+        BFM_REQUIRE(shape[d] > 0 && res[d] > 0, "bfm_perlin3d: non-positive shape / res");
+        BFM_REQUIRE(shape[d] % res[d] == 0, "bfm_perlin3d: shape must be a multiple of res");
+    }
+    const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
+    k_perlin3d<<<g1d(n), 256, 0, (cudaStream_t)stream>>>(grad, shape[0], shape[1], shape[2], res[0], res[1], res[2],
+                                                         (double)res[0] / shape[0], (double)res[1] / shape[1],
+                                                         (double)res[2] / shape[2], out);
+    return check_launch("bfm_perlin3d");
+}
+
+int bfm_threshold_mask(double *noise, double *mask, int64_t n, double thr, void *stream) {
+    BFM_REQUIRE(noise && mask && n > 0, "bfm_threshold_mask: bad argument");
+    k_threshold_mask<<<g1d(n), 256, 0, (cudaStream_t)stream>>>(noise, mask, n, thr);
+    return check_launch("bfm_threshold_mask");
+}
+
+int bfm_gradient3d(const void *X, int is_double, const int *shape, int mode, const float *spacing, float *out,
+                   void *stream) {
+    BFM_REQUIRE(X && shape && out && spacing, "bfm_gradient3d: null pointer");
+    BFM_REQUIRE(mode >= 0 && mode <= 2, "bfm_gradient3d: mode 0 central, 1 forward, 2 backward");
+    BFM_REQUIRE(shape[0] > 1 && shape[1] > 1 && shape[2] > 1, "bfm_gradient3d: every axis needs at least 2 samples");
+    const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_double) k_gradient3d<double><<<g1d(n), 256, 0, s>>>((const double *)X, shape[0], shape[1], shape[2], mode, spacing[0], spacing[1], spacing[2], out);
+    else k_gradient3d<float><<<g1d(n), 256, 0, s>>>((const float *)X, shape[0], shape[1], shape[2], mode, spacing[0], spacing[1], spacing[2], out);
+    return check_launch("bfm_gradient3d");
+}
+
+int bfm_curl3d(const void *A, const void *B, const void *Cc, int is_double, const int *shape, float multiplier,
+               float *Vx, float *Vy, float *Vz, void *stream) {
+    BFM_REQUIRE(A && B && Cc && shape && Vx && Vy && Vz, "bfm_curl3d: null pointer");
+    BFM_REQUIRE(shape[0] > 1 && shape[1] > 1 && shape[2] > 1, "bfm_curl3d: every axis needs at least 2 samples");
+    const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_double) k_curl3d<double><<<g1d(n), 256, 0, s>>>((const double *)A, (const double *)B, (const double *)Cc, shape[0], shape[1], shape[2], multiplier, Vx, Vy, Vz);
+    else k_curl3d<float><<<g1d(n), 256, 0, s>>>((const float *)A, (const float *)B, (const float *)Cc, shape[0], shape[1], shape[2], multiplier, Vx, Vy, Vz);
+    return check_launch("bfm_curl3d");
+}
+
+int bfm_advect_rhs(const void *C, int is_double, const float *Vx, const float *Vy, const float *Vz, const int *shape,
+                   int neumann, const float *spacing, float *out, void *stream) {
+    BFM_REQUIRE(C && Vx && Vy && Vz && shape && out && spacing, "bfm_advect_rhs: null pointer");
+    BFM_REQUIRE(shape[0] > 2 && shape[1] > 2 && shape[2] > 2, "bfm_advect_rhs: every axis needs at least 3 samples");
+    const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_double) k_advect_rhs<double><<<g1d(n), 256, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
+    else k_advect_rhs<float><<<g1d(n), 256, 0, s>>>((const float *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
+    return check_launch("bfm_advect_rhs");
+}
+
+int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, const float *coef_host, int n_terms,
+                   int64_t n, void *out, int out_is_double, void *stream) {
+    BFM_REQUIRE(k_host && coef_host && out && n > 0, "bfm_rk_combine: bad argument");
+    BFM_REQUIRE(n_terms >= 1 && n_terms <= 8, "bfm_rk_combine: 1..8 terms");
+    RkArgs a;
+    a.n_terms = n_terms;
+    for (int j = 0; j < 8; ++j) {
+        a.k[j] = j < n_terms ? k_host[j] : nullptr;
+        a.coef[j] = j < n_terms ? coef_host[j] : 0.f;
+        if (j < n_terms && !k_host[j]) return fail(BFM_E_INVALID, "%s", "bfm_rk_combine: null stage");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!y0) {
+        BFM_REQUIRE(!out_is_double, "bfm_rk_combine: the bare float32 sum is written as float32");
+        k_rk_combine<float, float><<<g1d(n), 256, 0, s>>>(nullptr, a, n, (float *)out);
+    } else if (is_double) {
+        BFM_REQUIRE(out_is_double, "bfm_rk_combine: float64 state needs float64 output");
+        k_rk_combine<double, double><<<g1d(n), 256, 0, s>>>((const double *)y0, a, n, (double *)out);
+    } else {
+        BFM_REQUIRE(!out_is_double, "bfm_rk_combine: float32 state needs float32 output");
+        k_rk_combine<float, float><<<g1d(n), 256, 0, s>>>((const float *)y0, a, n, (float *)out);
+    }
+    return check_launch("bfm_rk_combine");
+}
+
+int bfm_rk_error_sum(const float *err, const void *y0, const void *y1, int is_double, int64_t n, double rtol,
+                     double atol, double *result_dev, void *stream) {
+    BFM_REQUIRE(err && y0 && y1 && result_dev && n > 0, "bfm_rk_error_sum: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(result_dev, 0, sizeof(double), s);
+    if (is_double) k_rk_error_sum<double><<<g1d(n), 256, 0, s>>>(err, (const double *)y0, (const double *)y1, n, rtol, atol, result_dev);
+    else k_rk_error_sum<float><<<g1d(n), 256, 0, s>>>(err, (const float *)y0, (const float *)y1, n, rtol, atol, result_dev);
+    return check_launch("bfm_rk_error_sum");
+}
+
+}  // extern "C"

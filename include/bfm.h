@@ -220,6 +220,35 @@ int bfm_interpol(int mode, int is_double, const void *inp, const void *grid, voi
 int bfm_spline_filter(void *data, int is_double, int64_t outer, int n, int64_t inner, int bound,
                       const double *poles_host, int npoles, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ShapeID: Perlin shapes, curl velocity, advection PDE, Runge-Kutta building blocks
+ * ---------------------------------------------------------------------------------------------- */
+
+/* generate_perlin_noise_3d                                           ShapeID/perlin3d.py:15-90
+ * grad: (res0+1, res1+1, res2+1, 3) float64 unit gradients (tileable copies applied by the caller);
+ * out: (shape) float64, bit-exact with the numpy reference. */
+int bfm_perlin3d(const double *grad, const int *shape, const int *res, double *out, void *stream);
+/* mask = noise >= thr; noise *= mask                                 ShapeID/perlin3d.py:86-90 */
+int bfm_threshold_mask(double *noise, double *mask, int64_t n, double thr, void *stream);
+/* gradient_c (mode 0) / gradient_f (1) / gradient_b (2) of a 3-D volume -> (shape, 3) float32
+ * ShapeID/misc.py:198-259, ShapeID/DiffEqs/pde.py:13-183 */
+int bfm_gradient3d(const void *X, int is_double, const int *shape, int mode, const float *spacing, float *out,
+                   void *stream);
+/* stream_3D * V_multiplier                                           ShapeID/misc.py:66-80, perlin3d.py:149-156 */
+int bfm_curl3d(const void *A, const void *B, const void *C, int is_double, const int *shape, float multiplier,
+               float *Vx, float *Vy, float *Vz, void *stream);
+/* AdvDiffPDE.forward for perf_pattern 'adv', V_type 'vector_div_free' ShapeID/DiffEqs/pde.py:588-640, 301-328, 499-509
+ * neumann != 0: replicate-pad the interior before differencing (set_BC). */
+int bfm_advect_rhs(const void *C, int is_double, const float *Vx, const float *Vy, const float *Vz, const int *shape,
+                   int neumann, const float *spacing, float *out, void *stream);
+/* out = y0 + sum_j coef[j]*k[j] (float32 partial sums, state precision for the final add); y0 == NULL: out = sum
+ * _runge_kutta_step / _scaled_dot_product                            ShapeID/DiffEqs/rk_common.py:22-61, misc.py:22-25 */
+int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, const float *coef_host, int n_terms,
+                   int64_t n, void *out, int out_is_double, void *stream);
+/* result_dev[0] = sum((err / (atol + rtol*max(|y0|,|y1|)))^2)         ShapeID/DiffEqs/misc.py:146-157 */
+int bfm_rk_error_sum(const float *err, const void *y0, const void *y1, int is_double, int64_t n, double rtol,
+                     double atol, double *result_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
