@@ -20,10 +20,10 @@ from torch.utils.data import Dataset
 
 from .. import _lib, io as bio
 from ..draws import HostDraws
-from ..plan import Arena, band_host, fill_zoom_tab, zoom_newsize, zoom_tables_host
+from ..plan import Arena, band_host, device_tables, set_zoom_tab, zoom_newsize
 from . import constants as K
 from .utils import (DeformDict, DeformPlan, _stream, fast_3D_interp_torch, make_affine_matrix, myzoom_torch,
-                    resolution_sampler)
+                    read_and_deform_image, resolution_sampler)
 
 ct_brightness_group = {
     'darker': [4, 5, 14, 15, 24, 31, 72],
@@ -33,6 +33,10 @@ ct_brightness_group = {
 }
 
 _STOCK_STEPS = ['gamma', 'bias_field', 'resample', 'noise']
+
+# partial-volume blend weights of get_contrast (datasets.py:452): 0.02 * torch.arange(50) in float32
+_PV_V = np.arange(50).astype(np.float32) * np.float32(0.02)
+_PV_W = np.float32(1) - _PV_V
 
 
 class BaseGen(Dataset):
@@ -56,6 +60,10 @@ class BaseGen(Dataset):
         self.rng = draws or HostDraws()
         self.cache = bio.DeviceVolumeCache(self.device)
         self.arena = Arena(self.device)
+        self.tables = device_tables(self.device)
+        self._ws = {}                  # persistent device scratch of the fused chain (see _workspace)
+        self._info = {}                # t1 path -> modality table
+        self._inputs = {}              # volume path -> (img, aff, res)
         self.write_bflog = None        # None: follow the task list; True/False: force
         self.prepare_tasks()
         self.prepare_paths()
@@ -141,6 +149,10 @@ class BaseGen(Dataset):
                                      np.array(range(nn_, nn_ + nlat))])
 
     def get_info(self, t1):
+        hit = self._info.get(t1)
+        if hit is not None:
+            self.modalities = dict(hit)
+            return self.modalities
         stem = t1[:-7]
         self.modalities = {'T1': t1, 'Gen': stem + 'generation_labels.nii',
                            'segmentation': stem + self.gen_args.segment_prefix + '.nii',
@@ -152,6 +164,7 @@ class BaseGen(Dataset):
                             ('CT_DM', 'CT.defacingmask.nii')):
             if bio.exists(stem + suffix):
                 self.modalities[key] = stem + suffix
+        self._info[t1] = dict(self.modalities)
         return self.modalities
 
     # ---- random setup (datasets.py:466-493, 563-590) ---------------------------------------------
@@ -166,9 +179,13 @@ class BaseGen(Dataset):
                 input_mode = m
                 break
         path = self.modalities['Gen' if input_mode == 'synth' else input_mode]
-        img = bio.load(path)
-        aff = img.affine
-        res = np.sqrt(np.sum(abs(aff[:-1, :-1]), axis=0))
+        hit = self._inputs.get(path)
+        if hit is None:
+            img = bio.load(path)
+            aff = img.affine
+            hit = (img, aff, np.sqrt(np.sum(abs(aff[:-1, :-1]), axis=0)))
+            self._inputs[path] = hit
+        img, aff, res = hit
         return dataset_name, case_name, input_mode, img, aff, res, age
 
     def get_setup_params(self):
@@ -194,17 +211,19 @@ class BaseGen(Dataset):
 
     # ---- deformation (datasets.py:187-303) --------------------------------------------------------
     def random_affine_transform(self, shp):
+        """A (3,3) and c2 (3,) as float32 numpy arrays (the reference's float32 tensors, datasets.py:187-201)."""
         a, rng = self.synth_args, self.rng
         rotations = (2 * a.max_rotation * rng.rand3("aff.rot") - a.max_rotation) / 180.0 * np.pi
         shears = (2 * a.max_shear * rng.rand3("aff.shear") - a.max_shear)
         scalings = 1 + (2 * a.max_scaling * rng.rand3("aff.scale") - a.max_scaling)
         scaling_factor_distances = np.prod(scalings) ** .33333333333
-        A = torch.tensor(make_affine_matrix(rotations, shears, scalings), dtype=torch.float)
-        c2 = torch.tensor((np.array(shp[0:3]) - 1) / 2, dtype=torch.float)
+        A = make_affine_matrix(rotations, shears, scalings).astype(np.float32)
+        c2 = ((np.array(shp[0:3]) - 1) / 2).astype(np.float32)
         if a.random_shift:
             max_shift = torch.tensor(np.array(shp[0:3]) - self.size, dtype=torch.float) / 2
             max_shift[max_shift < 0] = 0
-            c2 = c2 + (2 * (max_shift * rng.torch_rand("aff.shift", 3, dtype=torch.float64)) - max_shift)
+            c2 = (torch.from_numpy(c2) + (2 * (max_shift * rng.torch_rand("aff.shift", 3, dtype=torch.float64))
+                                          - max_shift)).to(torch.float32).numpy()
         return scaling_factor_distances, A, c2
 
     def random_nonlinear_transform(self, photo_mode, spac):
@@ -243,11 +262,12 @@ class BaseGen(Dataset):
             if 'surface' in self.tasks:
                 full = self._full_field(Fsmall, setups['photo_mode'])
                 F, Fneg = self._integrate_svf(full), self._integrate_svf(-full)
-        plan = DeformPlan(self.size, shp, A.numpy(), c2.to(torch.float32).numpy(),
+        plan = DeformPlan(self.size, shp, A, c2,
                           None if (Fsmall is None or F is not None) else Fsmall.numpy(), setups['photo_mode'],
                           self.device, F_full=F, arena=arena, lazy=lazy)
-        d = DeformDict({'scaling_factor_distances': scaling_factor_distances, 'A': A.to(self.device),
-                        'c2': c2.to(self.device), 'Fneg': Fneg, '_plan': plan, '_Fsmall': Fsmall})
+        # 'A' and 'c2' (device tensors in the reference) are materialised on first access
+        d = DeformDict({'scaling_factor_distances': scaling_factor_distances, 'Fneg': Fneg, '_plan': plan,
+                        '_Fsmall': Fsmall})
         if F is not None or Fsmall is None:
             d['F'] = F
         return d
@@ -290,6 +310,11 @@ class BaseGen(Dataset):
 
     # ---- contrast (datasets.py:430-464) ------------------------------------------------------------
     def get_contrast(self, photo_mode):
+        """256-entry mean / std tables incl. partial-volume blends (datasets.py:430-464).  The random draws are
+        torch's; the blends are evaluated in numpy float32 with the reference's operation order (every product
+        and sum separately rounded): the means reproduce the torch float32 results bit for bit; the blended
+        stds can differ in the last bit because torch's CPU sqrt (MKL vsSqrt) is not correctly rounded
+        while numpy's is."""
         rng = self.rng
         mus = 25 + 200 * rng.torch_rand("gmm.mu", 256)
         sigmas = 5 + 20 * rng.torch_rand("gmm.sigma", 256)
@@ -301,15 +326,17 @@ class BaseGen(Dataset):
                     mus[l] = v
         if photo_mode or rng.rand1("gmm.bg") < 0.5:
             mus[0] = 0
-        v = 0.02 * torch.arange(50)
-        mus[100:150] = mus[1] * (1 - v) + mus[2] * v
-        mus[150:200] = mus[2] * (1 - v) + mus[3] * v
-        mus[200:250] = mus[3] * (1 - v) + mus[4] * v
-        mus[250] = mus[4]
-        sigmas[100:150] = torch.sqrt(sigmas[1] ** 2 * (1 - v) + sigmas[2] ** 2 * v)
-        sigmas[150:200] = torch.sqrt(sigmas[2] ** 2 * (1 - v) + sigmas[3] ** 2 * v)
-        sigmas[200:250] = torch.sqrt(sigmas[3] ** 2 * (1 - v) + sigmas[4] ** 2 * v)
-        sigmas[250] = sigmas[4]
+        m, sg = mus.numpy(), sigmas.numpy()
+        v, w = _PV_V, _PV_W
+        m[100:150] = m[1] * w + m[2] * v
+        m[150:200] = m[2] * w + m[3] * v
+        m[200:250] = m[3] * w + m[4] * v
+        m[250] = m[4]
+        q = sg[:5] * sg[:5]
+        sg[100:150] = np.sqrt(q[1] * w + q[2] * v)
+        sg[150:200] = np.sqrt(q[2] * w + q[3] * v)
+        sg[200:250] = np.sqrt(q[3] * w + q[4] * v)
+        sg[250] = sg[4]
         return mus, sigmas
 
     # ---- host-side plan of one synthetic sample (all scalar draws, reference order) ----------------
@@ -342,6 +369,7 @@ class BaseGen(Dataset):
             small[1] = int(np.round(size[1] / setups['spac']))
         std = torch.tensor(cfg.bf_std_min + (cfg.bf_std_max - cfg.bf_std_min) * rng.rand1("bf.std"), dtype=torch.float)
         p['bfsmall'] = (std * rng.torch_randn("bf.field", small)).numpy()
+        p['bf_shape'] = small
         # resample
         res = self.res_training_data
         stds = (0.85 + 0.3 * rng.rand("rs.u")) * np.log(5) / np.pi * setups['thickness'] / res
@@ -351,78 +379,114 @@ class BaseGen(Dataset):
         p['factors'] = np.array(p['new_size']) / np.array(size)
         # noise
         u = rng.rand1("noise.u")
-        p['noise_std'] = np.float32(torch.tensor(cfg.noise_std_min + (cfg.noise_std_max - cfg.noise_std_min) * u,
-                                                 dtype=torch.float)[0].item())
+        p['noise_std'] = np.float32((cfg.noise_std_min + (cfg.noise_std_max - cfg.noise_std_min) * u)[0])
         p['eps_noise'] = rng.field_randn("noise.eps")
         p['seed'] = rng.seed64()
         return p
 
     # ---- fused batched launch ----------------------------------------------------------------------
+    def _workspace(self, name, numel, dtype=torch.float32, zero=False):
+        """Persistent device scratch of the fused chain, grown on demand.  Reuse across batches is safe because
+        all work is ordered on one stream; nothing in here is ever returned to the caller."""
+        t = self._ws.get(name)
+        if t is None or t.numel() < numel:
+            t = (torch.zeros if zero else torch.empty)(int(numel), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t
+
     def _build_descs(self, jobs, arena):
-        """Fill one bfm_gen_sample per job (tables and small grids go into the arena).
-        jobs: dicts(plan=DeformPlan, flip, labels, p=<_plan_synth>, want_bflog, want_residual)."""
+        """Fill one bfm_gen_sample per job.  Per sample only the small random grids and the two 256-entry
+        tables travel through the arena; zoom tables come from the device-resident cache, the banded
+        blur-o-downsample tables are built on the GPU (bfm_gen_plan), scratch volumes are persistent.
+        jobs: dicts(plan=DeformPlan, flip, labels, p=<_plan_synth>, want_bflog, want_residual, aux=[(key, vol)])."""
         B = len(jobs)
-        dev, size = self.device, self.size
+        dev, size, tables = self.device, self.size, self.tables
         N = int(np.prod(size))
         descs = (_lib.GenSample * B)()
         out = torch.empty((B, 1, *size), dtype=torch.float32, device=dev)
-        i_bf = torch.empty((B, *size), dtype=torch.float32, device=dev)
-        tmp = torch.empty((B, 2, N), dtype=torch.float32, device=dev)
-        keep = [out, i_bf, tmp]
+        n_bfl = sum(1 for j in jobs if j['want_bflog'])
+        n_res = sum(1 for j in jobs if j['want_residual'])
+        n_aux = sum(len(j.get('aux') or ()) for j in jobs)
+        bfl_all = torch.empty((n_bfl, 1, *size), dtype=torch.float32, device=dev) if n_bfl else None
+        res_all = torch.empty((n_res, 1, *size), dtype=torch.float32, device=dev) if n_res else None
+        aux_all = torch.empty((n_aux, 1, *size), dtype=torch.float32, device=dev) if n_aux else None
+        # persistent scratch: syn is zero-initialised once and afterwards only ever holds finite values
+        src_pad = max(int(np.prod(j['plan'].src)) + j['plan'].src[1] * j['plan'].src[2] + j['plan'].src[2] + 1
+                      for j in jobs)
+        src_pad = (src_pad + 3) // 4 * 4
+        syn_ws = self._workspace('syn', B * src_pad, zero=True)
+        if self._ws.get('syn_stride') != src_pad:      # slots moved: stale data no longer lines up, start clean
+            if 'syn_stride' in self._ws:
+                syn_ws.zero_()
+            self._ws['syn_stride'] = src_pad
+        i_bf_ws = self._workspace('i_bf', B * N)
+        tmp_ws = self._workspace('tmp', B * 2 * N)
+        low_ws = self._workspace('lowres', B * N)
+        raw_ws = self._workspace('aux_raw', n_aux * N) if n_aux else None
+        p_syn, p_ibf, p_tmp, p_low = syn_ws.data_ptr(), i_bf_ws.data_ptr(), tmp_ws.data_ptr(), low_ws.data_ptr()
+        keep = [out, bfl_all, res_all, aux_all]
         results = []
+        k_bfl = k_res = k_aux = 0
         for b, job in enumerate(jobs):
             s, p, plan = descs[b], job['p'], job['plan']
             s.d = plan.struct
             lab = job['labels']
             s.labels = lab.data_ptr()
             s.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
-            s.mu = arena.put(p['mu'].numpy().astype(np.float32))
-            s.sigma = arena.put(p['sigma'].numpy().astype(np.float32))
+            s.mu = arena.put(p['mu'].numpy())
+            s.sigma = arena.put(p['sigma'].numpy())
             if p['eps_gmm'] is not None:
                 e = p['eps_gmm'].to(dev).contiguous()
                 keep.append(e)
                 s.eps_gmm = e.data_ptr()
             s.seed = int(p['seed'])
-            syn = torch.empty(plan.src, dtype=torch.float32, device=dev)
-            keep.append(syn)
-            s.syn = syn.data_ptr()
+            s.syn = p_syn + 4 * b * src_pad
             s.bbox = plan.bbox.data_ptr()
             if p['mix'] is not None:
                 for q in range(4):
                     s.mixw[q] = float(p['mix'][q])
             s.gamma = float(p['gamma'])
             bfs = p['bfsmall']
-            s.bfsmall = arena.put(bfs.astype(np.float32))
-            for a in range(3):
-                s.bs[a] = int(bfs.shape[a])
-            fac = np.array(size) / np.array(bfs.shape)
-            assert tuple(zoom_newsize(bfs.shape, fac)) == tuple(size)
-            fill_zoom_tab(s.btab, arena, [zoom_tables_host(bfs.shape[a], fac[a], size[a]) for a in range(3)])
-            s.i_bf = i_bf[b].data_ptr()
+            s.bfsmall = arena.put(bfs)
+            bshape = bfs.shape
+            s.bs[0], s.bs[1], s.bs[2] = bshape
+            fac = np.array(size) / np.array(bshape)
+            assert tuple(zoom_newsize(bshape, fac)) == tuple(size)
+            set_zoom_tab(s.btab, tables, bshape, fac, size)
+            s.i_bf = p_ibf + 4 * b * N
             sample = {}
             if job['want_bflog']:
-                bfl = torch.empty((1, *size), dtype=torch.float32, device=dev)
-                s.bflog_out = bfl.data_ptr()
-                sample['bias_field_log'] = bfl
+                s.bflog_out = bfl_all[k_bfl].data_ptr()
+                sample['bias_field_log'] = bfl_all[k_bfl]
+                k_bfl += 1
             s.flip = 1 if job['flip'] else 0
             # resolution degradation: banded passes in ascending factor order, identity axes folded away
             new = [int(v) for v in p['new_size']]
             order = sorted(range(3), key=lambda a: new[a] / size[a])
             nb = 0
             for a in order:
-                if new[a] == size[a] and p['stds'][a] == 0:
+                sigma = float(p['stds'][a])
+                if new[a] == size[a] and sigma == 0:
                     s.zero_first[a] = 1
                     continue
-                start, w, T = band_host(size[a], new[a], float(p['stds'][a]))
                 bd = s.band[nb]
-                bd.start, bd.w, bd.T = arena.put(start), arena.put(w), T
+                half = int(np.ceil(3 * sigma)) if sigma > 0 else 0
+                T = 2 * half + 2
+                if T <= 64:
+                    # tables built on the device by bfm_gen_plan into arena scratch
+                    bd.start, _ = arena.reserve(4 * new[a])
+                    bd.w, _ = arena.reserve(4 * new[a] * T)
+                    bd.T, bd.build, bd.sigma = T, 1, sigma
+                else:
+                    start, w, T = band_host(size[a], new[a], sigma)
+                    bd.start, bd.w, bd.T, bd.build = arena.put(start), arena.put(w), T, 0
                 bd.n_in, bd.n_out, bd.axis = size[a], new[a], a
                 nb += 1
             if nb == 0:
                 bd = s.band[0]
                 bd.start = arena.put(np.arange(size[2], dtype=np.int32))
                 bd.w = arena.put(np.ones(size[2], dtype=np.float32))
-                bd.T, bd.n_in, bd.n_out, bd.axis = 1, size[2], size[2], 2
+                bd.T, bd.n_in, bd.n_out, bd.axis, bd.build = 1, size[2], size[2], 2, 0
                 nb = 1
             s.n_band = nb
             s.noise_std = float(p['noise_std'])
@@ -430,48 +494,60 @@ class BaseGen(Dataset):
                 e = p['eps_noise'].to(dev).contiguous()
                 keep.append(e)
                 s.eps_noise = e.data_ptr()
-            s.tmp[0] = tmp[b, 0].data_ptr()
-            s.tmp[1] = tmp[b, 1].data_ptr()
-            low = torch.empty(new, dtype=torch.float32, device=dev)
-            keep.append(low)
-            s.lowres = low.data_ptr()
-            for a in range(3):
-                s.new_size[a] = new[a]
+            s.tmp[0] = p_tmp + 4 * (2 * b) * N
+            s.tmp[1] = p_tmp + 4 * (2 * b + 1) * N
+            s.lowres = p_low + 4 * b * N
+            s.new_size[0], s.new_size[1], s.new_size[2] = new
             up = 1 / p['factors']
             assert tuple(zoom_newsize(new, up)) == tuple(size), (new, up)
-            fill_zoom_tab(s.utab, arena, [zoom_tables_host(new[a], up[a], size[a]) for a in range(3)])
+            set_zoom_tab(s.utab, tables, new, up, size)
             s.maxval, _ = arena.reserve(16)
             s.out = out[b].data_ptr()
             if job['want_residual']:
-                r = torch.empty((1, *size), dtype=torch.float32, device=dev)
-                s.residual = r.data_ptr()
-                sample['high_res_residual'] = r
+                s.residual = res_all[k_res].data_ptr()
+                sample['high_res_residual'] = res_all[k_res]
+                k_res += 1
+            # real-image targets warped by the same gather (read_and_deform_image)
+            aux = job.get('aux') or ()
+            s.n_aux = len(aux)
+            job['aux_out'] = {}
+            if aux:
+                s.aux_mm, _ = arena.reserve(8 * _lib.MAX_AUX)
+            for c, (key, vol) in enumerate(aux):
+                s.aux_src[c] = vol.data_ptr()
+                s.aux_raw[c] = raw_ws.data_ptr() + 4 * k_aux * N
+                s.aux_out[c] = aux_all[k_aux].data_ptr()
+                job['aux_out'][key] = aux_all[k_aux]
+                k_aux += 1
             sample['input'] = out[b]
-            job['_lowres'], job['_i_bf'] = low, i_bf[b]
+            job['_new_size'] = new
             # key order of the reference's sample dict (datasets.py:345-352)
             results.append({k: sample[k] for k in ('high_res_residual', 'input', 'bias_field_log') if k in sample})
         self._keep = keep
         return descs, results
 
     def _run_chain(self, jobs, arena, targets_fn=None, timers=None):
-        """Planned jobs -> device.  Stage order: bbox (batched) -> targets_fn() (per-sample target kernels, which
-        need the bbox and may feed the mixing step) -> gmm -> warp -> resample -> finish (all batched)."""
+        """Planned jobs -> device.  Stage order: plan + bbox (batched) -> targets_fn() (per-sample target
+        kernels, which need the bbox and may feed the mixing step) -> gmm -> warp -> resample -> finish (all
+        batched)."""
         L = _lib.lib()
         B = len(jobs)
         descs, results = self._build_descs(jobs, arena)
         d_dev = arena.put_struct_array(descs)
         arena.commit()
         h = C.addressof(descs)
+        st = _stream()
 
         def stage(name, fn, dptr):
             if timers is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            _lib.check(fn(h, dptr, B, _stream()))
+            _lib.check(fn(h, dptr, B, st))
             if timers is not None:
                 e1.record()
                 timers.setdefault(name, []).append((e0, e1))
 
+        stage('plan', L.bfm_gen_plan, d_dev)
         stage('bbox', L.bfm_gen_bbox, d_dev)
         for job in jobs:
             job['plan'].have_bbox = True
@@ -623,13 +699,32 @@ class BaseGen(Dataset):
         if target is None:
             target = defaultdict(default)
         target['name'] = ctx['case_name']
+        fused = ctx.get('fused_job')
         for key in ('T1', 'T2', 'FLAIR'):
-            target.update(self.read_and_deform_target(idx, target.keys(), key, input_mode, setups, deform_dict))
+            if fused is not None and key in fused['aux_out']:
+                target[key] = fused['aux_out'][key]          # written by the fused chain (warp + finish stages)
+            else:
+                target.update(self.read_and_deform_target(idx, target.keys(), key, input_mode, setups, deform_dict))
         for task_name in self.tasks:
             if task_name in K.processing_funcs.keys() and task_name not in ['T1', 'T2', 'FLAIR']:
                 target.update(self.read_and_deform_target(idx, target.keys(), task_name, input_mode, setups,
                                                           deform_dict))
         return target
+
+    def _fused_image_targets(self, ctx, jobs):
+        """Real-image targets (T1/T2/FLAIR, read_and_deform_image) that can ride on the synthetic image's gather:
+        stock reader, no defacing mask, no hemisphere mask, same volume shape, and no job of this item mixes real
+        modalities into the synthetic image (mixing needs the normalised targets BEFORE the warp)."""
+        if self.hemis_mask is not None or any(j['p']['mix'] is not None for j in jobs):
+            return []
+        mods, plan, out = ctx['modalities'], ctx['deform']['_plan'], []
+        for key in ('T1', 'T2', 'FLAIR'):
+            if key not in mods or (key + '_DM') in mods or K.processing_funcs.get(key) is not read_and_deform_image:
+                continue
+            vol = self.cache.get(mods[key], 'f32')
+            if list(vol.shape[:3]) == plan.src:
+                out.append((key, vol))
+        return out[:_lib.MAX_AUX]
 
     def _real_input(self, input_mode, setups, deform_dict, res, target):
         from .utils import read_and_deform
@@ -677,6 +772,10 @@ class BaseGen(Dataset):
                 jobs.append(self._job(ctx['setups'], ctx['deform'], ctx['target'],
                                       self._plan_synth(ctx['setups'], ctx['target'])))
             spans.append((first, len(jobs)))
+            aux = self._fused_image_targets(ctx, jobs[first:])
+            if aux:
+                jobs[first]['aux'] = aux
+                ctx['fused_job'] = jobs[first]
 
         def run_targets():
             for n, ctx in enumerate(ctxs):

@@ -9,7 +9,7 @@ import torch
 
 from .. import _lib, io as bio
 from ..draws import HostDraws
-from ..plan import (band_host, fill_deform, gaussian_taps_host, zoom_newsize, zoom_tables_host)
+from ..plan import (band_host, device_tables, fill_deform, gaussian_taps_host, zoom_newsize, zoom_tables_host)
 
 _DRAWS = HostDraws()
 
@@ -209,14 +209,17 @@ class DeformPlan:
         self.F_full = F_full
         self.struct = _lib.Deform()
         fptr = F_full.data_ptr() if F_full is not None else None
+        tables = device_tables(self.device)
         if arena is not None:
-            # tables live in the caller's arena slot: valid until that slot is recycled
-            fill_deform(self.struct, arena, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr)
+            # the small grid lives in the caller's arena slot: valid until that slot is recycled
+            fill_deform(self.struct, arena, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr,
+                        tables=tables)
             addr, off = arena.reserve(32)
             self.bbox = arena.view(off, 8, torch.int32)
         else:
             ar = _MiniArena(self.device)
-            fill_deform(self.struct, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr)
+            fill_deform(self.struct, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr,
+                        tables=tables)
             ar.finalize()
             self._keep = ar.dev
             self.bbox = torch.empty(8, dtype=torch.int32, device=self.device)
@@ -250,6 +253,9 @@ class DeformDict(dict):
 
     def __missing__(self, key):
         plan = dict.__getitem__(self, '_plan')
+        if key in ('A', 'c2'):
+            self[key] = torch.from_numpy(np.array(plan.A_host if key == 'A' else plan.c2_host)).to(plan.device)
+            return self[key]
         if key == 'grid':
             xx2, yy2, zz2 = plan.coords()
             x1, y1, z1, x2, y2, z2 = plan.bbox_host()

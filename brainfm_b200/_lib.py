@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BFM_LIB") or os.path.join(_HERE, "libbfm.so")
 
 BFM_OK, BFM_E_INVALID, BFM_E_UNSUPPORTED, BFM_E_CUDA = 0, -1, -2, -3
+ABI_VERSION = 2
 
 c_f = C.c_float
 c_i = C.c_int
@@ -26,7 +27,11 @@ class Deform(C.Structure):
 
 
 class Band(C.Structure):
-    _fields_ = [("start", c_p), ("w", c_p), ("T", c_i), ("n_in", c_i), ("n_out", c_i), ("axis", c_i)]
+    _fields_ = [("start", c_p), ("w", c_p), ("T", c_i), ("n_in", c_i), ("n_out", c_i), ("axis", c_i),
+                ("build", c_i), ("sigma", C.c_double)]
+
+
+MAX_AUX = 3
 
 
 class GenSample(C.Structure):
@@ -38,7 +43,9 @@ class GenSample(C.Structure):
                 ("i_bf", c_p), ("bflog_out", c_p), ("flip", c_i),
                 ("band", Band * 3), ("n_band", c_i), ("zero_first", c_i * 3),
                 ("noise_std", c_f), ("eps_noise", c_p), ("tmp", c_p * 2), ("lowres", c_p), ("new_size", c_i * 3),
-                ("utab", ZoomTab), ("maxval", c_p), ("out", c_p), ("residual", c_p)]
+                ("utab", ZoomTab), ("maxval", c_p), ("out", c_p), ("residual", c_p),
+                ("n_aux", c_i), ("aux_src", c_p * MAX_AUX), ("aux_raw", c_p * MAX_AUX), ("aux_out", c_p * MAX_AUX),
+                ("aux_mm", c_p)]
 
 
 class BfmError(RuntimeError):
@@ -56,12 +63,15 @@ _PROTOS = {
     "bfm_zoom_linear": (c_i, [c_p, c_i, c_i, c_i, c_i] + [c_p, c_p, c_p, c_p, c_i] * 3 + [c_p, c_p]),
     "bfm_blur_axis": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     "bfm_band_axis": (c_i, [c_p, c_p, C.POINTER(c_i), c_i, c_i, c_p, c_p, c_i, c_f, c_p, c_u64, c_p]),
+    "bfm_sanitize_f32": (c_i, [c_p, c_i64, c_p]),
+    "bfm_band_build": (c_i, [c_i, c_i, C.c_double, c_i, c_p, c_p, c_p]),
     "bfm_minmax": (c_i, [c_p, c_i64, c_p, c_p]),
     "bfm_shift_scale_flip": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p, c_f, c_i, c_p]),
     "bfm_deform_grid": (c_i, [C.POINTER(Deform), c_p, c_p, c_p]),
     "bfm_warp_volume": (c_i, [C.POINTER(Deform), c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p, c_p]),
     "bfm_label_warp_onehot": (c_i, [C.POINTER(Deform), c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
     "bfm_svf_step": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "bfm_gen_plan": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_bbox": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_gmm": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_warp": (c_i, [c_p, c_p, c_i, c_p]),
@@ -97,7 +107,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.bfm_abi_version() != 1:
+        if L.bfm_abi_version() != ABI_VERSION:
             raise BfmError("libbfm.so ABI mismatch")
         _lib = L
     return _lib

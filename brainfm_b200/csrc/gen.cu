@@ -36,6 +36,76 @@ __global__ void k_gen_bbox_init(const bfm_gen_sample *__restrict__ S) {
     else if (threadIdx.x < 6) bb[threadIdx.x] = 0;
     else if (threadIdx.x == 6) bb[6] = 1;                   // 1 = full scan still required
     if (threadIdx.x == 7) *S[blockIdx.x].maxval = 0.f;      // chain values are >= 0 after the noise clamp
+    if (threadIdx.x >= 8 && threadIdx.x < 8 + 2 * S[blockIdx.x].n_aux) {
+        const int q = threadIdx.x - 8;
+        S[blockIdx.x].aux_mm[q] = (q & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- plan
+// Banded map of one axis = (zero-padded Gaussian correlation, utils.py:74-94) followed by (masked 2-tap linear
+// sampling at the float64 np.arange positions, utils.py:595-605), built on the device: one block per
+// (pass, sample).  Same construction as brainfm_b200.plan.band_host (which the op-level API still uses).
+__device__ __forceinline__ void build_band(int n_in, int n_out, int T, double sigma, int *start, float *w) {
+    __shared__ float g[64];
+    __shared__ float gsum;
+    const int half = (T - 2) / 2, L = 2 * half + 1;
+    if (L > 64) return;                                    // rejected on the host
+    if (sigma > 0.0) {
+        // make_gaussian_kernel: float32 tensor ops, the python-float sigma enters as a float32 scalar
+        const float sg = (float)sigma;
+        for (int t = threadIdx.x; t < L; t += blockDim.x) {
+            const float q = __fdiv_rn((float)(t - half), sg);
+            g[t] = expf(-__fmul_rn(__fmul_rn(q, q), 0.5f));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double acc = 0.0;
+            for (int t = 0; t < L; ++t) acc += (double)g[t];
+            gsum = (float)acc;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < L; t += blockDim.x) g[t] = __fdiv_rn(g[t], gsum);
+    } else if (threadIdx.x == 0) {
+        g[0] = 1.f;
+    }
+    __syncthreads();
+    // np.arange(delta, delta + n_out/f, 1/f)[:n_out] in float64: start + i*((start+step) - start)
+    const double f = (double)n_out / (double)n_in;
+    const double delta = (1.0 - f) / (2.0 * f), step = 1.0 / f;
+    const double dd = (delta + step) - delta;
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        const float v = (float)(delta + (double)o * dd);
+        const bool ok = (v > 0.f) && (v <= (float)(n_in - 1));
+        const float fx = floorf(v);
+        const int lo = (int)fx, hi = min(lo + 1, n_in - 1);
+        const float wh = __fsub_rn(v, fx), wl = __fsub_rn(1.f, wh);
+        start[o] = lo - half;
+        float *wr = w + (size_t)o * T;
+        const bool shift = hi != lo;
+        for (int t = 0; t < T; ++t) {
+            double acc = 0.0;
+            if (ok) {
+                if (t < L) acc += (double)wl * (double)g[t];
+                if (shift) { if (t >= 1) acc += (double)wh * (double)g[t - 1]; }
+                else if (t < L) acc += (double)wh * (double)g[t];
+            }
+            wr[t] = (float)acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_gen_plan(const bfm_gen_sample *__restrict__ S) {
+    const bfm_gen_sample &s = S[blockIdx.y];
+    const int pass = blockIdx.x;
+    if (pass >= s.n_band) return;
+    const bfm_band &b = s.band[pass];
+    if (!b.build) return;
+    build_band(b.n_in, b.n_out, b.T, b.sigma, const_cast<int *>(b.start), const_cast<float *>(b.w));
+}
+
+__global__ void __launch_bounds__(128) k_band_build(int n_in, int n_out, int T, double sigma, int *start, float *w) {
+    build_band(n_in, n_out, T, sigma, start, w);
 }
 
 // all three zoom passes for one voxel -- same operations as the row-wise evaluation
@@ -320,78 +390,223 @@ __global__ void __launch_bounds__(256) k_gen_gmm(const bfm_gen_sample *__restric
 // ---------------------------------------------------------------------------------------------- warp
 // pow / exp forms: ex2.approx(gamma * lg2.approx(x)) and ex2.approx(x*log2e); relative error ~1e-6, inside the
 // 1e-5 parity tolerance (the reference's own CPU and CUDA pow differ at that level).
-__device__ __forceinline__ float fast_pow(float x, float g) { return exp2f(g * __log2f(x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_pow(float x, float g) { return ex2_approx(g * lg2_approx(x)); }
 
+// Thread = one z index k, persistent over the rows (i, j0..j1) of its block: everything that depends only on k
+// (third-pass zoom entries of the deformation and bias grids, centred coordinate) lives in registers for the
+// whole block; everything that depends only on i (first zoom pass over the small grids) is evaluated once per
+// block into shared memory; everything that depends only on (i, j) (second pass) once per row, kWR rows per
+// barrier, double buffered.  A voxel then costs the third pass + affine + 8 (+8 per real-image target) gathers.
+//
+// Gathers always read the (lo, lo+1) pair per axis: when lo is the last index of the crop the coordinate sits
+// exactly on it, the hi weight is 0 and hi = min(lo+1, n-1) (utils.py:148-149) contributes nothing; the buffers
+// carry tail padding and only finite values so that 0 * neighbour == 0.
+// The coordinate path keeps the reference's separately rounded operations (bit-exact coordinates); the
+// interpolation of VALUES uses a + w*(b-a) with one FMA per lerp (<= 1 ulp from the reference's w0*a + w1*b).
+constexpr int kWR = 4;            // rows per barrier
+constexpr int kT2 = 128;          // floats per second-pass row: 3*fs[2] + bs[2] <= kT2
 #ifndef WARP_MINB
 #define WARP_MINB 3
 #endif
-template <bool MIX, bool BFL>
-__global__ void __launch_bounds__(kRowWarps * 32, WARP_MINB)
-k_gen_warp(const bfm_gen_sample *__restrict__ S, int fstride, int bstride) {
-    extern __shared__ float smem[];
-    __shared__ bfm_gen_sample sd;
-    {   // each instantiation handles the samples of its own kind
-        const bfm_gen_sample *sp = S + blockIdx.y;
-        if ((sp->mix[0] != nullptr) != MIX || (sp->bflog_out != nullptr) != BFL) return;
-    }
-    stage_desc(&sd, S + blockIdx.y);
-    const bfm_gen_sample &s = sd;
+
+struct WarpShared {
+    bfm_gen_sample sd;
+    float t2[2][kWR][kT2];
+    float red[8][2 * BFM_MAX_AUX];
+};
+
+// FIELD: 0 = affine only, 1 = small random grid zoomed on the fly, 2 = full-resolution (SVF-integrated) field
+template <int NAUX, bool MIX, int FIELD>
+__device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B, int rpb) {
+    const bfm_gen_sample &s = sh.sd;
     const bfm_deform &d = s.d;
     const DefRegs g = load_def(d);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *smF = smem + warp * kRowsPerWarp * (fstride + bstride);
-    float *smB = smF + kRowsPerWarp * fstride;
-    const int n_rows = g.s0 * g.s1;
-    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
-    if (row0 >= n_rows) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int i = blockIdx.y;
+    const int j0 = blockIdx.x * rpb, j1 = min(j0 + rpb, g.s1);
     const float *__restrict__ bfsmall = s.bfsmall;
-    const int bs2 = s.bs[2];
-    if (bfsmall) {
-#pragma unroll
-        for (int r = 0; r < kRowsPerWarp; ++r) {
-            const int row = min(row0 + r, n_rows - 1);
-            row_zoom_setup(bfsmall, s.bs[1], bs2, 1, s.btab, row / g.s1, row % g.s1, smB + r * bs2, lane);
-        }
+    const int fw = FIELD == 1 ? d.fs[2] * 3 : 0;      // floats per row of the deformation small grid
+    const int bw = bfsmall ? s.bs[2] : 0;
+    // ---- first zoom pass (axis 0) at this i: t1F[y][z*3+c], t1B[y][z]                 utils.py:239-240
+    if (FIELD == 1) {
+        const int lo = __ldg(d.ftab.lo[0] + i), hi = __ldg(d.ftab.hi[0] + i);
+        const float wl = __ldg(d.ftab.wl[0] + i), wh = __ldg(d.ftab.wh[0] + i);
+        const int n = d.fs[1] * fw;
+        const float *a = g.fsmall + lo * n, *b = g.fsmall + hi * n;
+        for (int q = tid; q < n; q += blockDim.x) t1F[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
     }
+    if (bw) {
+        const int lo = __ldg(s.btab.lo[0] + i), hi = __ldg(s.btab.hi[0] + i);
+        const float wl = __ldg(s.btab.wl[0] + i), wh = __ldg(s.btab.wh[0] + i);
+        const int n = s.bs[1] * bw;
+        const float *a = bfsmall + lo * n, *b = bfsmall + hi * n;
+        for (int q = tid; q < n; q += blockDim.x) t1B[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
+    }
+    __syncthreads();
+    // ---- second pass (axis 1) for kWR rows starting at jj into buffer `buf`           utils.py:241-243
+    auto ypass = [&](int jj, int buf) {
+        for (int r = warp; r < kWR; r += nwarps) {
+            const int j = min(jj + r, g.s1 - 1);
+            float *row = sh.t2[buf][r];
+            if (FIELD == 1) {
+                const int lo = __ldg(d.ftab.lo[1] + j) * fw, hi = __ldg(d.ftab.hi[1] + j) * fw;
+                const float wl = __ldg(d.ftab.wl[1] + j), wh = __ldg(d.ftab.wh[1] + j);
+                for (int q = lane; q < fw; q += 32) row[q] = lerp_rn(wl, t1F[lo + q], wh, t1F[hi + q]);
+            }
+            if (bw) {
+                const int lo = __ldg(s.btab.lo[1] + j) * bw, hi = __ldg(s.btab.hi[1] + j) * bw;
+                const float wl = __ldg(s.btab.wl[1] + j), wh = __ldg(s.btab.wh[1] + j);
+                for (int q = lane; q < bw; q += 32) row[fw + q] = lerp_rn(wl, t1B[lo + q], wh, t1B[hi + q]);
+            }
+        }
+    };
     const BoxRegs box = load_box(s.bbox, d.src[1], d.src[2]);
+    const int origin = box.b0 * box.n1n2 + box.b1 * box.n2 + box.b2;
     const float *__restrict__ syn = s.syn;
     const float *__restrict__ mix0 = s.mix[0], *__restrict__ mix1 = s.mix[1], *__restrict__ mix2 = s.mix[2];
     const float mw0 = s.mixw[0], mw1 = s.mixw[1], mw2 = s.mixw[2], mw3 = s.mixw[3];
     const float gamma = s.gamma;
     float *__restrict__ i_bf = s.i_bf;
-    float *__restrict__ bfl = s.bflog_out;
-    const int flip = s.flip;
-    const int *__restrict__ blo = s.btab.lo[2], *__restrict__ bhi = s.btab.hi[2];
-    const float *__restrict__ bwl = s.btab.wl[2], *__restrict__ bwh = s.btab.wh[2];
-    int klo = 0, khi = 0;
-    float kwl = 0.f, kwh = 0.f;
-    deform_rows<kRowsPerWarp>(
-        d, g, smF, row0, n_rows, lane,
-        [&](int k) {
-            if (bfsmall) { klo = __ldg(blo + k); khi = __ldg(bhi + k); kwl = __ldg(bwl + k); kwh = __ldg(bwh + k); }
-        },
-        [&](int r, int row, int i, int j, int k, float px, float py, float pz) {
-            const Taps32 t = make_taps32(px, py, pz, box);
-            float v = trilerp32(t, [&](int e) { return __ldg(syn + e); });
-            v = t.ok ? v : 0.f;
-            const int p = row * g.s2 + k;
-            if (MIX) {                                        // datasets.py:379-388
-                v = __fadd_rn(__fmul_rn(mw0, v), __fmul_rn(mw1, mix0[p]));
-                if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[p]));
-                if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[p]));
+    float *__restrict__ bfl = bw ? s.bflog_out : nullptr;
+    const float *__restrict__ asrc[NAUX > 0 ? NAUX : 1];
+    float *__restrict__ araw[NAUX > 0 ? NAUX : 1];
+    float amin[NAUX > 0 ? NAUX : 1], amax[NAUX > 0 ? NAUX : 1];
+#pragma unroll
+    for (int c = 0; c < NAUX; ++c) { asrc[c] = s.aux_src[c]; araw[c] = s.aux_raw[c]; amin[c] = INFINITY; amax[c] = -INFINITY; }
+    const float xc = __fsub_rn((float)i, g.ctr0);
+    const int plane_in = i * g.s1, plane_out = (s.flip ? g.s0 - 1 - i : i) * g.s1;
+    const bool photo = g.photo != 0;
+
+    for (int k0 = 0; k0 < g.s2; k0 += blockDim.x) {
+        const int k = k0 + tid;
+        const bool kv = k < g.s2;
+        const int kk = kv ? k : g.s2 - 1;
+        // ---- everything that only depends on k
+        int zlo = 0, zhi = 0, blo = 0, bhi = 0;
+        float zwl = 0.f, zwh = 0.f, bwl = 0.f, bwh = 0.f;
+        if (FIELD == 1) {
+            zlo = __ldg(d.ftab.lo[2] + kk) * 3; zhi = __ldg(d.ftab.hi[2] + kk) * 3;
+            zwl = __ldg(d.ftab.wl[2] + kk); zwh = __ldg(d.ftab.wh[2] + kk);
+        }
+        if (bw) {
+            blo = fw + __ldg(s.btab.lo[2] + kk); bhi = fw + __ldg(s.btab.hi[2] + kk);
+            bwl = __ldg(s.btab.wl[2] + kk); bwh = __ldg(s.btab.wh[2] + kk);
+        }
+        const float zc = __fsub_rn((float)kk, g.ctr2);
+        int buf = 0;
+        ypass(j0, 0);
+        __syncthreads();
+        for (int jj = j0; jj < j1; jj += kWR) {
+            if (jj + kWR < j1) ypass(jj + kWR, buf ^ 1);
+            const float *rows = &sh.t2[buf][0][0];
+            const float *rzlo = rows + zlo, *rzhi = rows + zhi, *rblo = rows + blo, *rbhi = rows + bhi;
+            int p = (plane_in + jj) * g.s2 + kk;                   // element index of (i, jj, k)
+            int po = (plane_out + jj) * g.s2 + kk;
+#pragma unroll
+            for (int r = 0; r < kWR; ++r, p += g.s2, po += g.s2) {
+                const int j = jj + r;
+                if (j >= j1) break;
+                float x1 = xc, y1 = __fsub_rn((float)j, g.ctr1), z1 = zc;
+                if (FIELD == 2) {
+                    const float *f = g.F_full + (int64_t)p * 3;
+                    x1 = __fadd_rn(x1, __ldg(f)); y1 = __fadd_rn(y1, __ldg(f + 1)); z1 = __fadd_rn(z1, __ldg(f + 2));
+                } else if (FIELD == 1) {                                     // third pass (axis 2), utils.py:244-246
+                    const float f0 = lerp_rn(zwl, rzlo[r * kT2], zwh, rzhi[r * kT2]);
+                    const float f1 = photo ? 0.f : lerp_rn(zwl, rzlo[r * kT2 + 1], zwh, rzhi[r * kT2 + 1]);
+                    const float f2 = lerp_rn(zwl, rzlo[r * kT2 + 2], zwh, rzhi[r * kT2 + 2]);
+                    x1 = __fadd_rn(x1, f0); y1 = __fadd_rn(y1, f1); z1 = __fadd_rn(z1, f2);
+                }
+                float px, py, pz;
+                affine_clamp(g, x1, y1, z1, px, py, pz);
+                // ---- trilinear taps relative to the crop (fast_3D_interp_torch, utils.py:140-192)
+                const float rx = __fsub_rn(px, box.l0), ry = __fsub_rn(py, box.l1), rz = __fsub_rn(pz, box.l2);
+                const bool ok = (rx > 0.f) & (ry > 0.f) & (rz > 0.f) & (rx <= box.h0) & (ry <= box.h1) & (rz <= box.h2);
+                const int ix = __float2int_rd(rx), iy = __float2int_rd(ry), iz = __float2int_rd(rz);
+                const float ax = __fsub_rn(rx, (float)ix), ay = __fsub_rn(ry, (float)iy), az = __fsub_rn(rz, (float)iz);
+                const int e00 = ok ? origin + ix * box.n1n2 + iy * box.n2 + iz : origin;
+                const int e10 = e00 + box.n1n2, e01 = e00 + box.n2, e11 = e10 + box.n2;   // e<x><y>
+                auto gather = [&](const float *__restrict__ X) {
+                    const float v000 = __ldg(X + e00), v001 = __ldg(X + e00 + 1);
+                    const float v100 = __ldg(X + e10), v101 = __ldg(X + e10 + 1);
+                    const float v010 = __ldg(X + e01), v011 = __ldg(X + e01 + 1);
+                    const float v110 = __ldg(X + e11), v111 = __ldg(X + e11 + 1);
+                    const float c00 = fmaf(ax, v100 - v000, v000), c01 = fmaf(ax, v101 - v001, v001);
+                    const float c10 = fmaf(ax, v110 - v010, v010), c11 = fmaf(ax, v111 - v011, v011);
+                    const float c0 = fmaf(ay, c10 - c00, c00), c1 = fmaf(ay, c11 - c01, c01);
+                    const float v = fmaf(az, c1 - c0, c0);
+                    return ok ? v : 0.f;
+                };
+                float v = gather(syn);
+                if (MIX) {                                        // datasets.py:379-388
+                    v = __fadd_rn(__fmul_rn(mw0, v), __fmul_rn(mw1, mix0[p]));
+                    if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[p]));
+                    if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[p]));
+                }
+                v = fmaxf(v, 0.f);                                // datasets.py:411
+                // gamma: 300 * (I/300) ** gamma                  utils.py:568-572
+                v = 300.f * fast_pow(v * (1.f / 300.f), gamma);
+                // bias field: I * exp(zoom(BFsmall))             utils.py:574-589
+                float bl = 0.f;
+                if (bw) {
+                    bl = lerp_rn(bwl, rblo[r * kT2], bwh, rbhi[r * kT2]);
+                    v *= ex2_approx(bl * 1.4426950408889634f);
+                }
+                if (kv) {
+                    i_bf[p] = v;
+                    if (bfl) bfl[po] = bl;
+                }
+#pragma unroll
+                for (int c = 0; c < NAUX; ++c) {                  // read_and_deform_image: raw warp + min/max
+                    const float a = gather(asrc[c]);
+                    if (kv) araw[c][p] = a;
+                    amin[c] = fminf(amin[c], a);                  // (k >= s2 lanes repeat the last voxel)
+                    amax[c] = fmaxf(amax[c], a);
+                }
             }
-            v = v < 0.f ? 0.f : v;                            // datasets.py:411
-            // gamma: 300 * (I/300) ** gamma                  utils.py:568-572
-            v = 300.f * fast_pow(v * (1.f / 300.f), gamma);
-            // bias field: I * exp(zoom(BFsmall))             utils.py:574-589
-            if (bfsmall) {
-                const float *sb = smB + r * bs2;
-                const float bl = lerp_rn(kwl, sb[klo], kwh, sb[khi]);
-                v *= exp2f(bl * 1.4426950408889634f);
-                if (BFL) bfl[((flip ? g.s0 - 1 - i : i) * g.s1 + j) * g.s2 + k] = bl;
-            }
-            i_bf[p] = v;
-        });
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    if (NAUX > 0) {
+#pragma unroll
+        for (int c = 0; c < NAUX; ++c) {
+            const float lo = warp_min(amin[c]), hi = warp_max(amax[c]);
+            if (lane == 0) { sh.red[warp][2 * c] = lo; sh.red[warp][2 * c + 1] = hi; }
+        }
+        __syncthreads();
+        if (tid < 2 * NAUX) {
+            float v = sh.red[0][tid];
+            for (int w = 1; w < nwarps; ++w) v = (tid & 1) ? fmaxf(v, sh.red[w][tid]) : fminf(v, sh.red[w][tid]);
+            if (tid & 1) atomicMax(s.aux_mm + tid, f2ord(v));
+            else atomicMin(s.aux_mm + tid, f2ord(v));
+        }
+    }
+}
+
+template <int NAUX, bool MIX>
+__global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sample *__restrict__ S, int rpb, int t1f_cap) {
+    extern __shared__ float smem[];
+    __shared__ WarpShared sh;
+    {   // each instantiation handles the samples of its own kind
+        const bfm_gen_sample *sp = S + blockIdx.z;
+        if ((sp->mix[0] != nullptr) != MIX || sp->n_aux != NAUX) return;
+        if ((int)blockIdx.y >= sp->d.size[0] || (int)blockIdx.x * rpb >= sp->d.size[1]) return;
+    }
+    stage_desc(&sh.sd, S + blockIdx.z);
+    float *t1F = smem, *t1B = smem + t1f_cap;
+    if (sh.sd.d.F_full) warp_rows<NAUX, MIX, 2>(sh, t1F, t1B, rpb);
+    else if (sh.sd.d.fsmall) warp_rows<NAUX, MIX, 1>(sh, t1F, t1B, rpb);
+    else warp_rows<NAUX, MIX, 0>(sh, t1F, t1B, rpb);
 }
 
 // ---------------------------------------------------------------------------------------------- resample
@@ -503,6 +718,13 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_upsample(const bfm_gen_s
         const float rmx = WRITE ? __frcp_rn(*s.maxval) : 1.f;
         float *__restrict__ outp = s.out;
         float *__restrict__ resid = s.residual;
+        const int n_aux = WRITE ? s.n_aux : 0;
+        float amn[BFM_MAX_AUX], arg[BFM_MAX_AUX];
+#pragma unroll
+        for (int c = 0; c < BFM_MAX_AUX; ++c) {
+            amn[c] = c < n_aux ? ord2f(s.aux_mm[2 * c]) : 0.f;
+            arg[c] = c < n_aux ? __fsub_rn(ord2f(s.aux_mm[2 * c + 1]), amn[c]) : 1.f;
+        }
         const float *__restrict__ hr = s.i_bf;
         int obase[kRowsPerWarp];
 #pragma unroll
@@ -523,6 +745,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_upsample(const bfm_gen_s
                     const float y = v * rmx;
                     outp[obase[r] + k] = y;
                     if (resid) resid[obase[r] + k] = __fsub_rn(hr[(row0 + r) * s2 + k] * rmx, y);   // datasets.py:345-347
+#pragma unroll
+                    for (int c = 0; c < BFM_MAX_AUX; ++c)  // Idef -= min; Idef /= max; flip   utils.py:326-329
+                        if (c < n_aux)
+                            s.aux_out[c][obase[r] + k] =
+                                __fdiv_rn(__fsub_rn(__ldg(s.aux_raw[c] + (row0 + r) * s2 + k), amn[c]), arg[c]);
                 } else {
                     hi = fmaxf(hi, v);
                 }
@@ -636,28 +863,78 @@ int bfm_gen_gmm(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *s
     return rc;
 }
 
+int bfm_band_build(int n_in, int n_out, double sigma, int T, int *start, float *w, void *stream) {
+    if (n_in <= 0 || n_out <= 0 || !start || !w || T < 2 || T > 64 || (T & 1) ||
+        T != 2 * (sigma > 0 ? (int)ceil(3 * sigma) : 0) + 2)
+        return fail(BFM_E_INVALID, "%s", "bfm_band_build: T must equal 2*ceil(3*sigma)+2 and be <= 64");
+    k_band_build<<<1, 128, 0, (cudaStream_t)stream>>>(n_in, n_out, T, sigma, start, w);
+    return check_launch("bfm_band_build");
+}
+
+int bfm_gen_plan(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
+    int rc = check_batch(h, d, B);
+    if (rc) return rc;
+    bool any = false;
+    for (int b = 0; b < B; ++b)
+        for (int p = 0; p < h[b].n_band; ++p) {
+            const bfm_band &bd = h[b].band[p];
+            if (!bd.build) continue;
+            any = true;
+            if (bd.T < 2 || bd.T > 65 || (bd.T & 1) || !bd.start || !bd.w || bd.n_in <= 0 || bd.n_out <= 0)
+                return fail(BFM_E_INVALID, "%s", "bfm_gen_plan: bad band descriptor (T must be even, 2..64)");
+        }
+    if (!any) return BFM_OK;
+    k_gen_plan<<<dim3(3, B), 128, 0, (cudaStream_t)stream>>>(d);
+    return check_launch("bfm_gen_plan");
+}
+
 int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
     int rc = check_batch(h, d, B);
     if (rc) return rc;
-    const int fstride = max_fstride(h, B), bstride = max_bstride(h, B);
-    const size_t smem = (size_t)kRowWarps * kRowsPerWarp * (fstride + bstride) * sizeof(float);
-    if (smem > 200 * 1024) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_warp: small grids too deep for shared memory");
-    bool kinds[2][2] = {{false, false}, {false, false}};
-    for (int b = 0; b < B; ++b) kinds[h[b].mix[0] != nullptr][h[b].bflog_out != nullptr] = true;
-    const dim3 grid(rows_grid(h), B);
+    int t1f = 0, t1b = 0, wf = 0, wb = 0, s0 = 0, s1 = 0, s2 = 0;
+    bool kinds[BFM_MAX_AUX + 2] = {false, false, false, false, false};      // n_aux 0..3, then MIX
+    for (int b = 0; b < B; ++b) {
+        const bfm_gen_sample &s = h[b];
+        if (s.n_aux < 0 || s.n_aux > BFM_MAX_AUX || (s.mix[0] && s.n_aux))
+            return fail(BFM_E_INVALID, "%s", "bfm_gen_warp: n_aux must be 0..3 and 0 when mixing");
+        for (int c = 0; c < s.n_aux; ++c)
+            if (!s.aux_src[c] || !s.aux_raw[c] || !s.aux_out[c] || !s.aux_mm)
+                return fail(BFM_E_INVALID, "%s", "bfm_gen_warp: null real-image target buffer");
+        kinds[s.mix[0] ? BFM_MAX_AUX + 1 : s.n_aux] = true;
+        if (s.d.fsmall && !s.d.F_full) {
+            t1f = max(t1f, s.d.fs[1] * s.d.fs[2] * 3);
+            wf = max(wf, s.d.fs[2] * 3);
+        }
+        if (s.bfsmall) {
+            t1b = max(t1b, s.bs[1] * s.bs[2]);
+            wb = max(wb, s.bs[2]);
+        }
+        s0 = max(s0, s.d.size[0]); s1 = max(s1, s.d.size[1]); s2 = max(s2, s.d.size[2]);
+    }
+    const size_t smem = (size_t)(t1f + t1b) * sizeof(float);
+    if (wf + wb > kT2 || smem > 160 * 1024)
+        return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_warp: small grids too large for shared memory");
+    const int threads = min(256, (s2 + 31) / 32 * 32);
+    // rows per block: a multiple of kWR, small enough for >= ~4 waves of blocks
+    int rpb = s1;
+    while (rpb > 8 * kWR && (int64_t)B * s0 * ((s1 + rpb - 1) / rpb) < 4 * 148 * 4) rpb = (rpb / 2 + kWR - 1) / kWR * kWR;
+    if (rpb > 32) rpb = 32;
+    const dim3 grid((s1 + rpb - 1) / rpb, s0, B);
+    if (s0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_warp: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
-#define BFM_LAUNCH_WARP(M, L)                                                                                  \
-    if (kinds[M][L]) {                                                                                         \
+#define BFM_LAUNCH_WARP(IDX, NA, M)                                                                            \
+    if (kinds[IDX]) {                                                                                          \
         if (smem > 40 * 1024)                                                                                  \
-            cudaFuncSetAttribute(k_gen_warp<M, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        k_gen_warp<M, L><<<grid, kRowWarps * 32, smem, st>>>(d, fstride, bstride);                             \
+            cudaFuncSetAttribute(k_gen_warp<NA, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        k_gen_warp<NA, M><<<grid, threads, smem, st>>>(d, rpb, t1f);                                \
         rc = check_launch("bfm_gen_warp");                                                                     \
         if (rc) return rc;                                                                                     \
     }
-    BFM_LAUNCH_WARP(false, false)
-    BFM_LAUNCH_WARP(false, true)
-    BFM_LAUNCH_WARP(true, false)
-    BFM_LAUNCH_WARP(true, true)
+    BFM_LAUNCH_WARP(0, 0, false)
+    BFM_LAUNCH_WARP(1, 1, false)
+    BFM_LAUNCH_WARP(2, 2, false)
+    BFM_LAUNCH_WARP(3, 3, false)
+    BFM_LAUNCH_WARP(4, 0, true)
 #undef BFM_LAUNCH_WARP
     return BFM_OK;
 }
@@ -714,6 +991,7 @@ int bfm_gen_finish(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void
 
 int bfm_gen_run(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
     int rc;
+    if ((rc = bfm_gen_plan(h, d, B, stream))) return rc;
     if ((rc = bfm_gen_bbox(h, d, B, stream))) return rc;
     if ((rc = bfm_gen_gmm(h, d, B, stream))) return rc;
     if ((rc = bfm_gen_warp(h, d, B, stream))) return rc;

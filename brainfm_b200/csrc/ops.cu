@@ -28,6 +28,14 @@ __global__ void k_trilerp_pull(const float *__restrict__ X, int nx, int ny, int 
     }
 }
 
+// torch.nan_to_num in place (Generator/utils.py:305)
+__global__ void k_sanitize(float *__restrict__ x, int64_t n) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[p];
+        if (!(fabsf(v) <= 3.4028234663852886e38f)) x[p] = nan_to_num(v);
+    }
+}
+
 template <typename T>
 __global__ void k_nearest_pull(const T *__restrict__ X, int nx, int ny, int nz, int C,
                                const float *__restrict__ I, const float *__restrict__ J,
@@ -402,6 +410,14 @@ using namespace bfm;
 extern "C" {
 
 int bfm_abi_version(void) { return BFM_ABI_VERSION; }
+
+int bfm_sanitize_f32(float *x, int64_t n, void *stream) {
+    BFM_REQUIRE(x && n >= 0, "bfm_sanitize_f32: null pointer");
+    if (n == 0) return BFM_OK;
+    const int64_t blocks = (n + 4 * 256 - 1) / (4 * 256);
+    k_sanitize<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, n);
+    return check_launch("bfm_sanitize_f32");
+}
 const char *bfm_last_error(void) { return g_err; }
 uint64_t bfm_launch_count(void) { return g_launches.load(); }
 

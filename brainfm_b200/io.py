@@ -91,13 +91,21 @@ def load(path):
 
 class DeviceVolumeCache:
     """path -> device tensor, decoded once.  kinds: 'f32' (images), 'i32' (segmentation labels),
-    'gen' (generation labels: uint8 when every value is an integer in [0,255], else float32)."""
+    'gen' (generation labels: uint8 when every value is an integer in [0,255], else float32).
+
+    'f32' volumes are stored finite (torch.nan_to_num, which the reference applies at every crop read,
+    Generator/utils.py:305, is applied once here) and followed by one plane + one row + one voxel of zero
+    padding, which is what the fused gather kernel (bfm_gen_warp, real-image targets) requires."""
 
     def __init__(self, device, max_bytes=64 << 30):
         self.device = device
         self.max_bytes = max_bytes
         self._d = {}
         self._bytes = 0
+
+    @staticmethod
+    def _pad(shape):
+        return int(shape[1]) * int(shape[2]) + int(shape[2]) + 1 if len(shape) >= 3 else 1
 
     def get(self, path, kind="f32"):
         key = (path, kind)
@@ -107,22 +115,36 @@ class DeviceVolumeCache:
         a = load(path).get_fdata()
         a = np.squeeze(a)
         if kind == "f32":
-            h = torch.from_numpy(np.ascontiguousarray(a.astype(float))).to(torch.float32)
+            h = torch.nan_to_num(torch.from_numpy(np.ascontiguousarray(a.astype(float))).to(torch.float32))
+            buf = torch.zeros(h.numel() + self._pad(h.shape), dtype=torch.float32, device=self.device)
+            buf[:h.numel()].copy_(h.reshape(-1))
+            t = buf[:h.numel()].view(h.shape)
         elif kind == "i32":
-            h = torch.from_numpy(np.ascontiguousarray(a.astype(int))).to(torch.int32)
+            t = torch.from_numpy(np.ascontiguousarray(a.astype(int))).to(torch.int32).to(self.device)
         elif kind == "gen":
             f = a.astype(np.float32)
             if np.all(f == np.round(f)) and f.min() >= 0 and f.max() <= 255:
-                h = torch.from_numpy(np.ascontiguousarray(f.astype(np.uint8)))
+                t = torch.from_numpy(np.ascontiguousarray(f.astype(np.uint8))).to(self.device)
             else:
-                h = torch.from_numpy(np.ascontiguousarray(f))
+                t = torch.from_numpy(np.ascontiguousarray(f)).to(self.device)
         else:
             raise ValueError(kind)
-        t = h.to(self.device)
         nbytes = t.numel() * t.element_size()
         if self._bytes + nbytes > self.max_bytes:
             self._d.clear()
             self._bytes = 0
         self._d[key] = t
         self._bytes += nbytes
+        return t
+
+    def refresh(self, path, kind, host_tensor):
+        """Overwrite a cached volume with fresh host data (asynchronous copy from pinned memory on the
+        current stream); 'f32' volumes are made finite on the device afterwards."""
+        import ctypes as C
+        from . import _lib
+        t = self.get(path, kind)
+        t.copy_(host_tensor, non_blocking=True)
+        if kind == "f32":
+            _lib.check(_lib.lib().bfm_sanitize_f32(t.data_ptr(), t.numel(),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return t

@@ -183,6 +183,77 @@ class Arena:
         return self.slots[self.cur]["dev"][off:off + count * item].view(dtype)
 
 
+class DeviceTables:
+    """Device-resident cache of the per-axis myzoom_torch tables and of the bounding-box candidate lists.  Both
+    depend only on (n_in, factor, n_out); a generator sees a few hundred distinct keys, so after warm-up no
+    table is rebuilt or copied again (a miss costs one small synchronous upload)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._zoom = {}
+        self._cand = {}
+        self._keep = []
+
+    def _upload(self, arrays):
+        offs, total = [], 0
+        for a in arrays:
+            total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
+            offs.append(total)
+            total += a.nbytes
+        host = np.zeros(max(total, _ALIGN), dtype=np.uint8)
+        for a, o in zip(arrays, offs):
+            host[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        dev = torch.from_numpy(host).to(self.device)
+        self._keep.append(dev)
+        base = dev.data_ptr()
+        return [base + o for o in offs]
+
+    def zoom(self, n_in, factor, n_out):
+        """Device addresses (lo, hi, wl, wh) of one axis."""
+        key = (int(n_in), float(factor), int(n_out))
+        hit = self._zoom.get(key)
+        if hit is None:
+            hit = tuple(self._upload(zoom_tables_host(*key)))
+            self._zoom[key] = hit
+        return hit
+
+    def cand(self, n_in, factor, n_out):
+        """(device address, count) of the candidate list of one axis."""
+        key = (int(n_in), float(factor), int(n_out))
+        hit = self._cand.get(key)
+        if hit is None:
+            c = zoom_candidates_host(*key)
+            hit = (self._upload([c])[0], int(c.size))
+            self._cand[key] = hit
+        return hit
+
+    def ends(self, n_out):
+        """Candidate list {0, n_out-1} of an axis without a nonlinear field."""
+        key = ("ends", int(n_out))
+        hit = self._cand.get(key)
+        if hit is None:
+            hit = (self._upload([np.array([0, n_out - 1], dtype=np.int32)])[0], 2)
+            self._cand[key] = hit
+        return hit
+
+
+_TABLES = {}
+
+
+def device_tables(device):
+    key = str(torch.device(device))
+    if key not in _TABLES:
+        _TABLES[key] = DeviceTables(device)
+    return _TABLES[key]
+
+
+def set_zoom_tab(tab, tables, n_in, factors, n_out):
+    """Point a _lib.ZoomTab at the cached device tables of the three axes."""
+    for ax in range(3):
+        lo, hi, wl, wh = tables.zoom(n_in[ax], factors[ax], n_out[ax])
+        tab.lo[ax], tab.hi[ax], tab.wl[ax], tab.wh[ax] = lo, hi, wl, wh
+
+
 def fill_zoom_tab(tab, arena, tables):
     for ax, (lo, hi, wl, wh) in enumerate(tables):
         tab.lo[ax] = arena.put(lo)
@@ -191,8 +262,10 @@ def fill_zoom_tab(tab, arena, tables):
         tab.wh[ax] = arena.put(wh)
 
 
-def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None):
-    """Populate a _lib.Deform from host values (A, c2: float32 arrays as the reference's tensors)."""
+def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None, tables=None):
+    """Populate a _lib.Deform from host values (A, c2: float32 arrays as the reference's tensors).  With
+    `tables` (a DeviceTables) the zoom tables and candidate lists come from the device-resident cache and only
+    the small random grid goes through the arena."""
     for a in range(3):
         d.size[a] = int(size[a])
         d.src[a] = int(src[a])
@@ -208,21 +281,30 @@ def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None)
             d.ncand[a] = 0
     elif fsmall_host is None:
         for a in range(3):
-            d.cand[a] = arena.put(np.array([0, size[a] - 1], dtype=np.int32))
-            d.ncand[a] = 2
+            if tables is not None:
+                d.cand[a], d.ncand[a] = tables.ends(size[a])
+            else:
+                d.cand[a] = arena.put(np.array([0, size[a] - 1], dtype=np.int32))
+                d.ncand[a] = 2
     if fsmall_host is None:
         d.fsmall = None
         return
     fs = fsmall_host.shape[:3]
     for a in range(3):
         d.fs[a] = int(fs[a])
-    d.fsmall = arena.put(fsmall_host.astype(np.float32))
+    d.fsmall = arena.put(fsmall_host.astype(np.float32, copy=False))
     factor = np.array(size) / np.array(fs)
     new = zoom_newsize(fs, factor)
     assert tuple(new) == tuple(size), (new, size)
-    fill_zoom_tab(d.ftab, arena, [zoom_tables_host(fs[a], factor[a], int(new[a])) for a in range(3)])
+    if tables is not None:
+        set_zoom_tab(d.ftab, tables, fs, factor, size)
+    else:
+        fill_zoom_tab(d.ftab, arena, [zoom_tables_host(fs[a], factor[a], int(new[a])) for a in range(3)])
     if F_full_ptr is None:
         for a in range(3):
-            c = zoom_candidates_host(fs[a], factor[a], int(new[a]))
-            d.cand[a] = arena.put(c)
-            d.ncand[a] = int(c.size)
+            if tables is not None:
+                d.cand[a], d.ncand[a] = tables.cand(fs[a], factor[a], int(new[a]))
+            else:
+                c = zoom_candidates_host(fs[a], factor[a], int(new[a]))
+                d.cand[a] = arena.put(c)
+                d.ncand[a] = int(c.size)

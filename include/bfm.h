@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 1
+#define BFM_ABI_VERSION 2
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -73,6 +73,15 @@ int bfm_blur_axis(const float *in, float *out, int nx, int ny, int nz, int axis,
 int bfm_band_axis(const float *in, float *out, const int *in_shape, int axis, int n_out,
                   const int *start, const float *w, int T,
                   float noise_std, const float *eps, uint64_t seed, void *stream);
+
+/* x = nan_to_num(x) in place (torch.nan_to_num, Generator/utils.py:305): applied once when a real-image volume
+ * enters the device cache instead of at every crop read. */
+int bfm_sanitize_f32(float *x, int64_t n, void *stream);
+
+/* The banded map of one axis of resample_resolution (Gaussian slice-profile blur, then masked 2-tap linear
+ * sampling at the acquisition grid), built on the device: start[n_out], w[n_out*T], T = 2*ceil(3*sigma)+2 <= 64.
+ * make_gaussian_kernel Generator/utils.py:74-81; sample positions utils.py:595-605 */
+int bfm_band_build(int n_in, int n_out, double sigma, int T, int *start, float *w, void *stream);
 
 /* global min / max of a float volume (device results, 2 floats: min, max)  torch.min/torch.max */
 int bfm_minmax(const float *x, int64_t n, float *minmax_dev, void *stream);
@@ -143,10 +152,17 @@ int bfm_svf_step(const float *Fin, float *Fout, int sx, int sy, int sz, void *st
 typedef struct bfm_band {
     const int *start;   /* n_out */
     const float *w;     /* n_out * T */
-    int T;
+    int T;              /* 2*ceil(3*sigma) + 2 */
     int n_in, n_out;
     int axis;
+    /* build != 0: start/w point to uninitialised device scratch that bfm_gen_plan fills on the GPU from
+       (n_in, n_out, sigma) with the reference's expressions (make_gaussian_kernel utils.py:74-81, float64
+       np.arange sample positions utils.py:595-605); build == 0: the caller supplies the tables. */
+    int build;
+    double sigma;
 } bfm_band;
+
+#define BFM_MAX_AUX 3
 
 typedef struct bfm_gen_sample {
     bfm_deform d;
@@ -157,7 +173,8 @@ typedef struct bfm_gen_sample {
     const float *sigma;     /* 256 */
     const float *eps_gmm;   /* injected N(0,1) draws shaped like the bbox crop, or NULL => Philox */
     uint64_t seed;          /* Philox key (per sample) */
-    float *syn;             /* scratch, source-volume sized */
+    float *syn;             /* scratch, source-volume sized + src[1]*src[2]+src[2]+1 floats of tail padding;
+                               must only ever hold finite values (zero it once, then let bfm_gen_gmm write it) */
     int *bbox;              /* 6 ints (device) */
     /* optional mixing with real modalities (datasets.py:379-388): I = v0*I + v[m]*mix[m] */
     const float *mix[3];
@@ -184,16 +201,30 @@ typedef struct bfm_gen_sample {
     float *maxval;          /* device scalar */
     float *out;             /* (size) 'input', flipped if flip */
     float *residual;        /* optional 'high_res_residual' */
+    /* Real-image targets that share the deformation (read_and_deform_image, Generator/utils.py:324-343):
+       warped by the same gather as the synthetic image, then `Idef -= min; Idef /= max` and the flip are
+       applied by bfm_gen_finish.  aux_src: full source volumes (f32, finite -- nan_to_num applied when the
+       volume is cached -- and followed by >= src[1]*src[2]+src[2]+1 readable floats); aux_raw: (size) scratch;
+       aux_out: (size) result; aux_mm: 2*n_aux ints of device scratch.  n_aux must be 0 when mix[0] != NULL
+       (the mixing step needs the normalised targets before the warp). */
+    int n_aux;
+    const float *aux_src[BFM_MAX_AUX];
+    float *aux_raw[BFM_MAX_AUX];
+    float *aux_out[BFM_MAX_AUX];
+    int *aux_mm;
 } bfm_gen_sample;
 
 /* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,
  * `s_host` the host copy (grid sizing only). */
+/* bfm_gen_plan: builds the banded blur-o-downsample tables flagged `build` on the device (no host work, no
+ * host->device traffic for them); must precede bfm_gen_resample. */
+int bfm_gen_plan(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 int bfm_gen_bbox(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 int bfm_gen_gmm(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 int bfm_gen_warp(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 int bfm_gen_resample(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 int bfm_gen_finish(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
-/* all five stages back to back */
+/* all six stages back to back */
 int bfm_gen_run(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -90,3 +90,19 @@ def test_deform_grid_and_field_are_bit_exact():
     for d in range(3):
         assert np.array_equal(to_np(grid[d]), orc.deform["rel"][d].numpy()), "coordinate plane %d" % d
     assert [int(v) for v in grid[3:]] == orc.deform["lo"] + orc.deform["hi"]
+
+
+@pytest.mark.parametrize("n_in,n_out,sigma", [(160, 160, 0.0), (160, 25, 2.95), (160, 121, 0.51), (64, 13, 1.7),
+                                             (160, 32, 5.0), (96, 96, 0.3), (160, 159, 0.0)])
+def test_device_band_tables_match_host(n_in, n_out, sigma):
+    """bfm_band_build (tables built on the GPU) against plan.band_host (numpy/torch, the op-level path)."""
+    import ctypes as C
+    from brainfm_b200 import _lib, plan
+    start, w, T = plan.band_host(n_in, n_out, sigma)
+    ds = torch.empty(n_out, dtype=torch.int32, device="cuda")
+    dw = torch.empty((n_out, T), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().bfm_band_build(n_in, n_out, float(sigma), T, ds.data_ptr(), dw.data_ptr(),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert np.array_equal(to_np(ds), start)
+    np.testing.assert_allclose(to_np(dw), w, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(to_np(dw).sum(1), w.sum(1), rtol=1e-6, atol=1e-7)
