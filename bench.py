@@ -194,7 +194,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     from brainfm_b200 import _lib
-    n_subjects = BATCH
+    n_subjects = 2 * BATCH          # the end-to-end arm alternates between two sets of subjects
     subs = make_inputs(n_subjects)
     ds = build_dataset(subs, device)
     np.random.seed(1000 + rank)
@@ -263,29 +263,35 @@ def main():
                               "host_wall_ms_per_step": 1e3 * host_s / args.steps}), flush=True)
         return
     # ---------------- end-to-end arm: host buffers in, host buffers out ----------------
-    from brainfm_b200 import io as bio
+    # Every step uploads the label map (uint8) and the T1 volume (float32) of its 8 subjects from pinned host
+    # memory and downloads the 8 generated volumes into pinned host memory, through the public pipelined API
+    # (brainfm_b200.pipeline.HostPipeline): the upload of step k+1 and the download of step k-1 overlap the
+    # generation of step k, so consecutive steps alternate between two sets of 8 subjects.
+    from brainfm_b200.pipeline import HostPipeline
     host_lab = [torch.from_numpy(s["Gen"].astype(np.uint8)).pin_memory() for s in subs]
     host_t1 = [torch.from_numpy(s["T1"]).pin_memory() for s in subs]
-    host_out = torch.empty((BATCH, 1, SIZE, SIZE, SIZE), dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in host_lab) + sum(t.numel() * 4 for t in host_t1)
-    d2h = host_out.numel() * 4
+    sets = [list(range(0, BATCH)), list(range(BATCH, 2 * BATCH))]
+    uploads = [[u for s in st for u in ((ds.names[0][s][:-7] + "generation_labels.nii", "gen", host_lab[s]),
+                                        (ds.names[0][s], "f32", host_t1[s]))] for st in sets]
+    h2d = sum(t.numel() * t.element_size() for t in host_lab[:BATCH]) + sum(t.numel() * 4 for t in host_t1[:BATCH])
+    d2h = BATCH * SIZE ** 3 * 4
+    pipe = HostPipeline(ds, depth=3)
 
-    def e2e_step():
-        for s in range(BATCH):
-            ds.cache.refresh(ds.names[0][s][:-7] + "generation_labels.nii", "gen", host_lab[s])
-            ds.cache.refresh(ds.names[0][s], "f32", host_t1[s])
-        its = ds.generate_batch(idxs)
-        for s in range(BATCH):
-            host_out[s].copy_(its[s][4]["input"], non_blocking=True)
-        return its
+    def e2e_run(n):
+        tickets = []
+        for k in range(n):
+            tickets.append(pipe.submit(sets[k % 2], uploads[k % 2]))
+            if len(tickets) > 2:
+                tickets.pop(0).wait()
+        for t in tickets:
+            t.wait()
 
-    for _ in range(3):
-        e2e_step()
+    e2e_run(4)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for k in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
+    torch.cuda.synchronize()
     f1.record()
     barrier()
     el2 = torch.tensor([f0.elapsed_time(f1)], device=device, dtype=torch.float64)

@@ -69,6 +69,7 @@ class BaseGen(Dataset):
         self.prepare_paths()
         self.prepare_grid()
         self.prepare_one_hot()
+        self.tables.prebuild(self.size)
 
     def __len__(self):
         return sum([len(self.names[i]) for i in range(len(self.names))])
@@ -316,8 +317,15 @@ class BaseGen(Dataset):
         stds can differ in the last bit because torch's CPU sqrt (MKL vsSqrt) is not correctly rounded
         while numpy's is."""
         rng = self.rng
-        mus = 25 + 200 * rng.torch_rand("gmm.mu", 256)
-        sigmas = 5 + 20 * rng.torch_rand("gmm.sigma", 256)
+        # 25 + 200*u, 5 + 20*u in float32: product then sum, separately rounded, as torch evaluates them
+        mus = rng.torch_rand("gmm.mu", 256)
+        m = mus.numpy()
+        np.multiply(m, np.float32(200), out=m)
+        np.add(m, np.float32(25), out=m)
+        sigmas = rng.torch_rand("gmm.sigma", 256)
+        sg = sigmas.numpy()
+        np.multiply(sg, np.float32(20), out=sg)
+        np.add(sg, np.float32(5), out=sg)
         if rng.rand("gmm.ct") < self.synth_args.ct_prob:
             for name, (base, span) in (('darker', (25, 10)), ('dark', (90, 20)), ('bright', (110, 20)),
                                        ('brighter', (150, 50))):
@@ -325,17 +333,12 @@ class BaseGen(Dataset):
                 for l in ct_brightness_group[name]:
                     mus[l] = v
         if photo_mode or rng.rand1("gmm.bg") < 0.5:
-            mus[0] = 0
-        m, sg = mus.numpy(), sigmas.numpy()
-        v, w = _PV_V, _PV_W
-        m[100:150] = m[1] * w + m[2] * v
-        m[150:200] = m[2] * w + m[3] * v
-        m[200:250] = m[3] * w + m[4] * v
+            m[0] = 0
+        # labels 100-149 / 150-199 / 200-249 blend classes (1,2) / (2,3) / (3,4): three rows at once
+        m[100:250].reshape(3, 50)[:] = m[1:4, None] * _PV_W + m[2:5, None] * _PV_V
         m[250] = m[4]
         q = sg[:5] * sg[:5]
-        sg[100:150] = np.sqrt(q[1] * w + q[2] * v)
-        sg[150:200] = np.sqrt(q[2] * w + q[3] * v)
-        sg[200:250] = np.sqrt(q[3] * w + q[4] * v)
+        sg[100:250].reshape(3, 50)[:] = np.sqrt(q[1:4, None] * _PV_W + q[2:5, None] * _PV_V)
         sg[250] = sg[4]
         return mus, sigmas
 
@@ -400,7 +403,7 @@ class BaseGen(Dataset):
         blur-o-downsample tables are built on the GPU (bfm_gen_plan), scratch volumes are persistent.
         jobs: dicts(plan=DeformPlan, flip, labels, p=<_plan_synth>, want_bflog, want_residual, aux=[(key, vol)])."""
         B = len(jobs)
-        dev, size, tables = self.device, self.size, self.tables
+        dev, size, tables = self.device, tuple(self.size), self.tables
         N = int(np.prod(size))
         descs = (_lib.GenSample * B)()
         out = torch.empty((B, 1, *size), dtype=torch.float32, device=dev)
@@ -441,18 +444,15 @@ class BaseGen(Dataset):
                 s.eps_gmm = e.data_ptr()
             s.seed = int(p['seed'])
             s.syn = p_syn + 4 * b * src_pad
-            s.bbox = plan.bbox.data_ptr()
+            s.bbox = plan.bbox_ptr
             if p['mix'] is not None:
                 for q in range(4):
                     s.mixw[q] = float(p['mix'][q])
             s.gamma = float(p['gamma'])
             bfs = p['bfsmall']
             s.bfsmall = arena.put(bfs)
-            bshape = bfs.shape
-            s.bs[0], s.bs[1], s.bs[2] = bshape
-            fac = np.array(size) / np.array(bshape)
-            assert tuple(zoom_newsize(bshape, fac)) == tuple(size)
-            set_zoom_tab(s.btab, tables, bshape, fac, size)
+            s.bs[:] = bfs.shape
+            s.btab = tables.zoom_tab(bfs.shape, size)
             s.i_bf = p_ibf + 4 * b * N
             sample = {}
             if job['want_bflog']:
@@ -497,10 +497,8 @@ class BaseGen(Dataset):
             s.tmp[0] = p_tmp + 4 * (2 * b) * N
             s.tmp[1] = p_tmp + 4 * (2 * b + 1) * N
             s.lowres = p_low + 4 * b * N
-            s.new_size[0], s.new_size[1], s.new_size[2] = new
-            up = 1 / p['factors']
-            assert tuple(zoom_newsize(new, up)) == tuple(size), (new, up)
-            set_zoom_tab(s.utab, tables, new, up, size)
+            s.new_size[:] = new
+            s.utab = tables.zoom_tab(new, size, inverse=True)
             s.maxval, _ = arena.reserve(16)
             s.out = out[b].data_ptr()
             if job['want_residual']:

@@ -9,7 +9,7 @@ import torch
 
 from .. import _lib, io as bio
 from ..draws import HostDraws
-from ..plan import (band_host, device_tables, fill_deform, gaussian_taps_host, zoom_newsize, zoom_tables_host)
+from ..plan import (band_host, device_tables, gaussian_taps_host, make_deform, zoom_newsize, zoom_tables_host)
 
 _DRAWS = HostDraws()
 
@@ -98,9 +98,7 @@ def make_affine_matrix(rot, sh, s):
     shy = np.array([[1, sh[0], 0], [0, 1, 0], [0, sh[2], 1]])
     shz = np.array([[1, 0, sh[0]], [0, 1, sh[1]], [0, 0, 1]])
     A = shx @ shy @ shz @ rx @ ry @ rz
-    for r in range(3):
-        A[r, :] = A[r, :] * s[r]
-    return A
+    return A * np.asarray(s)[:, None]          # row r scaled by s[r]
 
 
 def binarize(p, thres):
@@ -207,22 +205,25 @@ class DeformPlan:
         self.c2_host = np.asarray(c2, dtype=np.float32)
         self.photo = bool(photo)
         self.F_full = F_full
-        self.struct = _lib.Deform()
         fptr = F_full.data_ptr() if F_full is not None else None
+        if fsmall_host is not None:
+            fsmall_host = np.ascontiguousarray(fsmall_host, dtype=np.float32)
         tables = device_tables(self.device)
+        self._arena, self._bbox = None, None
         if arena is not None:
             # the small grid lives in the caller's arena slot: valid until that slot is recycled
-            fill_deform(self.struct, arena, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr,
-                        tables=tables)
-            addr, off = arena.reserve(32)
-            self.bbox = arena.view(off, 8, torch.int32)
+            self.struct = make_deform(tables, arena, self.size, self.src, self.A_host, self.c2_host, fsmall_host,
+                                      photo, fptr)
+            self.bbox_ptr, self._bbox_off = arena.reserve(32)
+            self._arena, self._slot = arena, arena.cur
         else:
             ar = _MiniArena(self.device)
-            fill_deform(self.struct, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host, photo, fptr,
-                        tables=tables)
+            self.struct = make_deform(tables, ar, self.size, self.src, self.A_host, self.c2_host, fsmall_host,
+                                      photo, fptr)
             ar.finalize()
             self._keep = ar.dev
-            self.bbox = torch.empty(8, dtype=torch.int32, device=self.device)
+            self._bbox = torch.empty(8, dtype=torch.int32, device=self.device)
+            self.bbox_ptr = self._bbox.data_ptr()
         self._bbox_host = None
         self.have_bbox = False
         if not lazy:
@@ -230,9 +231,16 @@ class DeformPlan:
                 arena.commit()
             self.compute_bbox()
 
+    @property
+    def bbox(self):
+        """Device tensor view of the 6 bounding-box ints (+2 of scratch)."""
+        if self._bbox is None:
+            self._bbox = self._arena.view(self._bbox_off, 8, torch.int32, slot=self._slot)
+        return self._bbox
+
     def compute_bbox(self):
         if not self.have_bbox:
-            _lib.check(_lib.lib().bfm_deform_grid(C.byref(self.struct), self.bbox.data_ptr(), None, _stream()))
+            _lib.check(_lib.lib().bfm_deform_grid(C.byref(self.struct), self.bbox_ptr, None, _stream()))
             self.have_bbox = True
 
     def bbox_host(self):
@@ -244,7 +252,7 @@ class DeformPlan:
     def coords(self):
         """bbox-relative xx2, yy2, zz2 as the reference's deform_grid returns them."""
         out = torch.empty((3, *self.size), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().bfm_deform_grid(C.byref(self.struct), self.bbox.data_ptr(), out.data_ptr(), _stream()))
+        _lib.check(_lib.lib().bfm_deform_grid(C.byref(self.struct), self.bbox_ptr, out.data_ptr(), _stream()))
         return out[0], out[1], out[2]
 
 
@@ -308,7 +316,7 @@ def read_and_deform(file_name, dtype, deform_dict, device, mask, default_value_l
         raise ValueError("volume shape %s does not match the deformation's source shape %s" % (tuple(vol.shape), plan.src))
     out = torch.empty(plan.size, dtype=torch.float32, device=plan.device)
     scratch = torch.empty(1, dtype=torch.float32, device=plan.device)
-    _lib.check(_lib.lib().bfm_warp_volume(C.byref(plan.struct), plan.bbox.data_ptr(), vol.data_ptr(), float(mean),
+    _lib.check(_lib.lib().bfm_warp_volume(C.byref(plan.struct), plan.bbox_ptr, vol.data_ptr(), float(mean),
                                           float(scale), 1 if default_value_linear_mode == 'max' else 0,
                                           scratch.data_ptr(), out.data_ptr(),
                                           None if minmax_out is None else minmax_out.data_ptr(), _stream()))
@@ -409,7 +417,7 @@ def read_and_deform_segmentation(exist_keys, task_name, file_name, setups, defor
     lut32 = lut.to(device=plan.device, dtype=torch.int32)
     vf = torch.as_tensor(np.asarray(vflip), dtype=torch.int32, device=plan.device)
     out = torch.empty((n_classes, *plan.size), dtype=torch.float32, device=plan.device)
-    _lib.check(_lib.lib().bfm_label_warp_onehot(C.byref(plan.struct), plan.bbox.data_ptr(), S.data_ptr(),
+    _lib.check(_lib.lib().bfm_label_warp_onehot(C.byref(plan.struct), plan.bbox_ptr, S.data_ptr(),
                                                 lut32.data_ptr(), int(lut32.numel()), n_classes, vf.data_ptr(),
                                                 1 if setups['flip'] else 0, out.data_ptr(), None, _stream()))
     return {'segmentation': out}

@@ -414,9 +414,13 @@ __device__ __forceinline__ float fast_pow(float x, float g) { return ex2_approx(
 // The coordinate path keeps the reference's separately rounded operations (bit-exact coordinates); the
 // interpolation of VALUES uses a + w*(b-a) with one FMA per lerp (<= 1 ulp from the reference's w0*a + w1*b).
 constexpr int kWR = 4;            // rows per barrier
+#ifndef WARP_PIPE
+#define WARP_PIPE 2
+#endif
+constexpr int kWP = WARP_PIPE;    // rows whose gathers are in flight together (divides kWR)
 constexpr int kT2 = 128;          // floats per second-pass row: 3*fs[2] + bs[2] <= kT2
 #ifndef WARP_MINB
-#define WARP_MINB 3
+#define WARP_MINB 4
 #endif
 
 struct WarpShared {
@@ -512,65 +516,90 @@ __device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B
             const float *rzlo = rows + zlo, *rzhi = rows + zhi, *rblo = rows + blo, *rbhi = rows + bhi;
             int p = (plane_in + jj) * g.s2 + kk;                   // element index of (i, jj, k)
             int po = (plane_out + jj) * g.s2 + kk;
+            // kWP rows at a time: coordinates and addresses of all of them, then ALL their gathers (8 per row and
+            // volume) back to back, then the arithmetic -- the loads of several rows overlap each other's latency
 #pragma unroll
-            for (int r = 0; r < kWR; ++r, p += g.s2, po += g.s2) {
-                const int j = jj + r;
-                if (j >= j1) break;
-                float x1 = xc, y1 = __fsub_rn((float)j, g.ctr1), z1 = zc;
-                if (FIELD == 2) {
-                    const float *f = g.F_full + (int64_t)p * 3;
-                    x1 = __fadd_rn(x1, __ldg(f)); y1 = __fadd_rn(y1, __ldg(f + 1)); z1 = __fadd_rn(z1, __ldg(f + 2));
-                } else if (FIELD == 1) {                                     // third pass (axis 2), utils.py:244-246
-                    const float f0 = lerp_rn(zwl, rzlo[r * kT2], zwh, rzhi[r * kT2]);
-                    const float f1 = photo ? 0.f : lerp_rn(zwl, rzlo[r * kT2 + 1], zwh, rzhi[r * kT2 + 1]);
-                    const float f2 = lerp_rn(zwl, rzlo[r * kT2 + 2], zwh, rzhi[r * kT2 + 2]);
-                    x1 = __fadd_rn(x1, f0); y1 = __fadd_rn(y1, f1); z1 = __fadd_rn(z1, f2);
+            for (int r0 = 0; r0 < kWR; r0 += kWP) {
+                if (jj + r0 >= j1) break;
+                int e00[kWP];
+                float ax[kWP], ay[kWP], az[kWP];
+                bool ok[kWP];
+#pragma unroll
+                for (int q = 0; q < kWP; ++q) {
+                    const int r = r0 + q, j = jj + r;
+                    float x1 = xc, y1 = __fsub_rn((float)j, g.ctr1), z1 = zc;
+                    if (FIELD == 2) {
+                        const float *f = g.F_full + (int64_t)(p + r * g.s2) * 3;
+                        x1 = __fadd_rn(x1, __ldg(f)); y1 = __fadd_rn(y1, __ldg(f + 1)); z1 = __fadd_rn(z1, __ldg(f + 2));
+                    } else if (FIELD == 1) {                                 // third pass (axis 2), utils.py:244-246
+                        const float f0 = lerp_rn(zwl, rzlo[r * kT2], zwh, rzhi[r * kT2]);
+                        const float f1 = photo ? 0.f : lerp_rn(zwl, rzlo[r * kT2 + 1], zwh, rzhi[r * kT2 + 1]);
+                        const float f2 = lerp_rn(zwl, rzlo[r * kT2 + 2], zwh, rzhi[r * kT2 + 2]);
+                        x1 = __fadd_rn(x1, f0); y1 = __fadd_rn(y1, f1); z1 = __fadd_rn(z1, f2);
+                    }
+                    float px, py, pz;
+                    affine_clamp(g, x1, y1, z1, px, py, pz);
+                    // ---- trilinear taps relative to the crop (fast_3D_interp_torch, utils.py:140-192)
+                    const float rx = __fsub_rn(px, box.l0), ry = __fsub_rn(py, box.l1), rz = __fsub_rn(pz, box.l2);
+                    ok[q] = (rx > 0.f) & (ry > 0.f) & (rz > 0.f) & (rx <= box.h0) & (ry <= box.h1) & (rz <= box.h2) &
+                            (j < j1);
+                    const int ix = __float2int_rd(rx), iy = __float2int_rd(ry), iz = __float2int_rd(rz);
+                    ax[q] = __fsub_rn(rx, (float)ix); ay[q] = __fsub_rn(ry, (float)iy); az[q] = __fsub_rn(rz, (float)iz);
+                    e00[q] = ok[q] ? origin + ix * box.n1n2 + iy * box.n2 + iz : origin;
                 }
-                float px, py, pz;
-                affine_clamp(g, x1, y1, z1, px, py, pz);
-                // ---- trilinear taps relative to the crop (fast_3D_interp_torch, utils.py:140-192)
-                const float rx = __fsub_rn(px, box.l0), ry = __fsub_rn(py, box.l1), rz = __fsub_rn(pz, box.l2);
-                const bool ok = (rx > 0.f) & (ry > 0.f) & (rz > 0.f) & (rx <= box.h0) & (ry <= box.h1) & (rz <= box.h2);
-                const int ix = __float2int_rd(rx), iy = __float2int_rd(ry), iz = __float2int_rd(rz);
-                const float ax = __fsub_rn(rx, (float)ix), ay = __fsub_rn(ry, (float)iy), az = __fsub_rn(rz, (float)iz);
-                const int e00 = ok ? origin + ix * box.n1n2 + iy * box.n2 + iz : origin;
-                const int e10 = e00 + box.n1n2, e01 = e00 + box.n2, e11 = e10 + box.n2;   // e<x><y>
-                auto gather = [&](const float *__restrict__ X) {
-                    const float v000 = __ldg(X + e00), v001 = __ldg(X + e00 + 1);
-                    const float v100 = __ldg(X + e10), v101 = __ldg(X + e10 + 1);
-                    const float v010 = __ldg(X + e01), v011 = __ldg(X + e01 + 1);
-                    const float v110 = __ldg(X + e11), v111 = __ldg(X + e11 + 1);
-                    const float c00 = fmaf(ax, v100 - v000, v000), c01 = fmaf(ax, v101 - v001, v001);
-                    const float c10 = fmaf(ax, v110 - v010, v010), c11 = fmaf(ax, v111 - v011, v011);
-                    const float c0 = fmaf(ay, c10 - c00, c00), c1 = fmaf(ay, c11 - c01, c01);
-                    const float v = fmaf(az, c1 - c0, c0);
-                    return ok ? v : 0.f;
-                };
-                float v = gather(syn);
-                if (MIX) {                                        // datasets.py:379-388
-                    v = __fadd_rn(__fmul_rn(mw0, v), __fmul_rn(mw1, mix0[p]));
-                    if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[p]));
-                    if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[p]));
-                }
-                v = fmaxf(v, 0.f);                                // datasets.py:411
-                // gamma: 300 * (I/300) ** gamma                  utils.py:568-572
-                v = 300.f * fast_pow(v * (1.f / 300.f), gamma);
-                // bias field: I * exp(zoom(BFsmall))             utils.py:574-589
-                float bl = 0.f;
-                if (bw) {
-                    bl = lerp_rn(bwl, rblo[r * kT2], bwh, rbhi[r * kT2]);
-                    v *= ex2_approx(bl * 1.4426950408889634f);
-                }
-                if (kv) {
-                    i_bf[p] = v;
-                    if (bfl) bfl[po] = bl;
+                float tap[NAUX + 1][kWP][8];
+#pragma unroll
+                for (int c = 0; c <= NAUX; ++c) {
+                    const float *__restrict__ X = c == 0 ? syn : asrc[c > 0 ? c - 1 : 0];
+#pragma unroll
+                    for (int q = 0; q < kWP; ++q) {
+                        const float *b00 = X + e00[q], *b10 = b00 + box.n1n2, *b01 = b00 + box.n2, *b11 = b10 + box.n2;
+                        tap[c][q][0] = __ldg(b00); tap[c][q][1] = __ldg(b00 + 1);
+                        tap[c][q][2] = __ldg(b10); tap[c][q][3] = __ldg(b10 + 1);
+                        tap[c][q][4] = __ldg(b01); tap[c][q][5] = __ldg(b01 + 1);
+                        tap[c][q][6] = __ldg(b11); tap[c][q][7] = __ldg(b11 + 1);
+                    }
                 }
 #pragma unroll
-                for (int c = 0; c < NAUX; ++c) {                  // read_and_deform_image: raw warp + min/max
-                    const float a = gather(asrc[c]);
-                    if (kv) araw[c][p] = a;
-                    amin[c] = fminf(amin[c], a);                  // (k >= s2 lanes repeat the last voxel)
-                    amax[c] = fmaxf(amax[c], a);
+                for (int q = 0; q < kWP; ++q) {
+                    const int r = r0 + q, j = jj + r;
+                    const int pr = p + r * g.s2;
+                    auto interp = [&](const float *t) {      // t: 000 001 100 101 010 011 110 111
+                        const float c00 = fmaf(ax[q], t[2] - t[0], t[0]), c01 = fmaf(ax[q], t[3] - t[1], t[1]);
+                        const float c10 = fmaf(ax[q], t[6] - t[4], t[4]), c11 = fmaf(ax[q], t[7] - t[5], t[5]);
+                        const float c0 = fmaf(ay[q], c10 - c00, c00), c1 = fmaf(ay[q], c11 - c01, c01);
+                        const float v = fmaf(az[q], c1 - c0, c0);
+                        return ok[q] ? v : 0.f;
+                    };
+                    float v = interp(tap[0][q]);
+                    if (MIX) {                                        // datasets.py:379-388
+                        v = __fadd_rn(__fmul_rn(mw0, v), __fmul_rn(mw1, mix0[pr]));
+                        if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[pr]));
+                        if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[pr]));
+                    }
+                    v = fmaxf(v, 0.f);                                // datasets.py:411
+                    // gamma: 300 * (I/300) ** gamma                  utils.py:568-572
+                    v = 300.f * fast_pow(v * (1.f / 300.f), gamma);
+                    // bias field: I * exp(zoom(BFsmall))             utils.py:574-589
+                    float bl = 0.f;
+                    if (bw) {
+                        bl = lerp_rn(bwl, rblo[r * kT2], bwh, rbhi[r * kT2]);
+                        v *= ex2_approx(bl * 1.4426950408889634f);
+                    }
+                    const bool wr = kv && j < j1;
+                    if (wr) {
+                        i_bf[pr] = v;
+                        if (bfl) bfl[po + r * g.s2] = bl;
+                    }
+#pragma unroll
+                    for (int c = 0; c < NAUX; ++c) {                  // read_and_deform_image: raw warp + min/max
+                        const float a = interp(tap[c + 1][q]);
+                        if (wr) {
+                            araw[c][pr] = a;
+                            amin[c] = fminf(amin[c], a);
+                            amax[c] = fmaxf(amax[c], a);
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -689,80 +718,127 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
 }
 
 // ---------------------------------------------------------------------------------------------- finish
-// A warp owns kRowsPerWarp output rows; the first two zoom passes are evaluated once per low-res z node.
-template <bool WRITE>
-__global__ void __launch_bounds__(kRowWarps * 32) k_gen_upsample(const bfm_gen_sample *__restrict__ S, int max_lz) {
+// myzoom_torch(lowres, 1/factors) back to the training grid (datasets.py:337-340), in the same persistent-k
+// layout as the warp kernel: block = (i, kUR rows j), thread = k.  The first zoom pass (axis 0) of the low-res
+// rows this block touches is evaluated once per block into shared memory, the second (axis 1) once per output
+// row (kWR rows per barrier, double buffered), so a voxel costs one 2-tap lerp from shared memory.  The kernel
+// stores the UNNORMALISED value at its final (flipped) position and reduces the global maximum;
+// k_gen_normalize then applies I / max(I) (datasets.py:342-343) and finishes the real-image targets.
+constexpr int kUR = 16;           // output rows per block
+
+__global__ void __launch_bounds__(256) k_gen_upsample(const bfm_gen_sample *__restrict__ S, int lz_cap, int ny_cap) {
     extern __shared__ float smem[];
     __shared__ bfm_gen_sample sd;
-    __shared__ float red[kRowWarps];
-    stage_desc(&sd, S + blockIdx.y);
+    __shared__ float red[8];
+    {
+        const bfm_gen_sample *sp = S + blockIdx.z;
+        if ((int)blockIdx.y >= sp->d.size[0] || (int)blockIdx.x * kUR >= sp->d.size[1]) return;
+    }
+    stage_desc(&sd, S + blockIdx.z);
     const bfm_gen_sample &s = sd;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *sm = smem + warp * kRowsPerWarp * max_lz;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const int s0 = s.d.size[0], s1 = s.d.size[1], s2 = s.d.size[2];
-    const int n_rows = s0 * s1;
-    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
+    const int ly = s.new_size[1], lz = s.new_size[2];
+    const int i = blockIdx.y, j0 = blockIdx.x * kUR, j1 = min(j0 + kUR, s1);
+    float *t1 = smem;                                   // [ny][lz]   first pass at this i
+    float *t2 = smem + ny_cap * lz_cap;                 // [2][kWR][lz_cap]
+    const bfm_zoom_tab &u = s.utab;
+    // low-res rows needed by output rows j0..j1-1 (the tables are monotone in j)
+    const int y0 = __ldg(u.lo[1] + j0), y1 = __ldg(u.hi[1] + j1 - 1);
+    const int ny = y1 - y0 + 1;
+    {
+        const int lo = __ldg(u.lo[0] + i), hi = __ldg(u.hi[0] + i);
+        const float wl = __ldg(u.wl[0] + i), wh = __ldg(u.wh[0] + i);
+        const float *a = s.lowres + ((size_t)lo * ly + y0) * lz, *b = s.lowres + ((size_t)hi * ly + y0) * lz;
+        const int n = ny * lz;                          // rows y0..y1 are contiguous in the low-res volume
+        for (int q = tid; q < n; q += blockDim.x) t1[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
+    }
+    __syncthreads();
+    auto ypass = [&](int jj, int buf) {
+        for (int r = warp; r < kWR; r += nwarps) {
+            const int j = min(jj + r, s1 - 1);
+            const float *a = t1 + (__ldg(u.lo[1] + j) - y0) * lz, *b = t1 + (__ldg(u.hi[1] + j) - y0) * lz;
+            const float wl = __ldg(u.wl[1] + j), wh = __ldg(u.wh[1] + j);
+            float *row = t2 + (buf * kWR + r) * lz_cap;
+            for (int q = lane; q < lz; q += 32) row[q] = lerp_rn(wl, a[q], wh, b[q]);
+        }
+    };
+    float *__restrict__ outp = s.out;
+    const int plane_out = (s.flip ? s0 - 1 - i : i) * s1;
     float hi = 0.f;
-    if (row0 < n_rows) {
-        const int lz = s.new_size[2];
-        const int nr = min(kRowsPerWarp, n_rows - row0);
+    for (int k0 = 0; k0 < s2; k0 += blockDim.x) {
+        const int k = k0 + tid;
+        const bool kv = k < s2;
+        const int kk = kv ? k : s2 - 1;
+        const int zlo = __ldg(u.lo[2] + kk), zhi = __ldg(u.hi[2] + kk);
+        const float zwl = __ldg(u.wl[2] + kk), zwh = __ldg(u.wh[2] + kk);
+        int buf = 0;
+        ypass(j0, 0);
+        __syncthreads();
+        for (int jj = j0; jj < j1; jj += kWR) {
+            if (jj + kWR < j1) ypass(jj + kWR, buf ^ 1);
+            const float *rows = t2 + buf * kWR * lz_cap;
 #pragma unroll
-        for (int r = 0; r < kRowsPerWarp; ++r) {
-            const int row = min(row0 + r, n_rows - 1);
-            row_zoom_setup(s.lowres, s.new_size[1], lz, 1, s.utab, row / s1, row % s1, sm + r * max_lz, lane);
-        }
-        __syncwarp();
-        const int *__restrict__ lo = s.utab.lo[2], *__restrict__ hi2 = s.utab.hi[2];
-        const float *__restrict__ wl = s.utab.wl[2], *__restrict__ wh = s.utab.wh[2];
-        // I / max(I) (datasets.py:342-343) as a multiplication by the reciprocal: <= 1 ulp from the division
-        const float rmx = WRITE ? __frcp_rn(*s.maxval) : 1.f;
-        float *__restrict__ outp = s.out;
-        float *__restrict__ resid = s.residual;
-        const int n_aux = WRITE ? s.n_aux : 0;
-        float amn[BFM_MAX_AUX], arg[BFM_MAX_AUX];
-#pragma unroll
-        for (int c = 0; c < BFM_MAX_AUX; ++c) {
-            amn[c] = c < n_aux ? ord2f(s.aux_mm[2 * c]) : 0.f;
-            arg[c] = c < n_aux ? __fsub_rn(ord2f(s.aux_mm[2 * c + 1]), amn[c]) : 1.f;
-        }
-        const float *__restrict__ hr = s.i_bf;
-        int obase[kRowsPerWarp];
-#pragma unroll
-        for (int r = 0; r < kRowsPerWarp; ++r) {
-            const int row = min(row0 + r, n_rows - 1);
-            const int i = row / s1, j = row - i * s1;
-            obase[r] = ((s.flip ? s0 - 1 - i : i) * s1 + j) * s2;
-        }
-        for (int k = lane; k < s2; k += 32) {
-            const int a = __ldg(lo + k), b = __ldg(hi2 + k);
-            const float wa = __ldg(wl + k), wb = __ldg(wh + k);
-#pragma unroll
-            for (int r = 0; r < kRowsPerWarp; ++r) {
-                if (r >= nr) break;
-                const float *row_sm = sm + r * max_lz;
-                const float v = lerp_rn(wa, row_sm[a], wb, row_sm[b]);
-                if (WRITE) {
-                    const float y = v * rmx;
-                    outp[obase[r] + k] = y;
-                    if (resid) resid[obase[r] + k] = __fsub_rn(hr[(row0 + r) * s2 + k] * rmx, y);   // datasets.py:345-347
-#pragma unroll
-                    for (int c = 0; c < BFM_MAX_AUX; ++c)  // Idef -= min; Idef /= max; flip   utils.py:326-329
-                        if (c < n_aux)
-                            s.aux_out[c][obase[r] + k] =
-                                __fdiv_rn(__fsub_rn(__ldg(s.aux_raw[c] + (row0 + r) * s2 + k), amn[c]), arg[c]);
-                } else {
+            for (int r = 0; r < kWR; ++r) {
+                const int j = jj + r;
+                if (j >= j1) break;
+                const float v = lerp_rn(zwl, rows[r * lz_cap + zlo], zwh, rows[r * lz_cap + zhi]);
+                if (kv) {
+                    outp[(plane_out + j) * s2 + k] = v;
                     hi = fmaxf(hi, v);
                 }
             }
+            __syncthreads();
+            buf ^= 1;
         }
     }
-    if (!WRITE) {
-        hi = warp_max(hi);
-        if (lane == 0) red[warp] = hi;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < kRowWarps; ++w) hi = fmaxf(hi, red[w]);
-            atomicMax((int *)s.maxval, __float_as_int(hi));           // values >= 0: bit order == float order
+    hi = warp_max(hi);
+    if (lane == 0) red[warp] = hi;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) hi = fmaxf(hi, red[w]);
+        atomicMax((int *)s.maxval, __float_as_int(hi));               // values >= 0: bit order == float order
+    }
+}
+
+// I / max(I), optional high_res_residual (datasets.py:342-347) and the real-image targets'
+// `Idef -= min; Idef /= max; flip` (utils.py:326-329).  One thread = VEC consecutive z voxels of one x plane.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gen_normalize(const bfm_gen_sample *__restrict__ S) {
+    const bfm_gen_sample &s = S[blockIdx.z];
+    const int s0 = s.d.size[0], plane = s.d.size[1] * s.d.size[2];
+    if ((VEC == 4) != ((plane & 3) == 0)) return;
+    const int i = blockIdx.y;
+    if (i >= s0) return;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (q >= plane) return;
+    const int io = s.flip ? s0 - 1 - i : i;
+    const size_t pin = (size_t)i * plane + q, pout = (size_t)io * plane + q;
+    // I / max(I) as a multiplication by the correctly rounded reciprocal: <= 1 ulp from the division
+    const float rmx = __frcp_rn(*s.maxval);
+    float y[VEC];
+    if (VEC == 4) {
+        const float4 v = *(const float4 *)(s.out + pout);
+        y[0] = v.x * rmx; y[1] = v.y * rmx; y[2] = v.z * rmx; y[VEC - 1] = v.w * rmx;
+        *(float4 *)(s.out + pout) = make_float4(y[0], y[1], y[2], y[VEC - 1]);
+    } else {
+        y[0] = s.out[pout] * rmx;
+        s.out[pout] = y[0];
+    }
+    if (s.residual) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) s.residual[pout + c] = __fsub_rn(__ldg(s.i_bf + pin + c) * rmx, y[c]);
+    }
+    for (int a = 0; a < s.n_aux; ++a) {
+        const float mn = ord2f(s.aux_mm[2 * a]), rg = __fsub_rn(ord2f(s.aux_mm[2 * a + 1]), mn);
+        const float *__restrict__ raw = s.aux_raw[a] + pin;
+        float *__restrict__ o = s.aux_out[a] + pout;
+        if (VEC == 4) {
+            const float4 v = __ldg((const float4 *)raw);
+            *(float4 *)o = make_float4(__fdiv_rn(__fsub_rn(v.x, mn), rg), __fdiv_rn(__fsub_rn(v.y, mn), rg),
+                                       __fdiv_rn(__fsub_rn(v.z, mn), rg), __fdiv_rn(__fsub_rn(v.w, mn), rg));
+        } else {
+            o[0] = __fdiv_rn(__fsub_rn(__ldg(raw), mn), rg);
         }
     }
 }
@@ -974,19 +1050,38 @@ int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, vo
 int bfm_gen_finish(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
     int rc = check_batch(h, d, B);
     if (rc) return rc;
-    int max_lz = 1;
-    for (int b = 0; b < B; ++b) max_lz = h[b].new_size[2] > max_lz ? h[b].new_size[2] : max_lz;
-    const size_t smem = (size_t)kRowWarps * kRowsPerWarp * max_lz * sizeof(float);
-    if (smem > 200 * 1024) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: low-res row too long");
-    if (smem > 40 * 1024) {
-        cudaFuncSetAttribute(k_gen_upsample<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_gen_upsample<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int lz = 1, ny = 1, s0 = 0, s1 = 0, s2 = 0;
+    bool vec = false, scalar = false;
+    for (int b = 0; b < B; ++b) {
+        const bfm_gen_sample &s = h[b];
+        lz = max(lz, s.new_size[2]);
+        // low-res rows under kUR output rows: at most kUR * ly / s1 + 2 (and never more than ly)
+        const int rows = min(s.new_size[1], (int)((int64_t)kUR * s.new_size[1] / s.d.size[1]) + 3);
+        ny = max(ny, rows);
+        s0 = max(s0, s.d.size[0]); s1 = max(s1, s.d.size[1]); s2 = max(s2, s.d.size[2]);
+        if (((int64_t)s.d.size[1] * s.d.size[2]) & 3) scalar = true; else vec = true;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    k_gen_upsample<false><<<dim3(rows_grid(h), B), kRowWarps * 32, smem, s>>>(d, max_lz);
-    g_launches.fetch_add(1);
-    k_gen_upsample<true><<<dim3(rows_grid(h), B), kRowWarps * 32, smem, s>>>(d, max_lz);
-    return check_launch("bfm_gen_finish");
+    const size_t smem = ((size_t)ny * lz + 2 * kWR * lz) * sizeof(float);
+    if (smem > 200 * 1024) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: low-res rows too long for shared memory");
+    if (s0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: grid too large");
+    if (smem > 40 * 1024)
+        cudaFuncSetAttribute(k_gen_upsample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = min(256, (s2 + 31) / 32 * 32);
+    k_gen_upsample<<<dim3((s1 + kUR - 1) / kUR, s0, B), threads, smem, st>>>(d, lz, ny);
+    rc = check_launch("bfm_gen_finish");
+    if (rc) return rc;
+    const int64_t plane = (int64_t)s1 * s2;
+    if (vec) {
+        k_gen_normalize<4><<<dim3((unsigned)((plane / 4 + 255) / 256), s0, B), 256, 0, st>>>(d);
+        rc = check_launch("bfm_gen_finish");
+        if (rc) return rc;
+    }
+    if (scalar) {
+        k_gen_normalize<1><<<dim3((unsigned)((plane + 255) / 256), s0, B), 256, 0, st>>>(d);
+        rc = check_launch("bfm_gen_finish");
+    }
+    return rc;
 }
 
 int bfm_gen_run(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {

@@ -51,8 +51,19 @@ class HostDraws:
         """Volume-sized N(0,1) field: None => generated in-kernel (Philox)."""
         return None
 
+    _seed_base, _seed_count = None, 0
+
     def seed64(self):
-        return int(np.random.randint(0, 2 ** 62))
+        """Philox key of one sample's volume-sized fields.  Derived from ONE draw of the numpy generator (taken
+        the first time a key is needed) and a counter (splitmix64), so that it does not interleave extra draws
+        with the reference's scalar draw sequence."""
+        if self._seed_base is None:
+            self._seed_base = int(np.random.randint(0, 2 ** 62))
+        self._seed_count += 1
+        z = (self._seed_base + 0x9E3779B97F4A7C15 * self._seed_count) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
 
 
 class ReplayDraws(HostDraws):

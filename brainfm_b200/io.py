@@ -137,14 +137,25 @@ class DeviceVolumeCache:
         self._bytes += nbytes
         return t
 
-    def refresh(self, path, kind, host_tensor):
-        """Overwrite a cached volume with fresh host data (asynchronous copy from pinned memory on the
-        current stream); 'f32' volumes are made finite on the device afterwards."""
-        import ctypes as C
-        from . import _lib
+    def upload(self, path, kind, host_tensor):
+        """Overwrite a cached volume with fresh host data: asynchronous copy from pinned memory on the current
+        stream.  'f32' volumes must be passed through sanitize() before they are used."""
         t = self.get(path, kind)
         t.copy_(host_tensor, non_blocking=True)
-        if kind == "f32":
-            _lib.check(_lib.lib().bfm_sanitize_f32(t.data_ptr(), t.numel(),
-                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return t
+
+    def sanitize(self, path, kind="f32"):
+        """torch.nan_to_num in place on the current stream (Generator/utils.py:305)."""
+        import ctypes as C
+        from . import _lib
+        if kind != "f32":
+            return
+        t = self.get(path, kind)
+        _lib.check(_lib.lib().bfm_sanitize_f32(t.data_ptr(), t.numel(),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def refresh(self, path, kind, host_tensor):
+        """upload() + sanitize() on the current stream."""
+        t = self.upload(path, kind, host_tensor)
+        self.sanitize(path, kind)
         return t

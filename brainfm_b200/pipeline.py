@@ -1,0 +1,95 @@
+"""Host <-> device pipelining around BaseGen.generate_batch.
+
+The reference generator reads every volume from disk, decodes it on the host and uploads the crop for every
+sample (Generator/utils.py:296-305, datasets.py:312,364), synchronously on the training stream.  Here the
+volumes of batch k+1 are uploaded and the results of batch k-1 are downloaded on their own CUDA streams while
+batch k is being generated, so that in steady state a step costs max(upload, generate, download) instead of
+their sum (PCIe is full duplex; the copy engines run beside the SMs).
+
+    pipe = HostPipeline(ds)
+    t = pipe.submit(indices, uploads=[(path, kind, pinned_host_tensor), ...])   # asynchronous
+    ...
+    items, host_out = t.wait()      # host_out: pinned (B, 1, *size) float32 'input' volumes
+
+Hazards are ordered with events: an upload into a cached device volume waits for the last batch that read
+that volume; a download waits for the batch that produced it; a pinned output slot is reused only after its
+previous download has been waited for by the caller.
+"""
+import torch
+
+
+class _Ticket:
+    def __init__(self, items, host_out, event):
+        self.items, self.host_out, self._event = items, host_out, event
+
+    def wait(self):
+        self._event.synchronize()
+        return self.items, self.host_out
+
+
+class HostPipeline:
+    def __init__(self, ds, depth=3, key='input'):
+        self.ds = ds
+        self.device = ds.device
+        self.key = key
+        self.copy_in = torch.cuda.Stream(device=self.device)
+        self.copy_out = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self._slots = []                 # pinned host output buffers (ring)
+        self._slot_events = []           # download event of the last use of each slot
+        self._next = 0
+        self._last_reader = {}           # (path, kind) -> event of the last batch that read the volume
+
+    def _slot(self, shape):
+        if not self._slots:
+            for _ in range(self.depth):
+                self._slots.append(torch.empty(shape, dtype=torch.float32).pin_memory())
+                self._slot_events.append(None)
+        k = self._next
+        self._next = (self._next + 1) % self.depth
+        if tuple(self._slots[k].shape) != tuple(shape):
+            self._slots[k] = torch.empty(shape, dtype=torch.float32).pin_memory()
+        ev = self._slot_events[k]
+        if ev is not None:
+            ev.synchronize()             # the caller is done with this slot `depth` submissions later
+        return k
+
+    def submit(self, indices, uploads=()):
+        ds = self.ds
+        main = torch.cuda.current_stream(self.device)
+        # 1. uploads on the copy-in stream (after the last reader of each destination volume)
+        if uploads:
+            with torch.cuda.stream(self.copy_in):
+                for path, kind, host in uploads:
+                    ev = self._last_reader.get((path, kind))
+                    if ev is not None:
+                        self.copy_in.wait_event(ev)
+                    ds.cache.upload(path, kind, host)     # copies only: the copy stream never waits for an SM
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.copy_in)
+            main.wait_event(ev_in)
+            for path, kind, _ in uploads:
+                ds.cache.sanitize(path, kind)             # nan_to_num on the compute stream
+        # 2. generation on the caller's stream
+        items = ds.generate_batch(list(indices))
+        ev_done = torch.cuda.Event()
+        ev_done.record(main)
+        for path, kind, _ in uploads:
+            self._last_reader[(path, kind)] = ev_done
+        # 3. download on the copy-out stream
+        outs = [it[4][self.key] if not isinstance(it[4], list) else torch.cat([s[self.key] for s in it[4]], 0)
+                for it in items]
+        shape = (sum(o.shape[0] for o in outs), *outs[0].shape[1:])
+        k = self._slot(shape)
+        host = self._slots[k]
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(ev_done)
+            row = 0
+            for o in outs:
+                host[row:row + o.shape[0]].copy_(o, non_blocking=True)
+                o.record_stream(self.copy_out)
+                row += o.shape[0]
+            ev_out = torch.cuda.Event()
+            ev_out.record(self.copy_out)
+        self._slot_events[k] = ev_out
+        return _Ticket(items, host, ev_out)

@@ -177,10 +177,10 @@ class Arena:
         ev.record()
         self.slots[self.cur]["event"] = ev
 
-    def view(self, off, count, dtype):
-        """Device tensor view of arena bytes [off, off+count*itemsize)."""
+    def view(self, off, count, dtype, slot=None):
+        """Device tensor view of arena bytes [off, off+count*itemsize) of a slot (default: the current one)."""
         item = torch.empty((), dtype=dtype).element_size()
-        return self.slots[self.cur]["dev"][off:off + count * item].view(dtype)
+        return self.slots[self.cur if slot is None else slot]["dev"][off:off + count * item].view(dtype)
 
 
 class DeviceTables:
@@ -208,6 +208,31 @@ class DeviceTables:
         base = dev.data_ptr()
         return [base + o for o in offs]
 
+    def prebuild(self, size):
+        """Build and upload, in one copy, the tables of every zoom the generator can ask for on a grid of this
+        size: n_in -> n_out for n_in = 1..n_out with the factor n_out/n_in (small random grids) and with
+        1/(n_in/n_out) (low-res grid back to the training grid), plus the candidate lists.  A table miss later on
+        still works but costs a synchronous upload in the middle of the stream."""
+        todo_z, todo_c = [], []
+        for n_out in sorted(set(int(v) for v in size)):
+            for n_in in range(1, n_out + 1):
+                for factor in (n_out / n_in, 1 / (n_in / n_out)):
+                    key = (n_in, float(factor), n_out)
+                    if key not in self._zoom and key not in [k for k, _ in todo_z]:
+                        todo_z.append((key, zoom_tables_host(*key)))
+                key = (n_in, float(n_out / n_in), n_out)
+                if key not in self._cand:
+                    todo_c.append((key, zoom_candidates_host(*key)))
+        if not todo_z and not todo_c:
+            return
+        arrays = [a for _, tabs in todo_z for a in tabs] + [c for _, c in todo_c]
+        addrs = self._upload(arrays)
+        for n, (key, _) in enumerate(todo_z):
+            self._zoom[key] = tuple(addrs[4 * n:4 * n + 4])
+        base = 4 * len(todo_z)
+        for n, (key, c) in enumerate(todo_c):
+            self._cand[key] = (addrs[base + n], int(c.size))
+
     def zoom(self, n_in, factor, n_out):
         """Device addresses (lo, hi, wl, wh) of one axis."""
         key = (int(n_in), float(factor), int(n_out))
@@ -225,6 +250,45 @@ class DeviceTables:
             c = zoom_candidates_host(*key)
             hit = (self._upload([c])[0], int(c.size))
             self._cand[key] = hit
+        return hit
+
+    def zoom_tab(self, n_in, n_out, inverse=False):
+        """A filled _lib.ZoomTab for the three axes of a zoom from shape n_in to shape n_out (cached; assign it
+        to a descriptor field with `desc.tab = ...`, a struct copy).  The factor is what the caller of
+        myzoom_torch passes: n_out/n_in (deformation and bias grids, datasets.py:210, utils.py:585), or with
+        inverse=True 1/(n_in/n_out) (back to the training grid, datasets.py:340)."""
+        key = (tuple(n_in), tuple(n_out), inverse)
+        hit = self._zoom.get(key)
+        if hit is None:
+            a, b = np.array(key[0]), np.array(key[1])
+            factor = 1 / (a / b) if inverse else b / a
+            assert tuple(zoom_newsize(key[0], factor)) == key[1], (key, factor)
+            hit = _lib.ZoomTab()
+            set_zoom_tab(hit, self, key[0], factor, key[1])
+            self._zoom[key] = hit
+        return hit
+
+    def deform_template(self, size, fs):
+        """A _lib.Deform with everything that only depends on (output size, small-grid shape) filled in: zoom
+        tables, candidate lists, centre.  fs=None: no nonlinear field."""
+        key = ("deform", tuple(size), None if fs is None else tuple(fs))
+        hit = self._zoom.get(key)
+        if hit is None:
+            hit = _lib.Deform()
+            for a in range(3):
+                hit.size[a] = int(size[a])
+                hit.ctr[a] = float(np.float32((size[a] - 1) / 2))
+            if fs is None:
+                for a in range(3):
+                    hit.cand[a], hit.ncand[a] = self.ends(size[a])
+            else:
+                factor = np.array(size) / np.array(fs)
+                assert tuple(zoom_newsize(fs, factor)) == tuple(size), (fs, size)
+                hit.ftab = self.zoom_tab(fs, size)
+                for a in range(3):
+                    hit.fs[a] = int(fs[a])
+                    hit.cand[a], hit.ncand[a] = self.cand(fs[a], factor[a], int(size[a]))
+            self._zoom[key] = hit
         return hit
 
     def ends(self, n_out):
@@ -260,6 +324,23 @@ def fill_zoom_tab(tab, arena, tables):
         tab.hi[ax] = arena.put(hi)
         tab.wl[ax] = arena.put(wl)
         tab.wh[ax] = arena.put(wh)
+
+
+def make_deform(tables, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None):
+    """A filled _lib.Deform: the cached template of (size, small-grid shape) plus this sample's affine, source
+    shape and small random grid (the only array that goes through the arena)."""
+    fs = None if fsmall_host is None else fsmall_host.shape[:3]
+    d = _lib.Deform.from_buffer_copy(tables.deform_template(size, fs))
+    d.src[:] = [int(v) for v in src[:3]]
+    d.A[:] = np.asarray(A, dtype=np.float32).reshape(-1).tolist()
+    d.c2[:] = np.asarray(c2, dtype=np.float32).tolist()
+    d.photo = int(bool(photo))
+    if F_full_ptr is not None:
+        d.F_full = F_full_ptr
+        d.ncand[:] = [0, 0, 0]
+    if fsmall_host is not None:
+        d.fsmall = arena.put(fsmall_host)
+    return d
 
 
 def fill_deform(d, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None, tables=None):
