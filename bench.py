@@ -197,8 +197,11 @@ def main():
     n_subjects = 2 * BATCH          # the end-to-end arm alternates between two sets of subjects
     subs = make_inputs(n_subjects)
     ds = build_dataset(subs, device)
-    np.random.seed(1000 + rank)
-    torch.manual_seed(1000 + rank)
+    from brainfm_b200 import parallel as par
+    # the path shards by sample: every rank generates its own stream of batches (disjoint random streams),
+    # there is no data-path collective; only the timing below is reduced (max over ranks)
+    np.random.seed(par.rank_seed(1000, rank))
+    torch.manual_seed(par.rank_seed(1000, rank))
     idxs = list(range(BATCH))
 
     def barrier():
@@ -239,8 +242,8 @@ def main():
     # per sample: gather-read of the GMM image and of the T1 volume over the bbox crop (2 * 4*Nc) + write I_bf,
     # BFlog and the raw warped T1 (3 * 4*N)
     N = SIZE ** 3
-    np.random.seed(1000 + rank)
-    torch.manual_seed(1000 + rank)
+    np.random.seed(par.rank_seed(1000, rank))
+    torch.manual_seed(par.rank_seed(1000, rank))
     items = ds.generate_batch(idxs)
     nc = []
     ns = []

@@ -436,7 +436,7 @@ __device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B
     const bfm_deform &d = s.d;
     const DefRegs g = load_def(d);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const int i = blockIdx.y;
+    const int i = (s.x_count > 0 ? s.x_begin : 0) + blockIdx.y;
     const int j0 = blockIdx.x * rpb, j1 = min(j0 + rpb, g.s1);
     const float *__restrict__ bfsmall = s.bfsmall;
     const int fw = FIELD == 1 ? d.fs[2] * 3 : 0;      // floats per row of the deformation small grid
@@ -629,7 +629,8 @@ __global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sampl
     {   // each instantiation handles the samples of its own kind
         const bfm_gen_sample *sp = S + blockIdx.z;
         if ((sp->mix[0] != nullptr) != MIX || sp->n_aux != NAUX) return;
-        if ((int)blockIdx.y >= sp->d.size[0] || (int)blockIdx.x * rpb >= sp->d.size[1]) return;
+        const int nx = sp->x_count > 0 ? sp->x_count : sp->d.size[0];
+        if ((int)blockIdx.y >= nx || (int)blockIdx.x * rpb >= sp->d.size[1]) return;
     }
     stage_desc(&sh.sd, S + blockIdx.z);
     float *t1F = smem, *t1B = smem + t1f_cap;
@@ -985,7 +986,10 @@ int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
             t1b = max(t1b, s.bs[1] * s.bs[2]);
             wb = max(wb, s.bs[2]);
         }
-        s0 = max(s0, s.d.size[0]); s1 = max(s1, s.d.size[1]); s2 = max(s2, s.d.size[2]);
+        if (s.x_count < 0 || s.x_begin < 0 || (s.x_count > 0 && s.x_begin + s.x_count > s.d.size[0]))
+            return fail(BFM_E_INVALID, "%s", "bfm_gen_warp: slab outside the grid");
+        s0 = max(s0, s.x_count > 0 ? s.x_count : s.d.size[0]);
+        s1 = max(s1, s.d.size[1]); s2 = max(s2, s.d.size[2]);
     }
     const size_t smem = (size_t)(t1f + t1b) * sizeof(float);
     if (wf + wb > kT2 || smem > 160 * 1024)

@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 2
+#define BFM_ABI_VERSION 3
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -212,6 +212,11 @@ typedef struct bfm_gen_sample {
     float *aux_raw[BFM_MAX_AUX];
     float *aux_out[BFM_MAX_AUX];
     int *aux_mm;
+    /* Slab mode (one volume cut into x-slabs of the output grid, one per GPU): bfm_gen_warp only evaluates the
+       output planes [x_begin, x_begin + x_count); x_count == 0 means the whole grid.  i_bf, bflog_out and
+       aux_raw keep their whole-volume indexing: the caller passes pointers biased by -x_begin planes (the
+       flipped plane for bflog_out) so that only the owned planes have to exist. */
+    int x_begin, x_count;
 } bfm_gen_sample;
 
 /* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,

@@ -106,3 +106,30 @@ def test_device_band_tables_match_host(n_in, n_out, sigma):
     assert np.array_equal(to_np(ds), start)
     np.testing.assert_allclose(to_np(dw), w, rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(to_np(dw).sum(1), w.sum(1), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["g64_s0", "g64_s5_lowres"])
+def test_slab_mode_single_rank_matches_oracle(name):
+    """Slab mode (x-slabs + plane exchange, Generator/slab.py) on one rank: same volume as the oracle."""
+    from brainfm_b200.Generator.slab import generate_slab
+    item, orc = oracle_case(name)
+    ref = mg.flatten(item)
+    got, ds, draws = cuda_case(name, orc.log, run=lambda ds: generate_slab(ds, 0, 0, 1))
+    assert got["x_range"] == (0, int(ds.size[0]))
+    np.testing.assert_allclose(to_np(got["input"]), to_np(ref["sample0.input"]), rtol=RTOL, atol=ATOL)
+    if "bias_field_log" in got:
+        assert np.array_equal(to_np(got["bias_field_log"]), to_np(ref["sample0.bias_field_log"]))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_slab_mode_two_ranks():
+    """Two ranks over NCCL: assembled slabs == oracle within tolerance and == the single-rank slab run bit for bit."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("g64_s0", "g64_s5_lowres"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29533",
+                            os.path.join(root, "tests", "_slab_worker.py"), name],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
