@@ -247,66 +247,72 @@ __device__ __forceinline__ int label_index(float g) {
     return min(max(r, 0), 255);
 }
 
-// Vector path (n2 % 4 == 0): grid = (groups per x-plane / 256, n0, B); no integer division by runtime values
-// except one per thread.
+// Vector path (n2 % 4 == 0): block = one x plane of the crop (blockIdx.y) and one of gridDim.x tiles of its rows;
+// the 512-entry mean/std table is loaded once per block and the threads walk the (row, z-group) items of the tile
+// with carry arithmetic (no division in the loop).  Only the handful of descriptor fields the stage needs is read.
 __global__ void __launch_bounds__(256) k_gen_gmm_planes(const bfm_gen_sample *__restrict__ S) {
-    __shared__ bfm_gen_sample sd;
     __shared__ float lut[512];
     const bfm_gen_sample *sp = S + blockIdx.z;
-    const int x = blockIdx.y;
-    {
-        const int *bb = sp->bbox;
-        if (x >= sp->d.src[0] || (sp->d.src[2] & 3) || x < bb[0] || x >= bb[3]) return;
-    }
-    stage_desc(&sd, sp);
-    const bfm_gen_sample &s = sd;
-    const int n1 = s.d.src[1], n2 = s.d.src[2];
-    const int n2v = n2 >> 2;
-    const int b1 = s.bbox[1], b2 = s.bbox[2], e1 = s.bbox[4], e2 = s.bbox[5], b0 = s.bbox[0];
-    // block covers 256 consecutive groups of this plane: skip if all of its rows are outside [b1, e1)
-    const int g0 = blockIdx.x * blockDim.x;
-    if (g0 >= n1 * n2v) return;
-    {
-        const int ya = g0 / n2v, yb = min(g0 + (int)blockDim.x - 1, n1 * n2v - 1) / n2v;
-        if (yb < b1 || ya >= e1) return;
-    }
-    for (int q = threadIdx.x; q < 512; q += blockDim.x) lut[q] = q < 256 ? __ldg(s.mu + q) : __ldg(s.sigma + q - 256);
+    const int n0 = sp->d.src[0], n1 = sp->d.src[1], n2 = sp->d.src[2];
+    if (n2 & 3) return;                                            // handled by k_gen_gmm
+    const int *bb = sp->bbox;
+    const int b0 = bb[0], b1 = bb[1], b2 = bb[2], e0 = bb[3], e1 = bb[4], e2 = bb[5];
+    const int x = b0 + blockIdx.y;
+    if (x >= e0 || x >= n0) return;
+    // rows of this tile
+    const int rows = e1 - b1, per = (rows + gridDim.x - 1) / gridDim.x;
+    const int ya = b1 + blockIdx.x * per, yb = min(ya + per, e1);
+    if (ya >= yb) return;
+    const float *mu = sp->mu, *sigma = sp->sigma;
+    for (int q = threadIdx.x; q < 512; q += blockDim.x) lut[q] = q < 256 ? __ldg(mu + q) : __ldg(sigma + q - 256);
     __syncthreads();
-    const int gq = g0 + threadIdx.x;
-    if (gq >= n1 * n2v) return;
-    const int y = gq / n2v, z = (gq - y * n2v) << 2;
-    if (y < b1 || y >= e1 || z + 3 < b2 || z >= e2) return;
-    const int p0 = (x * n1 + y) * n2 + z;
-    float ev[4];
-    if (!s.eps_gmm) {
-        const float4 e = philox_normal4(s.seed, 0u, (uint64_t)(p0 >> 2));
-        ev[0] = e.x; ev[1] = e.y; ev[2] = e.z; ev[3] = e.w;
-    } else {
-        const int c1 = e1 - b1, c2 = e2 - b2;
-        const float *er = s.eps_gmm + ((x - b0) * c1 + (y - b1)) * c2 - b2;
+    const int zg0 = b2 >> 2, wz = ((e2 + 3) >> 2) - zg0;           // z groups touched by the crop
+    if (wz <= 0) return;
+    const int items = (yb - ya) * wz;
+    const int dy = blockDim.x / wz, dz = blockDim.x - dy * wz;      // one step of blockDim.x items
+    int y = ya + threadIdx.x / wz, zg = zg0 + threadIdx.x % wz;
+    const float *__restrict__ eps = sp->eps_gmm;
+    const void *labels = sp->labels;
+    const int is_u8 = sp->label_is_u8;
+    const uint64_t seed = sp->seed;
+    float *__restrict__ syn = sp->syn;
+    const int c1 = e1 - b1, c2 = e2 - b2;
+    for (int f = threadIdx.x; f < items; f += blockDim.x) {
+        const int z = zg << 2;
+        const int p0 = (x * n1 + y) * n2 + z;
+        float ev[4];
+        if (!eps) {
+            const float4 e = philox_normal4(seed, 0u, (uint64_t)(p0 >> 2));
+            ev[0] = e.x; ev[1] = e.y; ev[2] = e.z; ev[3] = e.w;
+        } else {
+            const float *er = eps + ((x - b0) * c1 + (y - b1)) * c2 - b2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ev[q] = (z + q >= b2 && z + q < e2) ? __ldg(er + z + q) : 0.f;
-    }
-    int lab[4];
-    if (s.label_is_u8) {
-        const uint32_t w = __ldg((const uint32_t *)((const uint8_t *)s.labels + p0));
+            for (int q = 0; q < 4; ++q) ev[q] = (z + q >= b2 && z + q < e2) ? __ldg(er + z + q) : 0.f;
+        }
+        int lab[4];
+        if (is_u8) {
+            const uint32_t w = __ldg((const uint32_t *)((const uint8_t *)labels + p0));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int l = (w >> (8 * q)) & 0xff;
+                lab[q] = (l == 77) ? 2 : l;
+            }
+        } else {
+            const float4 v = __ldg((const float4 *)((const float *)labels + p0));
+            lab[0] = label_index(v.x); lab[1] = label_index(v.y); lab[2] = label_index(v.z); lab[3] = label_index(v.w);
+        }
+        float o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int l = (w >> (8 * q)) & 0xff;
-            lab[q] = (l == 77) ? 2 : l;
+            const float v = __fadd_rn(lut[lab[q]], __fmul_rn(lut[256 + lab[q]], ev[q]));
+            o[q] = v < 0.f ? 0.f : v;
         }
-    } else {
-        const float4 f = __ldg((const float4 *)((const float *)s.labels + p0));
-        lab[0] = label_index(f.x); lab[1] = label_index(f.y); lab[2] = label_index(f.z); lab[3] = label_index(f.w);
+        // positions just outside the crop are never gathered with a non-zero weight; writing them keeps the
+        // store 128-bit (the values are finite, which is all the warp kernel's always-read hi taps need)
+        *(float4 *)(syn + p0) = make_float4(o[0], o[1], o[2], o[3]);
+        y += dy; zg += dz;
+        if (zg >= zg0 + wz) { zg -= wz; ++y; }
     }
-    float o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float v = __fadd_rn(lut[lab[q]], __fmul_rn(lut[256 + lab[q]], ev[q]));
-        o[q] = v < 0.f ? 0.f : v;
-    }
-    // positions just outside the crop are never gathered; writing them keeps the store 128-bit
-    *(float4 *)(s.syn + p0) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(256) k_gen_gmm(const bfm_gen_sample *__restrict__ S) {
@@ -644,10 +650,11 @@ __global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sampl
 // weight is uniform across the warp.  Axis 2: a thread owns one output, taps are contiguous.
 template <int VEC>
 __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restrict__ S, int pass) {
-    __shared__ bfm_gen_sample sd;
-    if (pass >= S[blockIdx.y].n_band) return;
-    stage_desc(&sd, S + blockIdx.y);
-    const bfm_gen_sample &s = sd;
+    // persistent blocks: a few hundred per sample, each thread walks its outputs with carry arithmetic; only
+    // the descriptor fields this pass needs are read (no 936-byte staging per block)
+    const bfm_gen_sample &s = S[blockIdx.y];
+    const int n_band = s.n_band;
+    if (pass >= n_band) return;
     int sh0 = s.d.size[0], sh1 = s.d.size[1], sh2 = s.d.size[2];
     for (int q = 0; q < pass; ++q) {
         const int ax = s.band[q].axis, no = s.band[q].n_out;
@@ -658,7 +665,7 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
     const int o0 = axis == 0 ? b.n_out : sh0, o1 = axis == 1 ? b.n_out : sh1, o2 = axis == 2 ? b.n_out : sh2;
     if (VEC == 4 && (axis == 2 || (sh2 & 3))) return;        // handled by the scalar instantiation
     if (VEC == 1 && !(axis == 2 || (sh2 & 3))) return;
-    const bool last = (pass == s.n_band - 1);
+    const bool last = (pass == n_band - 1);
     const float *__restrict__ in = pass == 0 ? s.i_bf : s.tmp[(pass - 1) & 1];
     float *__restrict__ out = last ? s.lowres : s.tmp[pass & 1];
     const int stride = axis == 0 ? sh1 * sh2 : axis == 1 ? sh2 : 1;
@@ -668,10 +675,15 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
     const int zf0 = s.zero_first[0], zf1 = s.zero_first[1], zf2 = s.zero_first[2];
     const float nstd = s.noise_std;
     const float *__restrict__ eps = s.eps_noise;
+    const uint64_t seed = s.seed;
     const int *__restrict__ bstart = b.start;
     const float *__restrict__ bw = b.w;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-        const int kv = p % o2v, j = (p / o2v) % o1, i = p / (o1 * o2v);
+    // (i, j, kv) of this thread's first output and of one grid-stride step
+    const int step = gridDim.x * blockDim.x;
+    const int p_first = blockIdx.x * blockDim.x + threadIdx.x;
+    int kv = p_first % o2v, j = (p_first / o2v) % o1, i = p_first / (o1 * o2v);
+    const int dk = step % o2v, dj = (step / o2v) % o1, di = step / (o1 * o2v);
+    for (int p = p_first; p < total; p += step) {
         const int k = kv * VEC;
         const int q = axis == 0 ? i : axis == 1 ? j : k;
         const int st = __ldg(bstart + q);
@@ -696,7 +708,7 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
         const int op = (i * o1 + j) * o2 + k;
         if (last) {
             float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!eps && VEC == 4) e4 = philox_normal4(s.seed, 1u, (uint64_t)(op >> 2));   // o2 % 4 == 0 here
+            if (!eps && VEC == 4) e4 = philox_normal4(seed, 1u, (uint64_t)(op >> 2));   // o2 % 4 == 0 here
             const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
             for (int c = 0; c < VEC; ++c) {
@@ -705,7 +717,7 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
                 if (eps) e = __ldg(eps + op + c);
                 else if (VEC == 4) e = ev[c];
                 else {
-                    const float4 g4 = philox_normal4(s.seed, 1u, (uint64_t)(op >> 2));
+                    const float4 g4 = philox_normal4(seed, 1u, (uint64_t)(op >> 2));
                     const int r = op & 3;
                     e = r == 0 ? g4.x : r == 1 ? g4.y : r == 2 ? g4.z : g4.w;
                 }
@@ -715,6 +727,9 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
         }
         if (VEC == 4) *(float4 *)(out + op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         else out[op] = acc[0];
+        kv += dk; j += dj; i += di;
+        if (kv >= o2v) { kv -= o2v; ++j; }
+        if (j >= o1) { j -= o1; ++i; }
     }
 }
 
@@ -929,7 +944,9 @@ int bfm_gen_gmm(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *s
     }
     if (plane_groups > 0) {
         if (max_n0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_gmm: grid too large");
-        k_gen_gmm_planes<<<dim3((unsigned)((plane_groups + 255) / 256), max_n0, B), 256, 0, (cudaStream_t)stream>>>(d);
+        // blockIdx.y walks the x planes of the crop (<= src[0]); a few row tiles per plane when the batch is small
+        const int tiles = (int)min((int64_t)8, max((int64_t)1, (int64_t)(4 * 148) / ((int64_t)max_n0 * B)));
+        k_gen_gmm_planes<<<dim3(tiles, max_n0, B), 256, 0, (cudaStream_t)stream>>>(d);
         rc = check_launch("bfm_gen_gmm");
         if (rc) return rc;
     }
@@ -1024,6 +1041,8 @@ int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, vo
     if (rc) return rc;
     int maxp = 0;
     for (int b = 0; b < B; ++b) maxp = h[b].n_band > maxp ? h[b].n_band : maxp;
+    // persistent blocks: ~16 per SM over the whole batch
+    const int64_t band_blocks = max((int64_t)8, (int64_t)(16 * 148 + B - 1) / B);
     for (int pass = 0; pass < maxp; ++pass) {
         int64_t most4 = 0, most1 = 0;
         for (int b = 0; b < B; ++b) {
@@ -1038,12 +1057,12 @@ int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, vo
             else most4 = n / 4 > most4 ? n / 4 : most4;
         }
         if (most4 > 0) {
-            k_gen_band<4><<<dim3((unsigned)((most4 + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(d, pass);
+            k_gen_band<4><<<dim3((unsigned)min((most4 + 255) / 256, band_blocks), B), 256, 0, (cudaStream_t)stream>>>(d, pass);
             int rc2 = check_launch("bfm_gen_resample");
             if (rc2) return rc2;
         }
         if (most1 > 0) {
-            k_gen_band<1><<<dim3((unsigned)((most1 + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(d, pass);
+            k_gen_band<1><<<dim3((unsigned)min((most1 + 255) / 256, band_blocks), B), 256, 0, (cudaStream_t)stream>>>(d, pass);
             int rc2 = check_launch("bfm_gen_resample");
             if (rc2) return rc2;
         }

@@ -1,0 +1,73 @@
+"""512^3 volume generated in slab mode on N GPUs (BASELINE.json configs[4], second half): x-slabs of the output
+grid, plane exchange over NCCL for the x stencils.  Launch with torchrun for N > 1:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/slab_bench.py
+
+One JSON line on rank 0: ms per volume (max over ranks, CUDA events), volumes/s, voxels/s."""
+import json
+import os
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from brainfm_b200 import io as bio, parallel as par
+from brainfm_b200.Generator import BaseGen
+from brainfm_b200.Generator.slab import generate_slab
+from tests import _inputs as ti
+
+
+def main():
+    size = int(os.environ.get("SLAB_SIZE", "512"))
+    steps = int(os.environ.get("SLAB_STEPS", "5"))
+    rank, world, local = par.init()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    half = ti.brain_like_labels((size // 2,) * 3, seed=7)
+    lab = np.repeat(np.repeat(np.repeat(half, 2, 0), 2, 1), 2, 2)       # nearest x2
+    root = tempfile.mkdtemp(prefix="bfm_slab_")
+    stem = os.path.join(root, "HCP.sub00.")
+    bio.register_volume(stem + "T1w.nii", np.zeros((2, 2, 2), dtype=np.float32))
+    bio.register_volume(stem + "generation_labels.nii", lab)
+    with open(os.path.join(root, "train.txt"), "w") as f:
+        f.write(stem + "T1w.nii\n")
+    cfg = ti.default_cfg((size,) * 3)
+    for k in vars(cfg.task):
+        setattr(cfg.task, k, False)
+    cfg.split_root = root
+    ds = BaseGen(cfg, dev)
+    ds.write_bflog = True
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    np.random.seed(4321)
+    torch.manual_seed(4321)                  # the same draws on every rank
+    for _ in range(2):
+        generate_slab(ds, 0, rank, world)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = generate_slab(ds, 0, rank, world)
+    e1.record()
+    sync()
+    ms = par.all_reduce_max(e0.elapsed_time(e1) / steps, device=dev)
+    if rank == 0:
+        print(json.dumps({"workload": "one %d^3 BaseGen sample (input + bias_field_log), slab mode" % size,
+                          "n_gpus": world, "ms_per_volume": ms, "volumes_per_s": 1e3 / ms,
+                          "Mvoxels_per_s": size ** 3 / ms / 1e3, "slab_planes": list(out["x_range"]),
+                          "steps": steps}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
