@@ -50,6 +50,26 @@ def bench_cfg():
     return cfg
 
 
+def ncu_traffic(kernel_prefix):
+    """dram__bytes_read + dram__bytes_write (bytes per launch) of the newest committed ncu full capture."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_v*_summary.csv")))
+    for path in reversed(files):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:]
+                    if r[0].replace("void ", "").startswith(kernel_prefix)]
+            if vals:
+                return float(np.mean(vals)), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,6 +280,7 @@ def main():
     chain_bytes = 4 * nc_mean + 16 * N + 12 * ns_mean + (4 * nc_mean + 4 * N)
     chain_gbs = chain_bytes * value / world / 1e9
 
+    traffic, traffic_src = ncu_traffic("k_gen_warp<1")
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "value": value, "stage_ms_per_step": stage_ms,
@@ -319,7 +340,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
                 "roofline": {"bound": "hbm", "kernel": "k_gen_warp<1,0> (gather of synth + T1, gamma, bias; batch 8)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src,
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": warp_ms},
                 "chain": {"algorithmic_bytes_per_sample": chain_bytes, "achieved_gbs": chain_gbs,
                           "frac_of_peak": chain_gbs / peak, "nc_over_n": nc_mean / N, "ns_over_n": ns_mean / N,
