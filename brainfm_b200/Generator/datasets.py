@@ -37,6 +37,8 @@ _STOCK_STEPS = ['gamma', 'bias_field', 'resample', 'noise']
 # partial-volume blend weights of get_contrast (datasets.py:452): 0.02 * torch.arange(50) in float32
 _PV_V = np.arange(50).astype(np.float32) * np.float32(0.02)
 _PV_W = np.float32(1) - _PV_V
+_GMM_SCALE = np.array([[200], [20]], dtype=np.float32)     # mus = 25 + 200*u, sigmas = 5 + 20*u (datasets.py:432-433)
+_GMM_SHIFT = np.array([[25], [5]], dtype=np.float32)
 
 
 class BaseGen(Dataset):
@@ -64,6 +66,7 @@ class BaseGen(Dataset):
         self._ws = {}                  # persistent device scratch of the fused chain (see _workspace)
         self._info = {}                # t1 path -> modality table
         self._inputs = {}              # volume path -> (img, aff, res)
+        self._c2 = {}                  # source shape -> centre (float32)
         self.write_bflog = None        # None: follow the task list; True/False: force
         self.prepare_tasks()
         self.prepare_paths()
@@ -212,14 +215,20 @@ class BaseGen(Dataset):
 
     # ---- deformation (datasets.py:187-303) --------------------------------------------------------
     def random_affine_transform(self, shp):
-        """A (3,3) and c2 (3,) as float32 numpy arrays (the reference's float32 tensors, datasets.py:187-201)."""
+        """A (3,3) and c2 (3,) as float32 numpy arrays (the reference's float32 tensors, datasets.py:187-201).
+        The per-component float64 arithmetic is evaluated on python floats (same IEEE operations in the same
+        order as the reference's numpy expressions on 3-vectors)."""
         a, rng = self.synth_args, self.rng
-        rotations = (2 * a.max_rotation * rng.rand3("aff.rot") - a.max_rotation) / 180.0 * np.pi
-        shears = (2 * a.max_shear * rng.rand3("aff.shear") - a.max_shear)
-        scalings = 1 + (2 * a.max_scaling * rng.rand3("aff.scale") - a.max_scaling)
-        scaling_factor_distances = np.prod(scalings) ** .33333333333
+        mr, ms, mc = a.max_rotation, a.max_shear, a.max_scaling
+        rotations = np.array([(2 * mr * u - mr) / 180.0 * np.pi for u in rng.rand3("aff.rot").tolist()])
+        shears = [(2 * ms * u - ms) for u in rng.rand3("aff.shear").tolist()]
+        scalings = [1 + (2 * mc * u - mc) for u in rng.rand3("aff.scale").tolist()]
+        scaling_factor_distances = (scalings[0] * scalings[1] * scalings[2]) ** .33333333333
         A = make_affine_matrix(rotations, shears, scalings).astype(np.float32)
-        c2 = ((np.array(shp[0:3]) - 1) / 2).astype(np.float32)
+        key = tuple(int(v) for v in shp[0:3])
+        c2 = self._c2.get(key)
+        if c2 is None:
+            c2 = self._c2[key] = ((np.array(key) - 1) / 2).astype(np.float32)
         if a.random_shift:
             max_shift = torch.tensor(np.array(shp[0:3]) - self.size, dtype=torch.float) / 2
             max_shift[max_shift < 0] = 0
@@ -227,17 +236,23 @@ class BaseGen(Dataset):
                                           - max_shift)).to(torch.float32).numpy()
         return scaling_factor_distances, A, c2
 
-    def random_nonlinear_transform(self, photo_mode, spac):
-        """Returns the SMALL random grid (host float32, [sx,sy,sz,3]); the full-resolution field F is never
+    def random_nonlinear_transform(self, photo_mode, spac, arena=None):
+        """Returns the SMALL random grid (host float32, [sx,sy,sz,3]) and, with an arena, its device address:
+        the draw is written straight into the pinned plan arena.  The full-resolution field F is never
         materialised unless somebody reads deform_dict['F'] or the SVF integration is requested."""
         a, rng = self.synth_args, self.rng
-        nonlin_scale = a.nonlin_scale_min + rng.rand1("nl.scale") * (a.nonlin_scale_max - a.nonlin_scale_min)
-        size_F_small = np.round(nonlin_scale * np.array(self.size)).astype(int).tolist()
+        nonlin_scale = a.nonlin_scale_min + float(rng.rand1("nl.scale")[0]) * (a.nonlin_scale_max - a.nonlin_scale_min)
+        size_F_small = [int(round(nonlin_scale * n)) for n in self.size]     # np.round: half to even, like round()
         if photo_mode:
-            size_F_small[1] = np.round(self.size[1] / spac).astype(int)
+            size_F_small[1] = int(round(self.size[1] / spac))
         nonlin_std = a.nonlin_std_max * rng.rand("nl.std")
-        Fsmall = nonlin_std * rng.torch_randn("nl.field", [*size_F_small, 3])
-        return Fsmall
+        shape = [*size_F_small, 3]
+        if arena is None:
+            return nonlin_std * rng.torch_randn("nl.field", shape), None
+        dev, view = arena.alloc_tensor(shape)
+        rng.torch_randn("nl.field", shape, out=view)
+        view.mul_(float(nonlin_std))
+        return view, dev
 
     def _full_field(self, Fsmall, photo_mode):
         F = myzoom_torch(Fsmall.to(self.device), np.array(self.size) / np.array(Fsmall.shape[:3]))
@@ -257,18 +272,18 @@ class BaseGen(Dataset):
 
     def generate_deformation(self, setups, shp, arena=None, lazy=False):
         scaling_factor_distances, A, c2 = self.random_affine_transform(shp)
-        Fsmall, F, Fneg = None, None, None
+        Fsmall, F, Fneg, fdev = None, None, None, None
         if self.synth_args.nonlinear_transform:
-            Fsmall = self.random_nonlinear_transform(setups['photo_mode'], setups['spac'])
+            Fsmall, fdev = self.random_nonlinear_transform(setups['photo_mode'], setups['spac'], arena)
             if 'surface' in self.tasks:
                 full = self._full_field(Fsmall, setups['photo_mode'])
                 F, Fneg = self._integrate_svf(full), self._integrate_svf(-full)
         plan = DeformPlan(self.size, shp, A, c2,
                           None if (Fsmall is None or F is not None) else Fsmall.numpy(), setups['photo_mode'],
-                          self.device, F_full=F, arena=arena, lazy=lazy)
-        # 'A' and 'c2' (device tensors in the reference) are materialised on first access
+                          self.device, F_full=F, arena=arena, lazy=lazy, fsmall_dev=fdev)
+        # 'A', 'c2' and 'F' (device tensors in the reference) are materialised on first access
         d = DeformDict({'scaling_factor_distances': scaling_factor_distances, 'Fneg': Fneg, '_plan': plan,
-                        '_Fsmall': Fsmall})
+                        '_Fsmall': None if Fsmall is None else Fsmall.clone(), '_photo': setups['photo_mode']})
         if F is not None or Fsmall is None:
             d['F'] = F
         return d
@@ -310,22 +325,24 @@ class BaseGen(Dataset):
             vars(self.gen_args.generator)[key] = value
 
     # ---- contrast (datasets.py:430-464) ------------------------------------------------------------
-    def get_contrast(self, photo_mode):
+    def get_contrast(self, photo_mode, out=None):
         """256-entry mean / std tables incl. partial-volume blends (datasets.py:430-464).  The random draws are
         torch's; the blends are evaluated in numpy float32 with the reference's operation order (every product
         and sum separately rounded): the means reproduce the torch float32 results bit for bit; the blended
         stds can differ in the last bit because torch's CPU sqrt (MKL vsSqrt) is not correctly rounded
-        while numpy's is."""
+        while numpy's is.  `out`: optional (2, 256) float32 CPU tensor (a view of the plan arena) that receives
+        the two tables in place."""
         rng = self.rng
+        if out is None:
+            out = torch.empty((2, 256), dtype=torch.float32)
+        mus, sigmas = out[0], out[1]
+        rng.torch_rand("gmm.mu", 256, out=mus)
+        rng.torch_rand("gmm.sigma", 256, out=sigmas)
+        ms = out.numpy()
         # 25 + 200*u, 5 + 20*u in float32: product then sum, separately rounded, as torch evaluates them
-        mus = rng.torch_rand("gmm.mu", 256)
-        m = mus.numpy()
-        np.multiply(m, np.float32(200), out=m)
-        np.add(m, np.float32(25), out=m)
-        sigmas = rng.torch_rand("gmm.sigma", 256)
-        sg = sigmas.numpy()
-        np.multiply(sg, np.float32(20), out=sg)
-        np.add(sg, np.float32(5), out=sg)
+        np.multiply(ms, _GMM_SCALE, out=ms)
+        np.add(ms, _GMM_SHIFT, out=ms)
+        m, sg = ms[0], ms[1]
         if rng.rand("gmm.ct") < self.synth_args.ct_prob:
             for name, (base, span) in (('darker', (25, 10)), ('dark', (90, 20)), ('bright', (110, 20)),
                                        ('brighter', (150, 50))):
@@ -349,12 +366,17 @@ class BaseGen(Dataset):
                                                     for k in _STOCK_STEPS)
                 and not self.synth_args.bspline_zooming)
 
-    def _plan_synth(self, setups, target):
+    def _plan_synth(self, setups, target, arena=None):
         """Draws of generate_sample + the stock augmentation chain, in the reference's order
-        (datasets.py:357-428, utils.py:568-638)."""
+        (datasets.py:357-428, utils.py:568-638).  With an arena the array-shaped draws (mean/std tables, bias
+        grid) are written straight into the pinned plan arena and `p` carries their device addresses."""
         cfg, rng, size = self.gen_args.generator, self.rng, self.size
         p = {}
-        p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'])
+        if arena is not None:
+            p['musigma_dev'], ms = arena.alloc_tensor((2, 256))
+            p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'], out=ms)
+        else:
+            p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'])
         p['eps_gmm'] = rng.field_randn("gmm.eps")
         p['mix'] = None
         if rng.rand("mix.u") < self.gen_args.mix_synth_prob:
@@ -366,12 +388,17 @@ class BaseGen(Dataset):
         # gamma
         p['gamma'] = np.float32(np.exp(cfg.gamma_std * rng.randn1("gamma.n")))
         # bias field
-        bf_scale = cfg.bf_scale_min + rng.rand1("bf.scale") * (cfg.bf_scale_max - cfg.bf_scale_min)
-        small = np.round(bf_scale * np.array(size)).astype(int).tolist()
+        bf_scale = cfg.bf_scale_min + float(rng.rand1("bf.scale")[0]) * (cfg.bf_scale_max - cfg.bf_scale_min)
+        small = [int(round(bf_scale * n)) for n in size]                    # np.round: half to even, like round()
         if setups['photo_mode']:
-            small[1] = int(np.round(size[1] / setups['spac']))
-        std = torch.tensor(cfg.bf_std_min + (cfg.bf_std_max - cfg.bf_std_min) * rng.rand1("bf.std"), dtype=torch.float)
-        p['bfsmall'] = (std * rng.torch_randn("bf.field", small)).numpy()
+            small[1] = int(round(size[1] / setups['spac']))
+        std = float(np.float32(cfg.bf_std_min + (cfg.bf_std_max - cfg.bf_std_min) * float(rng.rand1("bf.std")[0])))
+        if arena is not None:
+            p['bfsmall_dev'], bf = arena.alloc_tensor(small)
+            rng.torch_randn("bf.field", small, out=bf)
+        else:
+            bf = rng.torch_randn("bf.field", small)
+        p['bfsmall'] = bf.mul_(std).numpy()                                  # float32(std) * randn, in float32
         p['bf_shape'] = small
         # resample
         res = self.res_training_data
@@ -436,8 +463,11 @@ class BaseGen(Dataset):
             lab = job['labels']
             s.labels = lab.data_ptr()
             s.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
-            s.mu = arena.put(p['mu'].numpy())
-            s.sigma = arena.put(p['sigma'].numpy())
+            if 'musigma_dev' in p:
+                s.mu, s.sigma = p['musigma_dev'], p['musigma_dev'] + 1024
+            else:
+                s.mu = arena.put(p['mu'].numpy())
+                s.sigma = arena.put(p['sigma'].numpy())
             if p['eps_gmm'] is not None:
                 e = p['eps_gmm'].to(dev).contiguous()
                 keep.append(e)
@@ -450,7 +480,7 @@ class BaseGen(Dataset):
                     s.mixw[q] = float(p['mix'][q])
             s.gamma = float(p['gamma'])
             bfs = p['bfsmall']
-            s.bfsmall = arena.put(bfs)
+            s.bfsmall = p['bfsmall_dev'] if 'bfsmall_dev' in p else arena.put(bfs)
             s.bs[:] = bfs.shape
             s.btab = tables.zoom_tab(bfs.shape, size)
             s.i_bf = p_ibf + 4 * b * N
@@ -768,7 +798,7 @@ class BaseGen(Dataset):
                 for a in arg_sets:
                     self.update_gen_args(a)
                 jobs.append(self._job(ctx['setups'], ctx['deform'], ctx['target'],
-                                      self._plan_synth(ctx['setups'], ctx['target'])))
+                                      self._plan_synth(ctx['setups'], ctx['target'], arena)))
             spans.append((first, len(jobs)))
             aux = self._fused_image_targets(ctx, jobs[first:])
             if aux:

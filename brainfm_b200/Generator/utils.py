@@ -88,16 +88,26 @@ def resolution_sampler(low_res_only=False, draws=None):
     return resolution, thickness
 
 
+_AFF = np.zeros((6, 3, 3))                     # SHx SHy SHz Rx Ry Rz templates (unit diagonal filled below)
+for _q in range(6):
+    _AFF[_q] = np.eye(3)
+
+
 def make_affine_matrix(rot, sh, s):
-    """A = SHx SHy SHz Rx Ry Rz with row i scaled by s[i], float64 (Generator/utils.py:102-116)."""
-    cr, sr = np.cos(rot), np.sin(rot)
-    rx = np.array([[1, 0, 0], [0, cr[0], -sr[0]], [0, sr[0], cr[0]]])
-    ry = np.array([[cr[1], 0, sr[1]], [0, 1, 0], [-sr[1], 0, cr[1]]])
-    rz = np.array([[cr[2], -sr[2], 0], [sr[2], cr[2], 0], [0, 0, 1]])
-    shx = np.array([[1, 0, 0], [sh[1], 1, 0], [sh[2], 0, 1]])
-    shy = np.array([[1, sh[0], 0], [0, 1, 0], [0, sh[2], 1]])
-    shz = np.array([[1, 0, sh[0]], [0, 1, sh[1]], [0, 0, 1]])
-    A = shx @ shy @ shz @ rx @ ry @ rz
+    """A = SHx SHy SHz Rx Ry Rz with row i scaled by s[i], float64 (Generator/utils.py:102-116).  Same numpy
+    operations as the reference (np.cos/np.sin on the 3-vectors, five BLAS `@` products in the same order, the
+    row scaling); only the six factor matrices are written into a preallocated buffer instead of being built
+    from nested lists."""
+    cr, sr = np.cos(rot).tolist(), np.sin(rot).tolist()
+    sh = sh.tolist() if isinstance(sh, np.ndarray) else list(sh)
+    m = _AFF
+    m[0, 1, 0] = sh[1]; m[0, 2, 0] = sh[2]                                       # SHx
+    m[1, 0, 1] = sh[0]; m[1, 2, 1] = sh[2]                                       # SHy
+    m[2, 0, 2] = sh[0]; m[2, 1, 2] = sh[1]                                       # SHz
+    m[3, 1, 1] = cr[0]; m[3, 1, 2] = -sr[0]; m[3, 2, 1] = sr[0]; m[3, 2, 2] = cr[0]     # Rx
+    m[4, 0, 0] = cr[1]; m[4, 0, 2] = sr[1]; m[4, 2, 0] = -sr[1]; m[4, 2, 2] = cr[1]     # Ry
+    m[5, 0, 0] = cr[2]; m[5, 0, 1] = -sr[2]; m[5, 1, 0] = sr[2]; m[5, 1, 1] = cr[2]     # Rz
+    A = m[0] @ m[1] @ m[2] @ m[3] @ m[4] @ m[5]
     return A * np.asarray(s)[:, None]          # row r scaled by s[r]
 
 
@@ -197,7 +207,8 @@ class DeformPlan:
     """Device-side description of one random deformation: affine + small nonlinear grid + zoom tables +
     the bounding box of the deformed grid in the source volume.  Owns its device buffers."""
 
-    def __init__(self, size, src, A, c2, fsmall_host, photo, device, F_full=None, arena=None, lazy=False):
+    def __init__(self, size, src, A, c2, fsmall_host, photo, device, F_full=None, arena=None, lazy=False,
+                 fsmall_dev=None):
         self.size = [int(v) for v in size]
         self.src = [int(v) for v in src[:3]]
         self.device = torch.device(device)
@@ -213,7 +224,7 @@ class DeformPlan:
         if arena is not None:
             # the small grid lives in the caller's arena slot: valid until that slot is recycled
             self.struct = make_deform(tables, arena, self.size, self.src, self.A_host, self.c2_host, fsmall_host,
-                                      photo, fptr)
+                                      photo, fptr, fsmall_dev=fsmall_dev)
             self.bbox_ptr, self._bbox_off = arena.reserve(32)
             self._arena, self._slot = arena, arena.cur
         else:
@@ -264,6 +275,17 @@ class DeformDict(dict):
         if key in ('A', 'c2'):
             self[key] = torch.from_numpy(np.array(plan.A_host if key == 'A' else plan.c2_host)).to(plan.device)
             return self[key]
+        if key == 'F':
+            # full-resolution nonlinear field (datasets.py:209-212), only when somebody asks for it
+            small = dict.get(self, '_Fsmall')
+            if small is None:
+                self['F'] = None
+                return None
+            F = myzoom_torch(small.to(plan.device), np.array(plan.size) / np.array(small.shape[:3]))
+            if dict.get(self, '_photo'):
+                F[:, :, :, 1] = 0
+            self['F'] = F
+            return F
         if key == 'grid':
             xx2, yy2, zz2 = plan.coords()
             x1, y1, z1, x2, y2, z2 = plan.bbox_host()

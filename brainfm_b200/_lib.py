@@ -63,6 +63,7 @@ _PROTOS = {
     "bfm_zoom_linear": (c_i, [c_p, c_i, c_i, c_i, c_i] + [c_p, c_p, c_p, c_p, c_i] * 3 + [c_p, c_p]),
     "bfm_blur_axis": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     "bfm_band_axis": (c_i, [c_p, c_p, C.POINTER(c_i), c_i, c_i, c_p, c_p, c_i, c_f, c_p, c_u64, c_p]),
+    "bfm_upload_pinned": (c_i, [c_p, c_p, c_i64, c_p]),
     "bfm_sanitize_f32": (c_i, [c_p, c_i64, c_p]),
     "bfm_band_build": (c_i, [c_i, c_i, C.c_double, c_i, c_p, c_p, c_p]),
     "bfm_minmax": (c_i, [c_p, c_i64, c_p, c_p]),

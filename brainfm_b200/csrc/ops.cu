@@ -28,6 +28,13 @@ __global__ void k_trilerp_pull(const float *__restrict__ X, int nx, int ny, int 
     }
 }
 
+// Small host -> device copy done by the SMs: reads mapped pinned host memory over PCIe.  Used for the plan arena
+// (~16 KB per sample) so that it never queues behind bulk uploads in the copy engine's FIFO.
+__global__ void k_upload(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+        dst[p] = src[p];
+}
+
 // torch.nan_to_num in place (Generator/utils.py:305)
 __global__ void k_sanitize(float *__restrict__ x, int64_t n) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
@@ -410,6 +417,18 @@ using namespace bfm;
 extern "C" {
 
 int bfm_abi_version(void) { return BFM_ABI_VERSION; }
+
+int bfm_upload_pinned(void *dst, const void *src_pinned, int64_t nbytes, void *stream) {
+    BFM_REQUIRE(dst && src_pinned && nbytes >= 0, "bfm_upload_pinned: null pointer");
+    BFM_REQUIRE(((uintptr_t)dst & 15) == 0 && ((uintptr_t)src_pinned & 15) == 0 && (nbytes & 15) == 0,
+                "bfm_upload_pinned: addresses and size must be multiples of 16 bytes");
+    if (nbytes == 0) return BFM_OK;
+    const int64_t n = nbytes / 16;
+    const int64_t blocks = (n + 255) / 256;
+    k_upload<<<(unsigned)(blocks < 148 * 4 ? blocks : 148 * 4), 256, 0, (cudaStream_t)stream>>>(
+        (uint4 *)dst, (const uint4 *)src_pinned, n);
+    return check_launch("bfm_upload_pinned");
+}
 
 int bfm_sanitize_f32(float *x, int64_t n, void *stream) {
     BFM_REQUIRE(x && n >= 0, "bfm_sanitize_f32: null pointer");

@@ -41,11 +41,14 @@ class HostDraws:
     def choice(self, tag, seq):
         return _pyrandom.choice(seq)
 
-    def torch_rand(self, tag, shape, dtype=torch.float32):
-        return torch.rand(shape, dtype=dtype)
+    def torch_rand(self, tag, shape, dtype=torch.float32, out=None):
+        """`out` (a contiguous CPU tensor of that shape, e.g. a view of the pinned plan arena) receives the draw
+        in place: same generator consumption and same values as the allocating form."""
+        return torch.rand(shape, dtype=dtype) if out is None else torch.rand(shape, dtype=dtype, out=out)
 
-    def torch_randn(self, tag, shape):
-        return torch.randn(shape, dtype=torch.float32)
+    def torch_randn(self, tag, shape, out=None):
+        return torch.randn(shape, dtype=torch.float32) if out is None else torch.randn(shape, dtype=torch.float32,
+                                                                                       out=out)
 
     def field_randn(self, tag, shape=None):
         """Volume-sized N(0,1) field: None => generated in-kernel (Philox)."""
@@ -93,11 +96,13 @@ class ReplayDraws(HostDraws):
     def choice(self, tag, seq):
         return self._next(tag)
 
-    def torch_rand(self, tag, shape, dtype=torch.float32):
-        return self._next(tag).clone()
+    def torch_rand(self, tag, shape, dtype=torch.float32, out=None):
+        v = self._next(tag)
+        return v.clone() if out is None else out.copy_(v.reshape(out.shape))
 
-    def torch_randn(self, tag, shape):
-        return self._next(tag).clone()
+    def torch_randn(self, tag, shape, out=None):
+        v = self._next(tag)
+        return v.clone() if out is None else out.copy_(v.reshape(out.shape))
 
     def field_randn(self, tag, shape=None):
         return self._next(tag)

@@ -155,6 +155,20 @@ class Arena:
         self.used = off + nbytes
         return self.base + off, off
 
+    def alloc_tensor(self, shape, dtype=torch.float32):
+        """Uninitialised array INSIDE the pinned host buffer: (device address, CPU tensor view).  Draws written
+        into the view (torch.rand(..., out=view)) reach the device with the slot's single copy."""
+        n = 1
+        for v in shape:
+            n *= int(v)
+        item = 4 if dtype in (torch.float32, torch.int32) else torch.empty((), dtype=dtype).element_size()
+        off = (self.used + _ALIGN - 1) // _ALIGN * _ALIGN
+        if off + n * item > self.capacity:
+            raise MemoryError("plan arena overflow")
+        self.used = off + n * item
+        view = self.slots[self.cur]["host"][off:off + n * item].view(dtype).view(*shape)
+        return self.base + off, view
+
     def put_struct_array(self, arr):
         n = C.sizeof(arr)
         off = (self.used + _ALIGN - 1) // _ALIGN * _ALIGN
@@ -165,11 +179,15 @@ class Arena:
         return self.base + off
 
     def commit(self, stream=None):
-        """Ship everything put() since the last commit (one async copy on the current stream)."""
+        """Ship everything put() since the last commit: one asynchronous copy on the current stream, done by a
+        kernel that reads the pinned host buffer (bfm_upload_pinned) -- a cudaMemcpyAsync would queue behind
+        whatever bulk uploads are sitting in the copy engine's FIFO (HostPipeline)."""
         s = self.slots[self.cur]
         if self.used > self.committed:
             a = self.committed // _ALIGN * _ALIGN
-            s["dev"][a:self.used].copy_(s["host"][a:self.used], non_blocking=True)
+            b = min((self.used + _ALIGN - 1) // _ALIGN * _ALIGN, self.capacity)
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(_lib.lib().bfm_upload_pinned(s["dev"].data_ptr() + a, s["host"].data_ptr() + a, b - a, st))
             self.committed = self.used
 
     def mark_done(self):
@@ -326,10 +344,10 @@ def fill_zoom_tab(tab, arena, tables):
         tab.wh[ax] = arena.put(wh)
 
 
-def make_deform(tables, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None):
+def make_deform(tables, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=None, fsmall_dev=None):
     """A filled _lib.Deform: the cached template of (size, small-grid shape) plus this sample's affine, source
-    shape and small random grid (the only array that goes through the arena)."""
-    fs = None if fsmall_host is None else fsmall_host.shape[:3]
+    shape and small random grid (the only array that goes through the arena; fsmall_dev: it is already there)."""
+    fs = None if fsmall_host is None else tuple(fsmall_host.shape[:3])
     d = _lib.Deform.from_buffer_copy(tables.deform_template(size, fs))
     d.src[:] = [int(v) for v in src[:3]]
     d.A[:] = np.asarray(A, dtype=np.float32).reshape(-1).tolist()
@@ -339,7 +357,7 @@ def make_deform(tables, arena, size, src, A, c2, fsmall_host, photo, F_full_ptr=
         d.F_full = F_full_ptr
         d.ncand[:] = [0, 0, 0]
     if fsmall_host is not None:
-        d.fsmall = arena.put(fsmall_host)
+        d.fsmall = fsmall_dev if fsmall_dev is not None else arena.put(fsmall_host)
     return d
 
 

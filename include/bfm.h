@@ -74,6 +74,11 @@ int bfm_band_axis(const float *in, float *out, const int *in_shape, int axis, in
                   const int *start, const float *w, int T,
                   float noise_std, const float *eps, uint64_t seed, void *stream);
 
+/* dst (device) <- src_pinned (page-locked HOST memory, device-accessible under unified addressing), copied by a
+ * kernel instead of the copy engine: the plan arena of a batch (a few KB per sample) must not wait behind bulk
+ * uploads queued on the copy engine.  Addresses and nbytes: multiples of 16. */
+int bfm_upload_pinned(void *dst, const void *src_pinned, int64_t nbytes, void *stream);
+
 /* x = nan_to_num(x) in place (torch.nan_to_num, Generator/utils.py:305): applied once when a real-image volume
  * enters the device cache instead of at every crop read. */
 int bfm_sanitize_f32(float *x, int64_t n, void *stream);
