@@ -627,8 +627,10 @@ class BaseGen(Dataset):
     # ---- reference-shaped sample generation ---------------------------------------------------------
     def generate_sample(self, name, G, setups, deform_dict, res, target):
         """GMM synthesis + augmentation of one sample (datasets.py:357-428)."""
-        if not self._stock_chain('synth'):
-            return self._generate_sample_opwise(setups, deform_dict, res, target)
+        P = target['pathology'] if 'pathology' in target else None
+        has_pathol = isinstance(P, torch.Tensor) and bool(P.sum() > 0)       # host sync, datasets.py:390
+        if has_pathol or not self._stock_chain('synth'):
+            return self._generate_sample_opwise(setups, deform_dict, res, target, has_pathol)
         deform_dict['_plan'].compute_bbox()
         p = self._plan_synth(setups, target)
         arena = self.arena.begin()
@@ -637,8 +639,8 @@ class BaseGen(Dataset):
         target['pathology_prob'] = 0.
         return target['pathology'], target['pathology_prob'], sample
 
-    def _generate_sample_opwise(self, setups, deform_dict, res, target):
-        """Op-by-op path through the registries (custom or reordered augmentation steps)."""
+    def _generate_sample_opwise(self, setups, deform_dict, res, target, has_pathol=False):
+        """Op-by-op path through the registries (custom or reordered augmentation steps, pathology encoding)."""
         rng = self.rng
         mus, sigmas = self.get_contrast(setups['photo_mode'])
         xx2, yy2, zz2, x1, y1, z1, x2, y2, z2 = deform_dict['grid']
@@ -660,11 +662,26 @@ class BaseGen(Dataset):
                 SYN += v[2] * target['T2'][0]
             if 'FLAIR' in self.modalities:
                 SYN += v[3] * target['FLAIR'][0]
-        target['pathology'] = 0.
-        target['pathology_prob'] = 0.
+        if has_pathol:
+            # datasets.py:390-406, quirks included: the masks have the crop's shape, so this branch (like the
+            # reference's) only works when the crop covers the whole output shape; SYN_cerebral is warped twice
+            SYN_cerebral = SYN.clone()
+            SYN_cerebral[Gr == 0] = 0
+            SYN_cerebral = fast_3D_interp_torch(SYN_cerebral.contiguous(), xx2, yy2, zz2)[None]
+            wm_mask = (Gr == 2) | (Gr == 41)
+            wm_mean = (SYN * wm_mask).sum() / wm_mask.sum()
+            gm_mask = (Gr != 0) & (Gr != 2) & (Gr != 41)
+            gm_mean = (SYN * gm_mask).sum() / gm_mask.sum()
+            target['pathology'][SYN_cerebral == 0] = 0
+            target['pathology_prob'][SYN_cerebral == 0] = 0
+            pathol_direction = self.get_pathology_direction('synth', bool(gm_mean > wm_mean))
+        else:
+            pathol_direction = None
+            target['pathology'] = 0.
+            target['pathology_prob'] = 0.
         SYN[SYN < 0.] = 0.
-        return target['pathology'], target['pathology_prob'], self.augment_sample(None, SYN, setups, deform_dict, res,
-                                                                                  target)
+        return target['pathology'], target['pathology_prob'], self.augment_sample(
+            None, SYN, setups, deform_dict, res, target, pathol_direction=pathol_direction)
 
     def augment_sample(self, name, I_def, setups, deform_dict, res, target, pathol_direction=None, input_mode='synth'):
         """Augmentation of an already deformed image through the operator registry (datasets.py:306-354)."""
@@ -673,8 +690,13 @@ class BaseGen(Dataset):
             raise NotImplementedError("real-image inputs go through read_and_deform; pass a deformed tensor")
         if input_mode == 'CT':
             I_def = torch.clamp(I_def, min=0., max=80.)
-        target['pathology'] = 0.
-        target['pathology_prob'] = 0.
+        P = target['pathology'] if 'pathology' in target else None
+        if isinstance(P, torch.Tensor) and bool(P.sum() > 0):            # datasets.py:321-326
+            I_def = self.encode_pathology(I_def, P, target['pathology_prob'], pathol_direction)
+            I_def[I_def < 0.] = 0.
+        else:
+            target['pathology'] = 0.
+            target['pathology_prob'] = 0.
         aux_dict = {}
         steps = self.augmentation_steps['synth'] if input_mode == 'synth' else self.augmentation_steps['real']
         for func_name in steps:
@@ -697,6 +719,25 @@ class BaseGen(Dataset):
         if 'bias_field' in self.tasks and input_mode != 'CT':
             sample.update({'bias_field_log': torch.flip(aux_dict['BFlog'], [0])[None] if flip else aux_dict['BFlog'][None]})
         return sample
+
+    def encode_pathology(self, I, P, Pprob, pathol_direction=None):
+        """Paint a lesion into the image: I += Pprob * N(mu_p, sigma_p), mu_p = +-(3/4 + u/4) * mean(I | P),
+        sigma_p = u'/4 * mean(I | P) (datasets.py:496-518; same tensor expressions, hence the same dtype
+        promotions: P / Pprob are float64 for random shapes, the image stays float32)."""
+        rng = self.rng
+        if pathol_direction is None:       # True: T2/FLAIR-resembled, False: T1-resembled
+            pathol_direction = rng.choice("pathol.dir", [True, False])
+        P, Pprob = torch.squeeze(P), torch.squeeze(Pprob)
+        I_mu = (I * P).sum() / P.sum()
+        p_mask = torch.round(P).long()
+        pth_mus = 3 * I_mu / 4 + I_mu / 4 * rng.torch_rand("pathol.mus", 10000).to(self.device)
+        pth_mus = pth_mus if pathol_direction else -pth_mus
+        pth_sigmas = I_mu / 4 * rng.torch_rand("pathol.sigmas", 10000).to(self.device)
+        eps = rng.field_randn("pathol.eps", tuple(p_mask.shape))
+        eps = torch.randn(p_mask.shape, dtype=torch.float, device=self.device) if eps is None else eps.to(self.device)
+        I += Pprob * (pth_mus[p_mask] + pth_sigmas[p_mask] * eps)
+        I[I < 0] = 0
+        return I
 
     def get_pathology_direction(self, input_mode, pathol_direction=None):
         if pathol_direction is not None:

@@ -455,14 +455,16 @@ def read_and_deform_pathology(exist_keys, task_name, file_name, setups, deform_d
         return {'pathology': z, 'pathology_prob': z.clone()}
     from ..ShapeID.perlin3d import generate_shape_3d
     if file_name == 'random_shape':
-        percentile = (kwargs.get('draws') or _DRAWS).rand("pathol.percentile")
-        percentile = shape_gen_args.mask_percentile_min + percentile * (shape_gen_args.mask_percentile_max -
-                                                                       shape_gen_args.mask_percentile_min)
-        _, Pdef = generate_shape_3d(tuple(plan.size), shape_gen_args.perlin_res, percentile, plan.device)
+        draws = kwargs.get('draws') or _DRAWS
+        # np.random.uniform(a, b) == a + (b - a) * random_sample()
+        percentile = shape_gen_args.mask_percentile_min + (shape_gen_args.mask_percentile_max -
+                                                           shape_gen_args.mask_percentile_min) * draws.rand("pathol.percentile")
+        _, Pdef = generate_shape_3d(tuple(plan.size), shape_gen_args.perlin_res, percentile, plan.device,
+                                    draws=draws)
     else:
         Pdef, _ = read_and_deform(file_name, torch.float, deform_dict, device, None)
     if augment:
-        Pdef = augment_pathology(Pdef, pde_func, t, shape_gen_args, device)
+        Pdef = augment_pathology(Pdef, pde_func, t, shape_gen_args, device, draws=kwargs.get('draws'))
     P = binarize(Pdef, thres)
     if P.mean() <= shape_gen_args.pathol_tol:
         z = torch.zeros(plan.size, device=plan.device)[None]

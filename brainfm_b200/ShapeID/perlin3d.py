@@ -13,9 +13,14 @@ def interpolant(t):
     return t * t * t * (t * (t * 6 - 15) + 10)
 
 
-def _lattice(res, tileable):
-    theta = 2 * np.pi * np.random.rand(res[0] + 1, res[1] + 1, res[2] + 1)
-    phi = 2 * np.pi * np.random.rand(res[0] + 1, res[1] + 1, res[2] + 1)
+def _lattice(res, tileable, draws=None):
+    shp = (res[0] + 1, res[1] + 1, res[2] + 1)
+    if draws is None:
+        theta = 2 * np.pi * np.random.rand(*shp)
+        phi = 2 * np.pi * np.random.rand(*shp)
+    else:                               # injectable draws (brainfm_b200.draws), same order
+        theta = 2 * np.pi * draws.rand_array("perlin.theta", shp)
+        phi = 2 * np.pi * draws.rand_array("perlin.phi", shp)
     g = np.stack((np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta), np.cos(phi)), axis=3)
     if tileable[0]:
         g[-1, :, :] = g[0, :, :]
@@ -46,12 +51,12 @@ def _percentile_device(noise, percentile):
     return out
 
 
-def _noise_device(shape, res, tileable, device):
+def _noise_device(shape, res, tileable, device, draws=None):
     shape, res = [int(s) for s in shape], [int(r) for r in res]
     for s, r in zip(shape, res):
         if s % r:
             raise ValueError("shape must be a multiple of res")
-    g = torch.from_numpy(np.ascontiguousarray(_lattice(res, tileable))).to(device)
+    g = torch.from_numpy(np.ascontiguousarray(_lattice(res, tileable, draws))).to(device)
     out = torch.empty(shape, dtype=torch.float64, device=device)
     _lib.check(_lib.lib().bfm_perlin3d(g.data_ptr(), ivec(shape), ivec(res), out.data_ptr(), stream()))
     return out
@@ -69,10 +74,10 @@ def _finish(noise, percentile, as_numpy):
 
 
 def generate_perlin_noise_3d(shape, res, tileable=(False, False, False), interpolant=interpolant, percentile=None,
-                             device='cuda', as_numpy=True):
+                             device='cuda', as_numpy=True, draws=None):
     """3-D Perlin noise (ShapeID/perlin3d.py:15-90).  Returns numpy arrays like the reference unless
     as_numpy=False (device tensors, no D2H)."""
-    noise = _noise_device(shape, res, tileable, torch.device(device))
+    noise = _noise_device(shape, res, tileable, torch.device(device), draws)
     return _finish(noise, percentile, as_numpy)
 
 
@@ -89,18 +94,18 @@ def generate_fractal_noise_3d(shape, res, octaves=1, persistence=0.5, lacunarity
     return _finish(noise, percentile, as_numpy)
 
 
-def generate_shape_3d(shape, perlin_res, percentile, device):
+def generate_shape_3d(shape, perlin_res, percentile, device, draws=None):
     """Random blob: (mask, noise*mask) as float64 device tensors (ShapeID/perlin3d.py:144-146)."""
     pprob, p = generate_perlin_noise_3d(shape, perlin_res, tileable=(True, False, False), percentile=percentile,
-                                        device=device, as_numpy=False)
+                                        device=device, as_numpy=False, draws=draws)
     return p, pprob
 
 
-def generate_velocity_3d(shape, perlin_res, V_multiplier, device):
+def generate_velocity_3d(shape, perlin_res, V_multiplier, device, draws=None):
     """Divergence-free velocity: curl of three Perlin potentials, float32 (ShapeID/perlin3d.py:149-156)."""
     dev = torch.device(device)
-    a = _noise_device(shape, perlin_res, (True, False, False), dev)
-    b = _noise_device(shape, perlin_res, (True, False, False), dev)
-    c = _noise_device(shape, perlin_res, (True, False, False), dev)
+    a = _noise_device(shape, perlin_res, (True, False, False), dev, draws)
+    b = _noise_device(shape, perlin_res, (True, False, False), dev, draws)
+    c = _noise_device(shape, perlin_res, (True, False, False), dev, draws)
     Vx, Vy, Vz = stream_3D(a, b, c, multiplier=V_multiplier)
     return {'Vx': Vx, 'Vy': Vy, 'Vz': Vz}

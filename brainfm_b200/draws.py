@@ -38,6 +38,9 @@ class HostDraws:
     def randint(self, tag, n):
         return np.random.randint(n)
 
+    def rand_array(self, tag, shape):
+        return np.random.rand(*shape)
+
     def choice(self, tag, seq):
         return _pyrandom.choice(seq)
 
@@ -92,6 +95,9 @@ class ReplayDraws(HostDraws):
 
     def randint(self, tag, n):
         return self._next(tag)
+
+    def rand_array(self, tag, shape):
+        return np.asarray(self._next(tag)).reshape(shape)
 
     def choice(self, tag, seq):
         return self._next(tag)

@@ -407,6 +407,52 @@ class GeneratorOracle:
             oh = torch.flip(oh, [0])[..., self.vflip]
         return {"segmentation": oh.permute(3, 0, 1, 2)}
 
+    def target_pathology(self, setups):
+        """read_and_deform_pathology (Generator/utils.py:428-455) for the branches the reference can run: no
+        pathology (file_name None) and a random Perlin shape (no advection: datasets.py:603-604)."""
+        z = torch.zeros(self.size)[None]
+        if not setups["pathol_mode"]:
+            return {"pathology": z, "pathology_prob": z.clone()}
+        if not setups["pathol_random_shape"]:
+            raise NotImplementedError("file-based pathology maps: site-specific paths, and the reference's "
+                                      "read_and_deform call omits a required argument (utils.py:442)")
+        from oracle import shapeid_oracle as so
+        sg = self.cfg.pathology_shape_generator
+        u = np.random.random_sample(); self.log.append(("pathol.percentile", u))       # np.random.uniform(a, b)
+        percentile = sg.mask_percentile_min + (sg.mask_percentile_max - sg.mask_percentile_min) * u
+        res = [int(r) for r in sg.perlin_res]
+        shp = (res[0] + 1, res[1] + 1, res[2] + 1)
+        th = np.random.rand(*shp); self.log.append(("perlin.theta", th.copy()))
+        ph = np.random.rand(*shp); self.log.append(("perlin.phi", ph.copy()))
+        theta, phi = 2 * np.pi * th, 2 * np.pi * ph
+        g = np.stack((np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta), np.cos(phi)), axis=3)
+        g[-1] = g[0]                                                                   # tileable=(True, False, False)
+        noise = so.perlin(tuple(self.size), res, g)
+        _, prob = so.shape_from_noise(noise, percentile)
+        Pdef = torch.from_numpy(prob)
+        thr = sg.pathol_thres * Pdef.max()
+        P = Pdef.clone()
+        P[Pdef < thr] = 0.
+        P[Pdef >= thr] = 1.
+        if P.mean() <= sg.pathol_tol:
+            return {"pathology": z, "pathology_prob": z.clone()}
+        return {"pathology": P[None], "pathology_prob": Pdef[None]}
+
+    def encode_pathology(self, I, P, Pprob, direction):
+        """datasets.py:496-518 (direction is always given on the synthetic path)."""
+        P, Pprob = torch.squeeze(P), torch.squeeze(Pprob)
+        I_mu = (I * P).sum() / P.sum()
+        p_mask = torch.round(P).long()
+        r1 = torch.rand(10000, dtype=torch.float); self.log.append(("pathol.mus", r1.clone()))
+        pth_mus = 3 * I_mu / 4 + I_mu / 4 * r1
+        pth_mus = pth_mus if direction else -pth_mus
+        r2 = torch.rand(10000, dtype=torch.float); self.log.append(("pathol.sigmas", r2.clone()))
+        pth_sigmas = I_mu / 4 * r2
+        eps = torch.randn(p_mask.shape, dtype=torch.float); self.log.append(("pathol.eps", eps.clone()))
+        I += Pprob * (pth_mus[p_mask] + pth_sigmas[p_mask] * eps)
+        I[I < 0] = 0
+        return I
+
     def targets(self, setups, D):
         T = {"name": self.case_name}
         for key in ("T1", "T2", "FLAIR"):
@@ -415,8 +461,7 @@ class GeneratorOracle:
             if task in ("T1", "T2", "FLAIR"):
                 continue
             if task == "pathology":
-                z = torch.zeros(self.size)[None]
-                T.update({"pathology": z, "pathology_prob": z.clone()})   # file_name None branch
+                T.update(self.target_pathology(setups))
                 continue
             fn = {"CT": self.target_ct, "segmentation": self.target_segmentation,
                   "distance": self.target_distance, "registration": self.target_registration,
@@ -474,8 +519,25 @@ class GeneratorOracle:
                 S += v[2] * target["T2"][0]
             if "FLAIR" in self.vol:
                 S += v[3] * target["FLAIR"][0]
+        direction = None
+        if isinstance(target.get("pathology"), torch.Tensor) and target["pathology"].sum() > 0:
+            # datasets.py:390-406, quirks included (masks of the crop's shape applied to the deformed image;
+            # the cerebral image is warped a second time)
+            Sc = S.clone()
+            Sc[Gr == 0] = 0
+            Sc = sample_trilinear(Sc, *D["rel"])[None]
+            wm = (Gr == 2) | (Gr == 41)
+            wm_mean = (S * wm).sum() / wm.sum()
+            gm = (Gr != 0) & (Gr != 2) & (Gr != 41)
+            gm_mean = (S * gm).sum() / gm.sum()
+            target["pathology"][Sc == 0] = 0
+            target["pathology_prob"][Sc == 0] = 0
+            direction = bool(gm_mean > wm_mean)
+        else:
+            target["pathology"] = 0.0
+            target["pathology_prob"] = 0.0
         S[S < 0.] = 0.
-        return self.augment(S, setups, "synth")
+        return self.augment(S, setups, "synth", target, direction)
 
     # -- augmentation chain (datasets.py:306-354, utils.py:568-638) ----------------------------
     def op_gamma(self, I, aux, setups):
@@ -522,7 +584,14 @@ class GeneratorOracle:
         out[out < 0] = 0
         return out
 
-    def augment(self, I, setups, input_mode):
+    def augment(self, I, setups, input_mode, target=None, direction=None):
+        if target is not None:
+            if isinstance(target.get("pathology"), torch.Tensor) and target["pathology"].sum() > 0:
+                I = self.encode_pathology(I, target["pathology"], target["pathology_prob"], direction)
+                I[I < 0.] = 0.
+            else:
+                target["pathology"] = 0.0
+                target["pathology_prob"] = 0.0
         aux = {}
         steps = self.aug_steps["synth"] if input_mode == "synth" else self.aug_steps["real"]
         table = {"gamma": self.op_gamma, "bias_field": self.op_bias_field, "resample": self.op_resample,
@@ -564,8 +633,12 @@ class GeneratorOracle:
                 self._merge(self.cfg.mild_generator if i < self.g.mild_samples else self.cfg.severe_generator)
                 self._merge(self.cfg.synth_image_generator)
                 sample.append(self.synth(setups, D, target))
-        target["pathology"] = 0.0
-        target["pathology_prob"] = 0.0
+        if not isinstance(target.get("pathology"), torch.Tensor):
+            target["pathology"] = 0.0
+            target["pathology_prob"] = 0.0
+        elif setups["flip"]:                                                       # datasets.py:672-674
+            target["pathology"] = torch.flip(target["pathology"], [1])
+            target["pathology_prob"] = torch.flip(target["pathology_prob"], [1])
         self.setups, self.deform = setups, D
         return 1, self.dataset_name, "synth", target, sample
 

@@ -57,6 +57,13 @@ CASES = {
     "g64_brainid_s6": (64, 96, "brain", 6, {"generator.all_samples": 3, "generator.mild_samples": 1}, [],
                        "brain_id", 2),
     "g160_s0": (160, 192, "brain", 0, {}, [], "default", 4),
+    # pathology: random Perlin shape encoded into the synthetic image.  The reference's branch only runs when the
+    # crop covers the whole output shape (datasets.py:391-398 index the deformed image with crop-shaped masks),
+    # hence source shape == output shape here.
+    "g64_pathol_s7": (64, 64, "brain", 7, {"task.pathology": True, "generator.pathology_prob": 1.0,
+                                           "generator.random_shape_prob": 1.0}, [], "default", 2),
+    "g64_pathol_s12": (64, 64, "brain", 12, {"task.pathology": True, "generator.pathology_prob": 1.0,
+                                             "generator.random_shape_prob": 1.0}, [], "default", 2),
 }
 
 

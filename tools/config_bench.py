@@ -1,0 +1,104 @@
+"""BASELINE.json configs[2] and configs[3] on one B200 (parity-test configurations, not bench lines; numbers go to
+DESIGN.md / profiles):
+
+  interpol : 4-channel 256^3 volume, 7-step scaling-and-squaring of a 3-channel displacement (trilinear, dct2),
+             cubic prefilter, cubic grid_pull of the 4 channels, nearest grid_pull of a label volume
+             (316*N algorithmic bytes; reference on 8 CPU threads: 63.4 s)
+  shapeid  : 192^3 Perlin shape + curl velocity + dopri5 advection, nt = 10
+             (reference on 8 CPU threads: 95.6 s, 224 RHS evaluations)
+
+    python tools/config_bench.py [interpol] [shapeid]
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return best, out
+
+
+def interpol_cfg(n=256):
+    from brainfm_b200 import interpol
+    torch.manual_seed(0)
+    vol = torch.rand(1, 4, n, n, n, device="cuda")
+    lab = torch.randint(0, 57, (1, 1, n, n, n), device="cuda").float()
+    svf = 2 * torch.randn(1, n, n, n, 3, device="cuda")
+    stages = {}
+
+    def ss():
+        disp = svf / 2 ** 7
+        for _ in range(7):
+            grid = interpol.add_identity_grid(disp)
+            disp = disp + interpol.grid_pull(disp.permute(0, 4, 1, 2, 3), grid, interpolation=1, bound='dct2',
+                                             extrapolate=True).permute(0, 2, 3, 4, 1)
+        return disp
+    stages["scaling_and_squaring_7"], disp = timed(ss)
+    grid = interpol.add_identity_grid(disp)
+    stages["cubic_prefilter_4ch"], coeff = timed(lambda: interpol.spline_coeff_nd(vol, interpolation=3, bound='dct2', dim=3))
+    stages["cubic_pull_4ch"], out = timed(lambda: interpol.grid_pull(coeff, grid, interpolation=3, bound='dct2',
+                                                                     extrapolate=True))
+    stages["nearest_pull_labels"], lo = timed(lambda: interpol.grid_pull(lab, grid, interpolation=0, bound='dct2',
+                                                                         extrapolate=True))
+    total = sum(stages.values())
+    N = n ** 3
+    print(json.dumps({"config": "interpol 4ch %d^3 (configs[2])" % n, "ms": stages, "total_ms": total,
+                      "algorithmic_GB": 316 * N / 1e9, "algorithmic_GBps": 316 * N / total / 1e6,
+                      "reference_cpu_s_8_threads": 63.4 if n == 256 else None}))
+
+
+def shapeid_cfg(n=192):
+    from brainfm_b200.ShapeID import perlin3d as P
+    from brainfm_b200.ShapeID.DiffEqs import odeint_adjoint
+    from brainfm_b200.ShapeID.DiffEqs.pde import AdvDiffPDE
+    shape, res, dt, nt = (n, n, n), [2, 2, 2], 0.1, 10
+    np.random.seed(0)
+    stages = {}
+    t0 = time.perf_counter()
+    mask, prob = P.generate_shape_3d(shape, res, 92, 'cuda')
+    torch.cuda.synchronize()
+    stages["generate_shape_3d"] = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    V = P.generate_velocity_3d(shape, res, 500, 'cuda')
+    torch.cuda.synchronize()
+    stages["generate_velocity_3d"] = 1e3 * (time.perf_counter() - t0)
+    pde = AdvDiffPDE(data_spacing=[1., 1., 1.], perf_pattern='adv', V_type='vector_div_free', V_dict=V, BC='neumann',
+                     dt=dt, device='cuda')
+    t = torch.from_numpy(np.arange(nt) * dt).cuda()
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol, solver = odeint_adjoint(pde, prob[None], t, dt, method='dopri5', return_solver=True)
+        torch.cuda.synchronize()
+        stages["dopri5_nt10"] = 1e3 * (time.perf_counter() - t0)
+    N = n ** 3
+    S = len(solver.trace)
+    alg = (84 * N + S * 368 * N + (nt - 1) * 60 * N)
+    print(json.dumps({"config": "ShapeID %d^3 (configs[3])" % n, "ms": stages, "total_ms": sum(stages.values()),
+                      "rhs_evaluations": int(solver.n_rhs), "steps": S, "algorithmic_GB": alg / 1e9,
+                      "algorithmic_GBps": alg / sum(stages.values()) / 1e6,
+                      "reference_cpu_s_8_threads": 95.6 if n == 192 else None}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["interpol", "shapeid"]
+    if "interpol" in which:
+        interpol_cfg(int(os.environ.get("INTERPOL_N", "256")))
+    if "shapeid" in which:
+        shapeid_cfg(int(os.environ.get("SHAPEID_N", "192")))
