@@ -165,12 +165,13 @@ def config_dict():
             "batch": BATCH, "size": [SIZE] * 3, "source": [SIZE] * 3,
             "l2": "working set per step (8 samples x ~100 MB of intermediates) exceeds the 126 MB L2; "
                   "no explicit flush",
-            "rng": "host scalars: numpy/torch global generators in reference order; volume-sized normal fields: "
-                   "in-kernel Philox4x32-10"}
+            "rng": "scalars: library planner (bfm_plan_batch), Philox4x32-10 stream seeded from numpy's global "
+                   "generator, reference draw order and distributions; small random grids and volume-sized normal "
+                   "fields: in-kernel Philox4x32-10"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def build_dataset(subs, device):
+def build_dataset(subs, device, planner="auto"):
     from brainfm_b200 import io as bio
     from brainfm_b200.Generator import BaseGen
     root = tempfile.mkdtemp(prefix="bfm_bench_")
@@ -184,7 +185,7 @@ def build_dataset(subs, device):
         f.write("\n".join(names) + "\n")
     cfg = bench_cfg()
     cfg.split_root = root
-    ds = BaseGen(cfg, device)
+    ds = BaseGen(cfg, device, planner=planner)
     ds.write_bflog = True
     return ds
 
@@ -197,6 +198,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident arm only (profiling runs)")
+    ap.add_argument("--planner", default="auto", choices=["auto", "python", "native"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -216,7 +218,7 @@ def main():
     from brainfm_b200 import _lib
     n_subjects = 2 * BATCH          # the end-to-end arm alternates between two sets of subjects
     subs = make_inputs(n_subjects)
-    ds = build_dataset(subs, device)
+    ds = build_dataset(subs, device, args.planner)
     from brainfm_b200 import parallel as par
     # the path shards by sample: every rank generates its own stream of batches (disjoint random streams),
     # there is no data-path collective; only the timing below is reduced (max over ranks)
@@ -267,10 +269,15 @@ def main():
     items = ds.generate_batch(idxs)
     nc = []
     ns = []
-    for j in ds._last_jobs:
-        bb = j["plan"].bbox_host()
-        nc.append((bb[3] - bb[0]) * (bb[4] - bb[1]) * (bb[5] - bb[2]))
-        ns.append(int(np.prod(j["p"]["new_size"])))
+    if ds._native is not None:
+        for bb, new in ds._native.last_shapes():
+            nc.append((bb[3] - bb[0]) * (bb[4] - bb[1]) * (bb[5] - bb[2]))
+            ns.append(int(np.prod(new)))
+    else:
+        for j in ds._last_jobs:
+            bb = j["plan"].bbox_host()
+            nc.append((bb[3] - bb[0]) * (bb[4] - bb[1]) * (bb[5] - bb[2]))
+            ns.append(int(np.prod(j["p"]["new_size"])))
     nc_mean, ns_mean = float(np.mean(nc)), float(np.mean(ns))
     peak, peak_src = peaks()
     warp_bytes = BATCH * (8 * nc_mean + 12 * N)

@@ -44,10 +44,18 @@ _GMM_SHIFT = np.array([[25], [5]], dtype=np.float32)
 class BaseGen(Dataset):
     """BaseGen dataset (Generator/datasets.py:25-681)."""
 
-    def __init__(self, gen_args, device='cuda', draws=None):
+    def __init__(self, gen_args, device='cuda', draws=None, planner='auto'):
+        """planner: 'python' -- every item is planned in Python with draws from the numpy/torch global generators
+        in the reference's order; 'native' -- batches are planned by the library (bfm_plan_batch, Generator/native.py;
+        raises if the configuration needs the Python planner); 'auto' -- native whenever the configuration allows it
+        and the draw source is the default one."""
         if not torch.cuda.is_available():
             raise _lib.BfmError("brainfm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _lib.lib()
+        if planner not in ('auto', 'python', 'native'):
+            raise ValueError("planner must be 'auto', 'python' or 'native'")
+        self.planner = planner
+        self._native = None
         self.gen_args = gen_args
         self.split = gen_args.split
         self.synth_args = self.gen_args.generator
@@ -786,14 +794,35 @@ class BaseGen(Dataset):
         modalities into the synthetic image (mixing needs the normalised targets BEFORE the warp)."""
         if self.hemis_mask is not None or any(j['p']['mix'] is not None for j in jobs):
             return []
-        mods, plan, out = ctx['modalities'], ctx['deform']['_plan'], []
+        return self._fused_aux_volumes(ctx['modalities'], ctx['deform']['_plan'].src)
+
+    def _fused_aux_volumes(self, mods, src):
+        out = []
         for key in ('T1', 'T2', 'FLAIR'):
             if key not in mods or (key + '_DM') in mods or K.processing_funcs.get(key) is not read_and_deform_image:
                 continue
             vol = self.cache.get(mods[key], 'f32')
-            if list(vol.shape[:3]) == plan.src:
+            if list(vol.shape[:3]) == list(src):
                 out.append((key, vol))
         return out[:_lib.MAX_AUX]
+
+    def _native_planner(self, indices):
+        """The NativePlanner to use for this batch, or None (Python planner)."""
+        if self.planner == 'python':
+            return None
+        from .native import NativePlanner
+        ok = NativePlanner.config_ok(self) and (self.planner == 'native' or type(self.rng) is HostDraws)
+        if ok:
+            if self._native is None:
+                self._native = NativePlanner(self)
+            for idx in indices:
+                _, input_prob, t1_path, _ = self.idx_to_path(int(idx))
+                if not self._native.item_ok(input_prob, self.get_info(t1_path)):
+                    ok = False
+                    break
+        if not ok and self.planner == 'native':
+            raise NotImplementedError("this configuration needs the Python planner (planner='python' or 'auto')")
+        return self._native if ok else None
 
     def _real_input(self, input_mode, setups, deform_dict, res, target):
         from .utils import read_and_deform
@@ -824,6 +853,9 @@ class BaseGen(Dataset):
     def generate_batch(self, indices, timers=None):
         """Several items in one go: all host draws first (reference order, item by item), then ONE batched launch
         per stage of the fused chain.  Returns a list of __getitem__ tuples."""
+        native = self._native_planner(indices)
+        if native is not None:
+            return native.run(indices, timers=timers)
         arena = self.arena.begin()
         ctxs, jobs, spans, slow = [], [], [], {}
         for n, idx in enumerate(indices):
@@ -898,8 +930,12 @@ class BrainIDGen(BaseGen):
     _default_target = staticmethod(lambda: 1.)
     _list_samples = True
 
-    def __init__(self, gen_args, device='cuda', draws=None):
-        super(BrainIDGen, self).__init__(gen_args, device, draws)
+    def __init__(self, gen_args, device='cuda', draws=None, planner='auto'):
+        self.all_samples = gen_args.generator.all_samples        # _gen_arg_sets may be asked early
+        self.mild_samples = gen_args.generator.mild_samples
+        self.mild_generator_args = gen_args.mild_generator
+        self.severe_generator_args = gen_args.severe_generator
+        super(BrainIDGen, self).__init__(gen_args, device, draws, planner)
         self.all_samples = gen_args.generator.all_samples
         self.mild_samples = gen_args.generator.mild_samples
         self.mild_generator_args = gen_args.mild_generator

@@ -1,0 +1,358 @@
+"""Batched planning through the native host planner (libbfm `bfm_plan_batch`, csrc/planner.cu).
+
+`BaseGen.generate_batch` plans every item in Python (draws from the numpy/torch global generators in the
+reference's order, ~250 us per sample).  When nothing in the configuration needs Python per sample -- synthetic
+inputs only, stock augmentation chain, no mixing with real modalities, no pathology / surface task, no random
+shift -- the whole batch is planned by ONE call into the library instead: the same arithmetic in C, draws from
+an in-library Philox stream keyed on (seed, item counter) (the seed itself is one draw of numpy's global
+generator, so `np.random.seed` still makes a run reproducible), small random grids drawn on the device.
+With a `ReplayDraws` source the planner runs in replay mode and consumes the recorded draws (parity tests).
+"""
+import ctypes as C
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..draws import HostDraws
+from . import constants as K
+from .utils import DeformDict, DeformPlan, _stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class NativePlanner:
+    def __init__(self, ds):
+        self.ds = ds
+        self.device = ds.device
+        self.size = [int(v) for v in ds.size]
+        self.N = int(np.prod(self.size))
+        self.n_samples = len(ds._gen_arg_sets())
+        self.counter = 0
+        self.seed = None
+        self._keep = []
+        self.cfg = self._build_cfg()
+        self.last = None
+
+    # ---- eligibility ------------------------------------------------------------------------------
+    @staticmethod
+    def config_ok(ds):
+        a = ds.synth_args
+        if a.left_hemis_only or a.random_shift or getattr(a, 'bspline_zooming', False):
+            return False
+        if ds.gen_args.mix_synth_prob > 0 or 'surface' in ds.tasks or 'pathology' in ds.tasks:
+            return False
+        if not ds._stock_chain('synth'):
+            return False
+        if len(ds._gen_arg_sets()) > _lib.PLAN_MAX_SAMPLES:
+            return False
+        return True
+
+    def item_ok(self, input_prob, modalities):
+        """Only synthetic inputs: no real modality of this subject can be drawn as the input (datasets.py:572-580)."""
+        return not any(input_prob.get(m, 0) > 0 and m in modalities for m in ('T1', 'T2', 'FLAIR', 'CT'))
+
+    # ---- configuration (built once) ------------------------------------------------------------------
+    def _build_cfg(self):
+        ds, size = self.ds, self.size
+        a = ds.synth_args
+        cfg = _lib.PlanCfg()
+        cfg.size[:] = size
+        cfg.res[:] = [float(v) for v in ds.res_training_data]
+        cfg.low_res_only = int(bool(a.low_res_only))
+        cfg.nonlinear_transform = int(bool(a.nonlinear_transform))
+        for k in ('photo_prob', 'pathology_prob', 'random_shape_prob', 'flip_prob', 'max_rotation', 'max_shear',
+                  'max_scaling', 'nonlin_scale_min', 'nonlin_scale_max', 'nonlin_std_max', 'ct_prob'):
+            setattr(cfg, k, float(getattr(a, k)))
+        cfg.mix_synth_prob = float(ds.gen_args.mix_synth_prob)
+        grp = np.full(256, -1, dtype=np.int8)
+        from .datasets import ct_brightness_group
+        for g, name in enumerate(('darker', 'dark', 'bright', 'brighter')):
+            for l in ct_brightness_group[name]:
+                grp[l] = g
+        C.memmove(cfg.ct_group, grp.ctypes.data, 256)
+        # per-sample parameter ranges: generator values with the overrides of each sample applied in order
+        sets = ds._gen_arg_sets()
+        cfg.n_samples = len(sets)
+        for k, overrides in enumerate(sets):
+            vals = dict(vars(ds.gen_args.generator))
+            for o in overrides:
+                vals.update(vars(o))
+            for f, _ in _lib.PlanAug._fields_:
+                setattr(cfg.aug[k], f, float(vals[f]))
+        # zoom-table directories
+        tables = ds.tables
+        tables.prebuild(size)
+        ends, dirs = [], []
+        for ax in range(3):
+            n_out = size[ax]
+            fwd = (_lib.ZoomAxis * (n_out + 1))()
+            inv = (_lib.ZoomAxis * (n_out + 1))()
+            for n_in in range(1, n_out + 1):
+                for arr, factor in ((fwd, n_out / n_in), (inv, 1 / (n_in / n_out))):
+                    z = arr[n_in]
+                    z.lo, z.hi, z.wl, z.wh = tables.zoom(n_in, factor, n_out)
+                    z.valid = int(int(np.round(n_in * factor)) == n_out)
+                fwd[n_in].cand, fwd[n_in].ncand = tables.cand(n_in, n_out / n_in, n_out)
+            dirs.append((fwd, inv))
+            cfg.fwd[ax] = C.addressof(fwd)
+            cfg.inv[ax] = C.addressof(inv)
+            cfg.ends[ax] = tables.ends(n_out)[0]
+        ident = torch.cat([torch.arange(size[2], dtype=torch.int32, device=self.device).view(torch.float32),
+                           torch.ones(size[2], dtype=torch.float32, device=self.device)])
+        cfg.ident_start = ident.data_ptr()
+        cfg.ident_w = ident.data_ptr() + 4 * size[2]
+        self._keep += [dirs, ident]
+        return cfg
+
+    # ---- one batch ---------------------------------------------------------------------------------------
+    def run(self, indices, timers=None):
+        ds, L = self.ds, _lib.lib()
+        size, N, ns = self.size, self.N, self.n_samples
+        B = len(indices)
+        total = B * ns
+        dev = self.device
+        rng = ds.rng
+        replay = getattr(rng, 'replay', False)
+        if self.seed is None and not replay:
+            self.seed = int(np.random.randint(0, 2 ** 62))
+        ds.hemis_mask = None
+        want_bflog = ds._want_bflog('synth')
+        want_res = 'super_resolution' in ds.tasks
+        # ---- items: volumes from the device cache
+        items = (_lib.PlanItem * B)()
+        metas = []
+        n_aux_total, src_pad = 0, 0
+        for n, idx in enumerate(indices):
+            if torch.is_tensor(idx):
+                idx = idx.tolist()
+            dataset_name, input_prob, t1_path, age = ds.idx_to_path(idx)
+            mods = ds.get_info(t1_path)
+            lab = ds.cache.get(mods['Gen'], 'gen')
+            it = items[n]
+            it.labels = lab.data_ptr()
+            it.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
+            src = [int(v) for v in lab.shape[:3]]
+            it.src[:] = src
+            aux = ds._fused_aux_volumes(mods, src)
+            it.n_aux = len(aux)
+            for c, (key, vol) in enumerate(aux):
+                it.aux_src[c] = vol.data_ptr()
+            n_aux_total += len(aux)
+            src_pad = max(src_pad, src[0] * src[1] * src[2] + src[1] * src[2] + src[2] + 1)
+            metas.append((idx, dataset_name, t1_path, age, dict(mods), aux, src))
+        src_pad = (src_pad + 3) // 4 * 4
+        # ---- outputs (fresh) and persistent scratch
+        out = torch.empty((total, 1, *size), dtype=torch.float32, device=dev)
+        bfl = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_bflog else None
+        res = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_res else None
+        aux_all = torch.empty((n_aux_total, 1, *size), dtype=torch.float32, device=dev) if n_aux_total else None
+        syn_ws = ds._workspace('syn', total * src_pad, zero=True)
+        if ds._ws.get('syn_stride') != src_pad:
+            if 'syn_stride' in ds._ws:
+                syn_ws.zero_()
+            ds._ws['syn_stride'] = src_pad
+        p_ibf = ds._workspace('i_bf', total * N).data_ptr()
+        p_tmp = ds._workspace('tmp', total * 2 * N).data_ptr()
+        p_low = ds._workspace('lowres', total * N).data_ptr()
+        p_raw = ds._workspace('aux_raw', n_aux_total * N).data_ptr() if n_aux_total else 0
+        outs = (_lib.PlanOut * total)()
+        o_np = np.frombuffer(outs, dtype=np.uint64).reshape(total, 8)
+        q = np.arange(total, dtype=np.uint64)
+        step = np.uint64(4 * N)
+        o_np[:, 0] = np.uint64(out.data_ptr()) + q * step
+        o_np[:, 1] = (np.uint64(bfl.data_ptr()) + q * step) if want_bflog else 0
+        o_np[:, 2] = (np.uint64(res.data_ptr()) + q * step) if want_res else 0
+        o_np[:, 3] = np.uint64(syn_ws.data_ptr()) + q * np.uint64(4 * src_pad)
+        o_np[:, 4] = np.uint64(p_ibf) + q * step
+        o_np[:, 5] = np.uint64(p_tmp) + (2 * q) * step
+        o_np[:, 6] = np.uint64(p_tmp) + (2 * q + 1) * step
+        o_np[:, 7] = np.uint64(p_low) + q * step
+        k_aux = 0
+        for n in range(B):
+            it = items[n]
+            for c in range(it.n_aux):
+                it.aux_out[c] = aux_all.data_ptr() + 4 * N * k_aux
+                it.aux_raw[c] = p_raw + 4 * N * k_aux
+                k_aux += 1
+        # ---- draws to replay (parity tests): scalars and small arrays flattened in log order
+        keep = []
+        flat, n_flat = None, 0
+        if replay:
+            vals, k_eps = [], defaultdict(int)
+            while not rng.done():
+                tag, v = rng.log[rng.pos]
+                rng.pos += 1
+                if tag in ('gmm.eps', 'noise.eps'):
+                    t = v.to(dev).float().contiguous()
+                    keep.append(t)
+                    arr = items[0].eps_gmm if tag == 'gmm.eps' else items[0].eps_noise
+                    arr[k_eps[tag]] = t.data_ptr()
+                    k_eps[tag] += 1
+                else:
+                    vals.append(np.asarray(v.numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float64).reshape(-1))
+            flat = np.ascontiguousarray(np.concatenate(vals))
+            n_flat = flat.size
+            if B != 1:
+                raise ValueError("replayed draws drive one item at a time")
+        # ---- plan
+        arena = ds.arena.begin()
+        slot = arena.slots[arena.cur]
+        start = (arena.used + 15) // 16 * 16
+        used, upload = C.c_int64(arena.used), C.c_int64(0)
+        descs = (_lib.GenSample * total)()
+        descs_dev = C.c_void_p(0)
+        info = (_lib.PlanInfo * B)()
+        consumed = C.c_int64(0)
+        _lib.check(L.bfm_plan_batch(C.addressof(self.cfg), B, C.addressof(items), C.addressof(outs),
+                                    self.seed or 0, self.counter, slot["host"].data_ptr(), slot["dev"].data_ptr(),
+                                    arena.capacity, C.byref(used), C.byref(upload), C.addressof(descs),
+                                    C.byref(descs_dev), C.addressof(info),
+                                    flat.ctypes.data if replay else None, n_flat, C.byref(consumed)))
+        if replay and consumed.value != n_flat:
+            raise AssertionError("native planner consumed %d of %d replayed draws" % (consumed.value, n_flat))
+        self.counter += B
+        arena.used = used.value
+        st = _stream()
+        nbytes = (upload.value + 15) // 16 * 16
+        _lib.check(L.bfm_upload_pinned(slot["dev"].data_ptr() + start, slot["host"].data_ptr() + start, nbytes, st))
+        arena.committed = arena.used
+        # ---- per-item context (targets that do not ride on the fused gather need a DeformPlan)
+        h, d_dev = C.addressof(descs), descs_dev.value
+        ctxs = []
+        other_targets = any(t in K.processing_funcs and t not in ('T1', 'T2', 'FLAIR') for t in ds.tasks)
+        for n, (idx, dataset_name, t1_path, age, mods, aux, src) in enumerate(metas):
+            inf = info[n]
+            setups = {'resolution': np.array(inf.resolution[:]), 'thickness': np.array(inf.thickness[:]),
+                      'photo_mode': bool(inf.photo_mode), 'pathol_mode': False, 'pathol_random_shape': False,
+                      'spac': inf.spac if inf.photo_mode else None, 'flip': bool(inf.flip), 'hemis': 'both'}
+            ctxs.append(dict(idx=idx, dataset_name=dataset_name, case_name=_case_name(t1_path), input_mode='synth',
+                             age=age, setups=setups, modalities=mods, aux=aux, src=src, n=n))
+        need_plans = other_targets or any(len(c['aux']) < sum(1 for k in ('T1', 'T2', 'FLAIR') if k in c['modalities'])
+                                          for c in ctxs)
+
+        def stage(name, fn):
+            if timers is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _lib.check(fn(h, d_dev, total, st))
+            if timers is not None:
+                e1.record()
+                timers.setdefault(name, []).append((e0, e1))
+
+        if timers is None and not need_plans:
+            _lib.check(L.bfm_gen_run(h, d_dev, total, st))
+        else:
+            stage('plan', L.bfm_gen_plan)
+            stage('bbox', L.bfm_gen_bbox)
+        aux_views = aux_all.unbind(0) if aux_all is not None else ()
+        k_aux = 0
+        targets = []
+        for ctx in ctxs:
+            n = ctx['n']
+            target = defaultdict(ds._default_target)
+            target['name'] = ctx['case_name']
+            fused = {}
+            for key, _ in ctx['aux']:
+                fused[key] = aux_views[k_aux]
+                k_aux += 1
+            deform = self._deform_dict(ctx, descs[n * ns], info[n], arena) if need_plans else None
+            ctx['deform'] = deform
+            ds.modalities = ctx['modalities']
+            for key in ('T1', 'T2', 'FLAIR'):
+                if key in fused:
+                    target[key] = fused[key]
+                elif key in ctx['modalities']:
+                    target.update(ds.read_and_deform_target(ctx['idx'], target.keys(), key, 'synth', ctx['setups'],
+                                                            deform))
+                else:
+                    target[key] = 0.
+            if other_targets:
+                for task_name in ds.tasks:
+                    if task_name in K.processing_funcs.keys() and task_name not in ('T1', 'T2', 'FLAIR'):
+                        target.update(ds.read_and_deform_target(ctx['idx'], target.keys(), task_name, 'synth',
+                                                                ctx['setups'], deform))
+            target['pathology'] = 0.
+            target['pathology_prob'] = 0.
+            targets.append(target)
+        if timers is not None or need_plans:
+            stage('gmm', L.bfm_gen_gmm)
+            stage('warp', L.bfm_gen_warp)
+            stage('resample', L.bfm_gen_resample)
+            stage('finish', L.bfm_gen_finish)
+        arena.mark_done()
+        # ---- results
+        out_v = out.unbind(0)
+        bfl_v = bfl.unbind(0) if bfl is not None else None
+        res_v = res.unbind(0) if res is not None else None
+        results = []
+        for q_ in range(total):
+            s = {}
+            if res_v is not None:
+                s['high_res_residual'] = res_v[q_]
+            s['input'] = out_v[q_]
+            if bfl_v is not None:
+                s['bias_field_log'] = bfl_v[q_]
+            results.append(s)
+        tuples = []
+        for ctx, target in zip(ctxs, targets):
+            n = ctx['n']
+            sample = results[n * ns:(n + 1) * ns] if ds._list_samples else results[n * ns]
+            if ctx['age'] is not None:
+                target['age'] = ctx['age']
+            tuples.append((ds.datasets_num, ctx['dataset_name'], 'synth', target, sample))
+        if ctxs:
+            ds.last_setups, ds.last_deform = ctxs[-1]['setups'], ctxs[-1]['deform']
+        self.last = dict(descs=descs, descs_dev=d_dev, info=info, total=total, keep=(out, bfl, res, aux_all, keep),
+                         arena_slot=arena.cur)
+        ds._last_descs = (descs, d_dev, total)
+        return tuples
+
+    def _deform_dict(self, ctx, desc, inf, arena):
+        """A DeformDict around the planned deformation, for targets computed by the op-wise entry points."""
+        ds = self.ds
+        plan = DeformPlan.__new__(DeformPlan)
+        plan.size = list(self.size)
+        plan.src = list(ctx['src'])
+        plan.device = self.device
+        plan.A_host = np.array(inf.A[:], dtype=np.float32).reshape(3, 3)
+        plan.c2_host = np.array(inf.c2[:], dtype=np.float32)
+        plan.photo = bool(inf.photo_mode)
+        plan.F_full = None
+        plan.struct = _lib.Deform.from_buffer_copy(desc.d)
+        plan.bbox_ptr = desc.bbox
+        plan._bbox = None
+        plan._arena, plan._slot = arena, arena.cur
+        plan._bbox_off = desc.bbox - arena.slots[arena.cur]["dev"].data_ptr()
+        plan._bbox_host = None
+        plan.have_bbox = True
+        fs = list(inf.fs[:])
+        small = None
+        if fs[0] > 0:
+            off = desc.d.fsmall - arena.slots[arena.cur]["dev"].data_ptr()
+            small = arena.view(off, fs[0] * fs[1] * fs[2] * 3, torch.float32).view(*fs, 3)
+        return DeformDict({'scaling_factor_distances': inf.scaling_factor_distances, 'Fneg': None, '_plan': plan,
+                           '_Fsmall': small, '_photo': bool(inf.photo_mode)})
+
+    # ---- what the last batch looked like (bench.py) ---------------------------------------------------------
+    def last_shapes(self):
+        """[(bbox ints, new_size)] of every sample of the last batch (one small D2H per sample)."""
+        torch.cuda.synchronize()
+        last = self.last
+        arena = self.ds.arena
+        base = arena.slots[last['arena_slot']]["dev"].data_ptr()
+        rows = []
+        ns = self.n_samples
+        for q in range(last['total']):
+            d = last['descs'][q]
+            bb = arena.view(d.bbox - base, 8, torch.int32, slot=last['arena_slot'])[:6].tolist()
+            rows.append((bb, list(last['info'][q // ns].new_size[q % ns])))
+        return rows
+
+
+def _case_name(t1_path):
+    import os
+    return os.path.basename(t1_path).split('.T1w.nii')[0]

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BFM_LIB") or os.path.join(_HERE, "libbfm.so")
 
 BFM_OK, BFM_E_INVALID, BFM_E_UNSUPPORTED, BFM_E_CUDA = 0, -1, -2, -3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_f = C.c_float
 c_i = C.c_int
@@ -45,7 +45,49 @@ class GenSample(C.Structure):
                 ("noise_std", c_f), ("eps_noise", c_p), ("tmp", c_p * 2), ("lowres", c_p), ("new_size", c_i * 3),
                 ("utab", ZoomTab), ("maxval", c_p), ("out", c_p), ("residual", c_p),
                 ("n_aux", c_i), ("aux_src", c_p * MAX_AUX), ("aux_raw", c_p * MAX_AUX), ("aux_out", c_p * MAX_AUX),
-                ("aux_mm", c_p), ("x_begin", c_i), ("x_count", c_i)]
+                ("aux_mm", c_p), ("x_begin", c_i), ("x_count", c_i),
+                ("gen_small", c_i), ("fs_std", c_f), ("bf_std", c_f)]
+
+
+# ---- native host planner (bfm_plan_batch) ----------------------------------------------------------------
+PLAN_MAX_SAMPLES = 16
+c_d = C.c_double
+
+
+class ZoomAxis(C.Structure):
+    _fields_ = [("lo", c_p), ("hi", c_p), ("wl", c_p), ("wh", c_p), ("cand", c_p), ("ncand", c_i), ("valid", c_i)]
+
+
+class PlanAug(C.Structure):
+    _fields_ = [("gamma_std", c_d), ("bf_scale_min", c_d), ("bf_scale_max", c_d), ("bf_std_min", c_d),
+                ("bf_std_max", c_d), ("noise_std_min", c_d), ("noise_std_max", c_d)]
+
+
+class PlanCfg(C.Structure):
+    _fields_ = [("size", c_i * 3), ("res", c_d * 3), ("low_res_only", c_i), ("nonlinear_transform", c_i),
+                ("photo_prob", c_d), ("pathology_prob", c_d), ("random_shape_prob", c_d), ("flip_prob", c_d),
+                ("max_rotation", c_d), ("max_shear", c_d), ("max_scaling", c_d),
+                ("nonlin_scale_min", c_d), ("nonlin_scale_max", c_d), ("nonlin_std_max", c_d),
+                ("ct_prob", c_d), ("mix_synth_prob", c_d), ("ct_group", C.c_int8 * 256), ("n_samples", c_i),
+                ("aug", PlanAug * PLAN_MAX_SAMPLES),
+                ("fwd", c_p * 3), ("inv", c_p * 3), ("ends", c_p * 3), ("ident_start", c_p), ("ident_w", c_p)]
+
+
+class PlanItem(C.Structure):
+    _fields_ = [("labels", c_p), ("label_is_u8", c_i), ("src", c_i * 3), ("n_aux", c_i),
+                ("aux_src", c_p * MAX_AUX), ("aux_out", c_p * MAX_AUX), ("aux_raw", c_p * MAX_AUX),
+                ("eps_gmm", c_p * PLAN_MAX_SAMPLES), ("eps_noise", c_p * PLAN_MAX_SAMPLES)]
+
+
+class PlanOut(C.Structure):
+    _fields_ = [("out", c_p), ("bflog_out", c_p), ("residual", c_p), ("syn", c_p), ("i_bf", c_p), ("tmp", c_p * 2),
+                ("lowres", c_p)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("photo_mode", c_i), ("flip", c_i), ("spac", c_d), ("resolution", c_d * 3), ("thickness", c_d * 3),
+                ("scaling_factor_distances", c_d), ("A", c_f * 9), ("c2", c_f * 3), ("fs", c_i * 3),
+                ("new_size", (c_i * 3) * PLAN_MAX_SAMPLES)]
 
 
 class BfmError(RuntimeError):
@@ -79,6 +121,8 @@ _PROTOS = {
     "bfm_gen_resample": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_finish": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_run": (c_i, [c_p, c_p, c_i, c_p]),
+    "bfm_plan_batch": (c_i, [c_p, c_i, c_p, c_p, c_u64, c_u64, c_p, c_p, c_i64, C.POINTER(c_i64), C.POINTER(c_i64),
+                             c_p, C.POINTER(c_p), c_p, c_p, c_i64, C.POINTER(c_i64)]),
     "bfm_interpol": (c_i, [c_i, c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_i, c_i, c_i,
                            c_i, c_i, c_i, c_i64, c_p]),
     "bfm_spline_filter": (c_i, [c_p, c_i, c_i64, c_i, c_i64, c_i, C.POINTER(C.c_double), c_i, c_p]),

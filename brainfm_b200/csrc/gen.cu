@@ -104,6 +104,23 @@ __global__ void __launch_bounds__(128) k_gen_plan(const bfm_gen_sample *__restri
     build_band(b.n_in, b.n_out, b.T, b.sigma, const_cast<int *>(b.start), const_cast<float *>(b.w));
 }
 
+// Small random grids of the native planner (gen_small): std * N(0,1), Philox streams 2 (deformation) and 3 (bias).
+__global__ void __launch_bounds__(256) k_gen_small(const bfm_gen_sample *__restrict__ S) {
+    const bfm_gen_sample &s = S[blockIdx.y];
+    const int which = blockIdx.z;                       // 0: deformation grid, 1: bias grid
+    if (!(s.gen_small & (1 << which))) return;
+    float *dst = const_cast<float *>(which == 0 ? s.d.fsmall : s.bfsmall);
+    if (!dst) return;
+    const int n = which == 0 ? s.d.fs[0] * s.d.fs[1] * s.d.fs[2] * 3 : s.bs[0] * s.bs[1] * s.bs[2];
+    const float std = which == 0 ? s.fs_std : s.bf_std;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; 4 * g < n; g += gridDim.x * blockDim.x) {
+        const float4 e = philox_normal4(s.seed, 2u + which, (uint64_t)g);
+        const float v[4] = {e.x, e.y, e.z, e.w};
+        for (int q = 0; q < 4; ++q)
+            if (4 * g + q < n) dst[4 * g + q] = std * v[q];
+    }
+}
+
 __global__ void __launch_bounds__(128) k_band_build(int n_in, int n_out, int T, double sigma, int *start, float *w) {
     build_band(n_in, n_out, T, sigma, start, w);
 }
@@ -968,8 +985,9 @@ int bfm_band_build(int n_in, int n_out, double sigma, int T, int *start, float *
 int bfm_gen_plan(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *stream) {
     int rc = check_batch(h, d, B);
     if (rc) return rc;
-    bool any = false;
-    for (int b = 0; b < B; ++b)
+    bool any = false, small = false;
+    for (int b = 0; b < B; ++b) {
+        if (h[b].gen_small) small = true;
         for (int p = 0; p < h[b].n_band; ++p) {
             const bfm_band &bd = h[b].band[p];
             if (!bd.build) continue;
@@ -977,6 +995,12 @@ int bfm_gen_plan(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
             if (bd.T < 2 || bd.T > 65 || (bd.T & 1) || !bd.start || !bd.w || bd.n_in <= 0 || bd.n_out <= 0)
                 return fail(BFM_E_INVALID, "%s", "bfm_gen_plan: bad band descriptor (T must be even, 2..64)");
         }
+    }
+    if (small) {
+        k_gen_small<<<dim3(4, B, 2), 256, 0, (cudaStream_t)stream>>>(d);
+        rc = check_launch("bfm_gen_plan");
+        if (rc) return rc;
+    }
     if (!any) return BFM_OK;
     k_gen_plan<<<dim3(3, B), 128, 0, (cudaStream_t)stream>>>(d);
     return check_launch("bfm_gen_plan");

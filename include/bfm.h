@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 3
+#define BFM_ABI_VERSION 4
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -222,6 +222,12 @@ typedef struct bfm_gen_sample {
        aux_raw keep their whole-volume indexing: the caller passes pointers biased by -x_begin planes (the
        flipped plane for bflog_out) so that only the owned planes have to exist. */
     int x_begin, x_count;
+    /* Small random grids drawn on the device (native planner, bfm_plan_batch): bfm_gen_plan fills d.fsmall with
+       fs_std * N(0,1) when gen_small & 1 (Philox stream 2 of `seed`; random_nonlinear_transform,
+       Generator/datasets.py:209) and bfsmall with bf_std * N(0,1) when gen_small & 2 (stream 3; add_bias_field,
+       Generator/utils.py:584) -- the pointers must then address writable device scratch. */
+    int gen_small;
+    float fs_std, bf_std;
 } bfm_gen_sample;
 
 /* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,
@@ -236,6 +242,93 @@ int bfm_gen_resample(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, 
 int bfm_gen_finish(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
 /* all six stages back to back */
 int bfm_gen_run(const bfm_gen_sample *s_host, const bfm_gen_sample *s_dev, int B, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Native host planner: every per-sample scalar draw and all the scalar set-up arithmetic of
+ * BaseGen.__getitem__ / BrainIDGen.__getitem__ for synthetic inputs with the stock augmentation chain, in the
+ * reference's draw order, filled straight into bfm_gen_sample descriptors (HOST code, no Python per sample):
+ *   read_input draw                      Generator/datasets.py:572
+ *   get_setup_params, resolution_sampler Generator/datasets.py:466-493, Generator/utils.py:34-57
+ *   random_affine_transform              Generator/datasets.py:187-201, make_affine_matrix utils.py:102-116
+ *   random_nonlinear_transform (sizes)   Generator/datasets.py:203-212
+ *   get_contrast                         Generator/datasets.py:430-464
+ *   gamma / bias / resample / noise set-up  Generator/utils.py:568-572, 574-585, 591-609, 633-635
+ * Draw source: replay == NULL: an in-library Philox4x32-10 stream keyed on (seed, sample counter) -- same
+ * distributions as the reference's numpy/torch draws, not the same streams; the small random grids are then
+ * drawn on the device (gen_small).  replay != NULL: the draws are read, in the reference's order, from a flat
+ * array of doubles (scalars, then every element of array-shaped draws; the parity tests feed the oracle's
+ * log) and the small grids are written into the pinned arena by the host.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bfm_zoom_axis {      /* device-resident myzoom_torch tables of one axis, one (n_in -> n_out) pair */
+    const int *lo, *hi;
+    const float *wl, *wh;
+    const int *cand;                /* bounding-box candidate voxels of this zoom (forward tables only) */
+    int ncand;
+    int valid;                      /* round(n_in * factor) == n_out */
+} bfm_zoom_axis;
+
+typedef struct bfm_plan_aug {       /* parameter ranges of one sample of an item (generator + overrides) */
+    double gamma_std, bf_scale_min, bf_scale_max, bf_std_min, bf_std_max, noise_std_min, noise_std_max;
+} bfm_plan_aug;
+
+#define BFM_PLAN_MAX_SAMPLES 16
+
+typedef struct bfm_plan_cfg {
+    int size[3];
+    double res[3];                  /* res_training_data */
+    int low_res_only, nonlinear_transform;
+    double photo_prob, pathology_prob, random_shape_prob, flip_prob;
+    double max_rotation, max_shear, max_scaling;
+    double nonlin_scale_min, nonlin_scale_max, nonlin_std_max;
+    double ct_prob, mix_synth_prob;
+    int8_t ct_group[256];           /* -1, or 0..3 = darker, dark, bright, brighter (constants.py) */
+    int n_samples;                  /* samples per item: 1 (BaseGen) or all_samples (BrainIDGen) */
+    bfm_plan_aug aug[BFM_PLAN_MAX_SAMPLES];
+    /* directories indexed by n_in = 0..size[a]: fwd = zoom by size/n_in (small grids -> training grid),
+       inv = zoom by 1/(n_in/size) (low-res grid -> training grid) */
+    const bfm_zoom_axis *fwd[3];
+    const bfm_zoom_axis *inv[3];
+    const int *ends[3];             /* device {0, size[a]-1}: candidates of an axis without nonlinear field */
+    const int *ident_start;         /* device arange(size[2]) and ones(size[2]): identity band */
+    const float *ident_w;
+} bfm_plan_cfg;
+
+typedef struct bfm_plan_item {
+    const void *labels;             /* device, full source volume */
+    int label_is_u8;
+    int src[3];
+    int n_aux;                      /* real-image targets riding on the gather of the item's FIRST sample */
+    const float *aux_src[BFM_MAX_AUX];
+    float *aux_out[BFM_MAX_AUX];
+    float *aux_raw[BFM_MAX_AUX];
+    /* replay mode only: injected volume-sized normal fields of each sample (device) */
+    const float *eps_gmm[BFM_PLAN_MAX_SAMPLES];
+    const float *eps_noise[BFM_PLAN_MAX_SAMPLES];
+} bfm_plan_item;
+
+typedef struct bfm_plan_out {       /* per SAMPLE buffers (device), caller allocated */
+    float *out, *bflog_out, *residual;
+    float *syn, *i_bf, *tmp[2], *lowres;
+} bfm_plan_out;
+
+typedef struct bfm_plan_info {      /* what the host needs to know about a planned ITEM */
+    int photo_mode, flip;
+    double spac, resolution[3], thickness[3], scaling_factor_distances;
+    float A[9], c2[3];
+    int fs[3];
+    int new_size[BFM_PLAN_MAX_SAMPLES][3];
+} bfm_plan_info;
+
+/* Plans n_items items = n_items * cfg->n_samples samples.  descs_host[n]: sample descriptors (item-major), written
+ * in place and mirrored into the arena; outs[n]: per-sample buffers.  The arena is one pinned host buffer and its
+ * device twin (same layout): on return *arena_used is the end of the reservations and *upload_bytes the length of
+ * the host-written prefix that has to reach the device (bfm_upload_pinned) before bfm_gen_run;
+ * *descs_dev = device address of the descriptor array.  replay/n_replay: see above (NULL/0 = native draws);
+ * *replay_used returns the number of doubles consumed. */
+int bfm_plan_batch(const bfm_plan_cfg *cfg, int n_items, const bfm_plan_item *items, const bfm_plan_out *outs,
+                   uint64_t seed, uint64_t counter, void *arena_host, void *arena_dev, int64_t arena_capacity,
+                   int64_t *arena_used, int64_t *upload_bytes, bfm_gen_sample *descs_host, void **descs_dev,
+                   bfm_plan_info *info, const double *replay, int64_t n_replay, int64_t *replay_used);
 
 /* ------------------------------------------------------------------------------------------------
  * utils/interpol (vendored torch-interpol 0.2.3): spline resampling, forward semantics

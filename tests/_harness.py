@@ -15,7 +15,7 @@ def oracle_case(name):
     return item, orc
 
 
-def cuda_case(name, log, dataset_option=None, run=None):
+def cuda_case(name, log, dataset_option=None, run=None, planner='auto'):
     from brainfm_b200 import io as bio
     from brainfm_b200.draws import ReplayDraws
     from brainfm_b200.Generator import dataset_options
@@ -42,7 +42,7 @@ def cuda_case(name, log, dataset_option=None, run=None):
     args = mg.cfg_for(size, over, option, ref=False)
     args.split_root = root
     draws = ReplayDraws(log)
-    ds = dataset_options[dataset_option or option](args, "cuda", draws=draws)
+    ds = dataset_options[dataset_option or option](args, "cuda", draws=draws, planner=planner)
     item = ds[0] if run is None else run(ds)
     torch.cuda.synchronize()
     return item, ds, draws
