@@ -125,6 +125,9 @@ _PROTOS = {
                              c_p, C.POINTER(c_p), c_p, c_p, c_i64, C.POINTER(c_i64)]),
     "bfm_interpol": (c_i, [c_i, c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_i, c_i, c_i,
                            c_i, c_i, c_i, c_i64, c_p]),
+    "bfm_interpol_pull_fast": (c_i, [c_p, C.POINTER(c_i64), c_p, c_i64, c_p, c_i, C.POINTER(c_i), c_i, C.POINTER(c_i),
+                                     c_i, c_i, c_i, c_i64, c_p]),
+    "bfm_add_identity_grid": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "bfm_spline_filter": (c_i, [c_p, c_i, c_i64, c_i, c_i64, c_i, C.POINTER(C.c_double), c_i, c_p]),
     "bfm_perlin3d": (c_i, [c_p, C.POINTER(c_i), C.POINTER(c_i), c_p, c_p]),
     "bfm_threshold_mask": (c_i, [c_p, c_p, c_i64, C.c_double, c_p]),

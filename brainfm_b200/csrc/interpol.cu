@@ -229,6 +229,125 @@ __global__ void __launch_bounds__(128) k_interpol(const T *__restrict__ inp, con
     }
 }
 
+
+// ---- fast pull: float32, one spline order on every axis (linear or cubic), compile-time unrolled -----------
+// Same arithmetic as k_interpol (node indices, bound signs, weights from the same helpers); what changes is the
+// memory side: 32-bit element offsets premultiplied by the input strides, so that channels-last inputs (a permuted
+// view, e.g. a displacement field) are read in place, with ONE 128-bit load per tap for 4 channels of unit stride;
+// weights of a tap are combined once and reused by every channel.
+struct PullFastArgs {
+    int ishape[3];
+    int bound[3];
+    int extrapolate;
+    int B, C;
+    int64_t sB, gB;       // input / grid batch strides (elements); 0 when broadcast
+    int sC, sX, sY, sZ;   // input element strides inside one batch element
+    int64_t P;
+    int out_chlast;       // 0: out (B, C, P);  1: out (B, P, C) (the memory format follows a channels-last input)
+};
+
+template <int ORDER, int CV>
+__global__ void __launch_bounds__(256) k_pull_fast(const float *__restrict__ inp, const float *__restrict__ grid,
+                                                   float *__restrict__ out, const PullFastArgs a) {
+    constexpr int NK = ORDER + 1;
+    const int64_t total = (int64_t)a.B * a.P;
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int b = (int)(q / a.P);
+    const int64_t p = q - (int64_t)b * a.P;
+    const float *g = grid + (int64_t)b * a.gB + p * 3;
+    int off[3][NK];
+    float w[3][NK];
+    bool inb = true;
+    const int strides[3] = {a.sX, a.sY, a.sZ};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float x = __ldg(g + d);
+        const int n = a.ishape[d];
+        if (a.extrapolate != 1) {
+            const float thr = a.extrapolate == 2 ? 0.55f : 0.05f;
+            inb = inb && (x > -thr) && (x < float(n - 1) + thr);
+        }
+        const float f0 = floorf(x - float(ORDER - 1) / 2.f);
+        const float dist0 = x - f0;
+        const int64_t i0 = (int64_t)f0;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int sg = bound_sign(a.bound[d], i0 + k, n);
+            off[d][k] = bound_index(a.bound[d], i0 + k, n) * strides[d];
+            w[d][k] = spline_weight<float>(ORDER, dist0 - float(k)) * float(sg);
+        }
+    }
+    const float m = inb ? 1.f : 0.f;
+    const float *src = inp + (int64_t)b * a.sB;
+    const int64_t oC = a.out_chlast ? 1 : a.P;
+    float *dst = out + (int64_t)b * a.C * a.P + (a.out_chlast ? p * a.C : p);
+    if (CV >= 2) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kx = 0; kx < NK; ++kx)
+#pragma unroll
+            for (int ky = 0; ky < NK; ++ky) {
+                const int oxy = off[0][kx] + off[1][ky];
+                const float wxy = w[0][kx] * w[1][ky];
+#pragma unroll
+                for (int kz = 0; kz < NK; ++kz) {
+                    const float ww = wxy * w[2][kz];
+                    const float *t = src + oxy + off[2][kz];
+                    if (CV == 4) {
+                        const float4 v = __ldg((const float4 *)t);
+                        acc[0] = fmaf(v.x, ww, acc[0]); acc[1] = fmaf(v.y, ww, acc[1]);
+                        acc[2] = fmaf(v.z, ww, acc[2]); acc[3] = fmaf(v.w, ww, acc[3]);
+                    } else if (CV == 2) {
+                        const float2 v = __ldg((const float2 *)t);
+                        acc[0] = fmaf(v.x, ww, acc[0]); acc[1] = fmaf(v.y, ww, acc[1]);
+                    } else {
+                        acc[0] = fmaf(__ldg(t), ww, acc[0]); acc[1] = fmaf(__ldg(t + 1), ww, acc[1]);
+                        acc[2] = fmaf(__ldg(t + 2), ww, acc[2]);
+                    }
+                }
+            }
+        if (CV == 4 && a.out_chlast) {
+            *(float4 *)dst = make_float4(acc[0] * m, acc[1] * m, acc[2] * m, acc[3] * m);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CV; ++c) dst[c * oC] = acc[c] * m;
+        }
+    } else {
+        for (int c = 0; c < a.C; ++c) {
+            const float *sc = src + (int64_t)c * a.sC;
+            float acc = 0.f;
+#pragma unroll
+            for (int kx = 0; kx < NK; ++kx)
+#pragma unroll
+                for (int ky = 0; ky < NK; ++ky) {
+                    const int oxy = off[0][kx] + off[1][ky];
+                    const float wxy = w[0][kx] * w[1][ky];
+#pragma unroll
+                    for (int kz = 0; kz < NK; ++kz) acc = fmaf(__ldg(sc + oxy + off[2][kz]), wxy * w[2][kz], acc);
+                }
+            dst[c * oC] = acc * m;
+        }
+    }
+}
+
+// out = disp + identity grid, (B, X, Y, Z, 3) float32 (add_identity_grid, utils/interpol/api.py:480-521)
+__global__ void __launch_bounds__(256) k_add_identity(const float *__restrict__ disp, float *__restrict__ out, int B,
+                                                      int X, int Y, int Z) {
+    const int64_t total = (int64_t)B * X * Y * Z;
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int z = (int)(q % Z);
+    const int64_t r = q / Z;
+    const int y = (int)(r % Y);
+    const int x = (int)((r / Y) % X);
+    const float *d = disp + q * 3;
+    float *o = out + q * 3;
+    o[0] = __ldg(d) + (float)x;
+    o[1] = __ldg(d + 1) + (float)y;
+    o[2] = __ldg(d + 2) + (float)z;
+}
+
 // ---- prefilter: one thread per line ------------------------------------------------------------------
 struct FilterArgs {
     int64_t outer, inner;   // tensor viewed as (outer, n, inner); line stride = inner
@@ -238,14 +357,14 @@ struct FilterArgs {
     double poles[3];
 };
 
+// One line of the recursive prefilter, in place; element i of the line lives at c[i * st].
 template <typename T>
-__global__ void k_spline_filter(T *__restrict__ data, const FilterArgs a) {
-    const int64_t lines = a.outer * a.inner;
+__device__ __forceinline__ void filter_line(T *c, const int64_t st, const FilterArgs &a, const T *wt = nullptr) {
+    // wt (optional): per pole k, at wt + k*(2n+2): the dct2 initial-value weights A[i] = (T)pole^i + (T)pole^(2n-1-i)
+    // (n entries) followed by the powers P[j] = (T)pole^j (n+2 entries) -- the same expressions as below, evaluated
+    // once per block instead of once per line (they do not depend on the line).
     const int n = a.n;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < lines; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t o = q / a.inner, in = q - o * a.inner;
-        T *c = data + o * (int64_t)n * a.inner + in;
-        const int64_t st = a.inner;
+    {
         double gain = 1.0;
         for (int k = 0; k < a.npoles; ++k) gain *= (1.0 - a.poles[k]) * (1.0 - 1.0 / a.poles[k]);
         const T tg = (T)gain;
@@ -276,19 +395,29 @@ __global__ void k_spline_filter(T *__restrict__ data, const FilterArgs a) {
                 const double polen = pow(pole, (double)n);
                 const double pole_last = polen * (1.0 + 1.0 / (pole + polen * polen));
                 T s = 0;
-                for (int i = 1; i < n - 1; ++i)
-                    s += c[i * st] * ((T)pow(pole, (double)i) + (T)pow(pole, (double)(2 * n - 1 - i)));
+                if (wt) {
+                    const T *A = wt + (int64_t)k * (2 * n + 2);
+                    for (int i = 1; i < n - 1; ++i) s += c[i * st] * A[i];
+                } else {
+                    for (int i = 1; i < n - 1; ++i)
+                        s += c[i * st] * ((T)pow(pole, (double)i) + (T)pow(pole, (double)(2 * n - 1 - i)));
+                }
                 T v = s + (c[0] + (T)pole_last * c[(int64_t)(n - 1) * st]);
                 v = v * (T)(pole / (1.0 - polen * polen));
                 init = v + c[0];
             } else {                                                          // dft
                 const int mi = max_iter0 < n ? max_iter0 : n;
                 T s = 0;
-                for (int i = 1; i < mi; ++i) s += c[(int64_t)(n - i) * st] * (T)pow(pole, (double)i);
+                const T *P = wt ? wt + (int64_t)k * (2 * n + 2) + n : nullptr;
+                for (int i = 1; i < mi; ++i) s += c[(int64_t)(n - i) * st] * (P ? P[i] : (T)pow(pole, (double)i));
                 init = (s + c[0]) / (T)(1.0 - pow(pole, (double)mi));
             }
             c[0] = init;
-            for (int i = 1; i < n; ++i) c[i * st] = fma(tp, c[(i - 1) * st], c[i * st]);     // coeff.py:272-273
+            {   // causal recursion, previous value carried in a register                    coeff.py:272-273
+                T prev = init;
+#pragma unroll 8
+                for (int i = 1; i < n; ++i) { prev = fma(tp, prev, c[i * st]); c[i * st] = prev; }
+            }
             // ---- final value (coeff.py:181-224)
             T fin;
             const int64_t l = (int64_t)(n - 1) * st;
@@ -297,11 +426,77 @@ __global__ void k_spline_filter(T *__restrict__ data, const FilterArgs a) {
             else {
                 const int mi = max_iter0 < n ? max_iter0 : n;
                 T s = 0;
-                for (int i = 0; i < mi - 1; ++i) s += c[i * st] * (T)pow(pole, (double)(i + 2));
+                const T *P = wt ? wt + (int64_t)k * (2 * n + 2) + n : nullptr;
+                for (int i = 0; i < mi - 1; ++i) s += c[i * st] * (P ? P[i + 2] : (T)pow(pole, (double)(i + 2)));
                 fin = (s + tp * c[l]) / (T)(pow(pole, (double)mi) - 1.0);
             }
             c[l] = fin;
-            for (int i = n - 2; i >= 0; --i) c[i * st] = (c[(i + 1) * st] - c[i * st]) * tp;   // coeff.py:277-278
+            {   // anticausal recursion                                                      coeff.py:277-278
+                T nxt = fin;
+#pragma unroll 8
+                for (int i = n - 2; i >= 0; --i) { nxt = (nxt - c[i * st]) * tp; c[i * st] = nxt; }
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void k_spline_filter(T *__restrict__ data, const FilterArgs a) {
+    const int64_t lines = a.outer * a.inner;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < lines; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = q / a.inner, in = q - o * a.inner;
+        filter_line<T>(data + o * (int64_t)a.n * a.inner + in, a.inner, a);
+    }
+}
+
+// Tiled float32 prefilter: a block stages L whole lines in shared memory with coalesced 1-pass loads, every thread
+// runs the recursion of its own line there (bank-conflict free: pitch L for strided lines, an odd pitch for
+// contiguous ones), and the tile is written back once -- one HBM read and one write per element and axis instead
+// of the four strided sweeps of the thread-per-line kernel.
+__device__ __forceinline__ int pitch_or_n(bool contig, int pitch, int n) { return contig ? pitch : n; }
+
+template <bool CONTIG>
+__global__ void __launch_bounds__(128) k_spline_filter_tile(float *__restrict__ data, const FilterArgs a, int L,
+                                                            int pitch) {
+    extern __shared__ float tile[];
+    const int n = a.n, tid = threadIdx.x;
+    float *wt = tile + (size_t)L * pitch_or_n(CONTIG, pitch, n);
+    for (int e = tid; e < a.npoles * (2 * n + 2); e += blockDim.x) {
+        const int k = e / (2 * n + 2), r = e - k * (2 * n + 2);
+        const double pole = a.poles[k];
+        float v = 0.f;
+        if (r < n) {
+            if (a.bound == 1 || a.bound == 3) v = (float)pow(pole, (double)r) + (float)pow(pole, (double)(2 * n - 1 - r));
+        } else if (a.bound == 6) {
+            v = (float)pow(pole, (double)(r - n));
+        }
+        wt[e] = v;
+    }
+    if (CONTIG) {                      // inner == 1: lines [q0, q0+L) are one contiguous run of L*n floats
+        const int64_t q0 = (int64_t)blockIdx.x * L;
+        const int nl = (int)min((int64_t)L, a.outer - q0);
+        float *base = data + q0 * n;
+        const int total = nl * n;
+        for (int e = tid; e < total; e += blockDim.x) tile[(e / n) * pitch + (e % n)] = base[e];
+        __syncthreads();
+        if (tid < nl) filter_line<float>(tile + tid * pitch, 1, a, wt);
+        __syncthreads();
+        for (int e = tid; e < total; e += blockDim.x) base[e] = tile[(e / n) * pitch + (e % n)];
+    } else {                           // lines (o, in0 .. in0+L): element i of line t at data[o*n*inner + i*inner + in0 + t]
+        const int64_t per_o = (a.inner + L - 1) / L;
+        const int64_t o = blockIdx.x / per_o, in0 = (blockIdx.x % per_o) * L;
+        const int nl = (int)min((int64_t)L, a.inner - in0);
+        float *base = data + o * (int64_t)n * a.inner + in0;
+        for (int e = tid; e < n * L; e += blockDim.x) {
+            const int i = e / L, t = e - i * L;
+            if (t < nl) tile[e] = base[(int64_t)i * a.inner + t];
+        }
+        __syncthreads();
+        if (tid < nl) filter_line<float>(tile + tid, L, a, wt);
+        __syncthreads();
+        for (int e = tid; e < n * L; e += blockDim.x) {
+            const int i = e / L, t = e - i * L;
+            if (t < nl) base[(int64_t)i * a.inner + t] = tile[e];
         }
     }
 }
@@ -357,6 +552,66 @@ int bfm_interpol(int mode, int is_double, const void *inp, const void *grid, voi
                      : launch_interpol<float>(mode, inp, grid, out, a, (cudaStream_t)stream);
 }
 
+int bfm_interpol_pull_fast(const float *inp, const int64_t *istride, const float *grid, int64_t grid_bstride,
+                           float *out, int out_chlast, const int *ishape, int order, const int *bound, int extrapolate,
+                           int B, int C, int64_t P, void *stream) {
+    BFM_REQUIRE(inp && istride && grid && out && ishape && bound, "bfm_interpol_pull_fast: null pointer");
+    BFM_REQUIRE(B > 0 && C > 0 && P >= 0, "bfm_interpol_pull_fast: bad batch");
+    BFM_REQUIRE(extrapolate >= 0 && extrapolate <= 2, "bfm_interpol_pull_fast: extrapolate must be 0, 1 or 2");
+    if (order != 1 && order != 3) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_interpol_pull_fast: order must be 1 or 3");
+    PullFastArgs a;
+    int64_t span = 0;
+    for (int d = 0; d < 3; ++d) {
+        if (ishape[d] <= 0) return fail(BFM_E_INVALID, "%s", "bfm_interpol_pull_fast: non-positive shape");
+        if (bound[d] < 0 || bound[d] > 6) return fail(BFM_E_INVALID, "%s", "bfm_interpol_pull_fast: bound must be 0..6");
+        if (istride[2 + d] < 0) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_interpol_pull_fast: negative stride");
+        a.ishape[d] = ishape[d]; a.bound[d] = bound[d];
+        span += (int64_t)(ishape[d] - 1) * istride[2 + d];
+    }
+    if (istride[0] < 0 || istride[1] < 0) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_interpol_pull_fast: negative stride");
+    span += (int64_t)(C - 1) * istride[1];
+    if (span >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_interpol_pull_fast: batch element too large");
+    a.extrapolate = extrapolate; a.B = B; a.C = C; a.P = P;
+    a.sB = istride[0]; a.sC = (int)istride[1]; a.sX = (int)istride[2]; a.sY = (int)istride[3]; a.sZ = (int)istride[4];
+    a.gB = grid_bstride;
+    a.out_chlast = out_chlast ? 1 : 0;
+    if (a.out_chlast && C == 4 && ((uintptr_t)out % 16) != 0)
+        return fail(BFM_E_INVALID, "%s", "bfm_interpol_pull_fast: channels-last output must be 16-byte aligned");
+    if (P == 0) return BFM_OK;
+    const int64_t total = (int64_t)B * P;
+    const int64_t nblocks = (total + 255) / 256;
+    if (nblocks >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_interpol_pull_fast: too many points");
+    cudaStream_t s = (cudaStream_t)stream;
+    int cv = 0;
+    if (a.sC == 1 && C == 3) cv = 3;
+    if (a.sC == 1 && C == 4 && ((uintptr_t)inp % 16) == 0 && a.sX % 4 == 0 && a.sY % 4 == 0 && a.sZ % 4 == 0 &&
+        a.sB % 4 == 0)
+        cv = 4;
+    if (a.sC == 1 && C == 2 && ((uintptr_t)inp % 8) == 0 && a.sX % 2 == 0 && a.sY % 2 == 0 && a.sZ % 2 == 0 &&
+        a.sB % 2 == 0)
+        cv = 2;
+#define BFM_PF(O)                                                                                   \
+    do {                                                                                            \
+        if (cv == 4) k_pull_fast<O, 4><<<(unsigned)nblocks, 256, 0, s>>>(inp, grid, out, a);        \
+        else if (cv == 3) k_pull_fast<O, 3><<<(unsigned)nblocks, 256, 0, s>>>(inp, grid, out, a);   \
+        else if (cv == 2) k_pull_fast<O, 2><<<(unsigned)nblocks, 256, 0, s>>>(inp, grid, out, a);   \
+        else k_pull_fast<O, 0><<<(unsigned)nblocks, 256, 0, s>>>(inp, grid, out, a);                \
+    } while (0)
+    if (order == 1) BFM_PF(1);
+    else BFM_PF(3);
+#undef BFM_PF
+    return check_launch("bfm_interpol_pull_fast");
+}
+
+int bfm_add_identity_grid(const float *disp, float *out, int B, int X, int Y, int Z, void *stream) {
+    BFM_REQUIRE(disp && out && B > 0 && X > 0 && Y > 0 && Z > 0, "bfm_add_identity_grid: bad argument");
+    const int64_t total = (int64_t)B * X * Y * Z;
+    const int64_t nblocks = (total + 255) / 256;
+    if (nblocks >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_add_identity_grid: too many points");
+    k_add_identity<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(disp, out, B, X, Y, Z);
+    return check_launch("bfm_add_identity_grid");
+}
+
 int bfm_spline_filter(void *data, int is_double, int64_t outer, int n, int64_t inner, int bound, const double *poles_host,
                       int npoles, void *stream) {
     BFM_REQUIRE(data && outer > 0 && n > 0 && inner > 0, "bfm_spline_filter: bad argument");
@@ -368,6 +623,27 @@ int bfm_spline_filter(void *data, int is_double, int64_t outer, int n, int64_t i
     a.outer = outer; a.inner = inner; a.n = n; a.bound = bound; a.npoles = npoles;
     for (int k = 0; k < 3; ++k) a.poles[k] = k < npoles ? poles_host[k] : 0.0;
     const int64_t lines = outer * inner;
+    if (!is_double) {
+        // tiled path: L whole lines per block in shared memory (<= 160 KB), L a multiple of 32
+        const bool contig = inner == 1;
+        const int pitch = contig ? (n | 1) : 0;
+        // 32 lines per block: several blocks per SM overlap their load / recursion / store phases
+        const int64_t wt_bytes = (int64_t)npoles * (2 * n + 2) * 4;
+        int L = (int64_t)32 * (contig ? pitch : n) * 4 + wt_bytes <= 160 * 1024 ? 32 : 0;
+        const int64_t nblocks = contig ? (outer + L - 1) / (L > 0 ? L : 1) : outer * ((inner + L - 1) / (L > 0 ? L : 1));
+        if (L >= 32 && lines >= 32 && nblocks < (1LL << 31)) {
+            const size_t smem = (size_t)L * (contig ? pitch : n) * 4 + (size_t)wt_bytes;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(k_spline_filter_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                cudaFuncSetAttribute(k_spline_filter_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                attr_done = true;
+            }
+            if (contig) k_spline_filter_tile<true><<<(unsigned)nblocks, 128, smem, (cudaStream_t)stream>>>((float *)data, a, L, pitch);
+            else k_spline_filter_tile<false><<<(unsigned)nblocks, 128, smem, (cudaStream_t)stream>>>((float *)data, a, L, L);
+            return check_launch("bfm_spline_filter");
+        }
+    }
     int64_t gsz = (lines + 127) / 128;
     if (gsz > 148 * 32) gsz = 148 * 32;
     if (is_double) k_spline_filter<double><<<(unsigned)gsz, 128, 0, (cudaStream_t)stream>>>((double *)data, a);

@@ -151,6 +151,25 @@ def _pull_raw(input, grid, order, bound, extrapolate, mode=0):
     oshape = list(grid.shape[1:-1])
     P = int(math.prod(oshape))
     dt = torch.promote_types(input.dtype, grid.dtype)
+    if (mode == 0 and dim == 3 and dt == torch.float32 and order[0] in (1, 3) and order[0] == order[1] == order[2]
+            and all(s >= 0 for s in input.stride())
+            and sum((n - 1) * s for n, s in zip(input.shape[1:], input.stride()[1:])) < 2 ** 31):
+        # fast path: one compile-time order, the input read in place through its strides (channels-last views too)
+        inp = input.to(dt)
+        # the memory format of the result follows the input: a channels-last view in, a channels-last view out
+        chlast = Cn > 1 and inp.stride(1) == 1
+        if order[0] == 3 and Cn in (2, 3, 4) and not chlast:
+            # 64 taps per point: one transposition to channels-last turns C scalar gathers per tap into one vector load
+            inp = inp.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+        g = grid.to(dt).reshape(B, P, dim).contiguous()
+        if chlast:
+            out = torch.empty((B, *oshape, Cn), dtype=dt, device=inp.device).permute(0, 4, 1, 2, 3)
+        else:
+            out = torch.empty((B, Cn, *oshape), dtype=dt, device=inp.device)
+        _lib.check(_lib.lib().bfm_interpol_pull_fast(
+            inp.data_ptr(), (C.c_int64 * 5)(*inp.stride()), g.data_ptr(), P * 3, out.data_ptr(), int(chlast),
+            (C.c_int * 3)(*ishape), order[0], (C.c_int * 3)(*bound), extrapolate, B, Cn, P, _stream()))
+        return out
     inp = input.to(dt).contiguous()
     g = _grid3(grid.to(dt).reshape(B, P, dim))
     if mode == 0:
@@ -312,6 +331,13 @@ def add_identity_grid_(disp):
 
 def add_identity_grid(disp):
     """Adds the identity grid to a displacement field (api.py:507-521)."""
+    if disp.is_cuda and disp.dtype == torch.float32 and disp.shape[-1] == 3 and disp.dim() >= 4 and disp.is_contiguous():
+        out = torch.empty_like(disp)
+        X, Y, Z = disp.shape[-4:-1]
+        Bn = int(math.prod(disp.shape[:-4]))
+        if Bn > 0 and disp.numel() > 0:
+            _lib.check(_lib.lib().bfm_add_identity_grid(disp.data_ptr(), out.data_ptr(), Bn, X, Y, Z, _stream()))
+        return out
     return add_identity_grid_(disp.clone())
 
 

@@ -349,6 +349,20 @@ int bfm_interpol(int mode, int is_double, const void *inp, const void *grid, voi
                  const int *order, const int *bound, int extrapolate, int iso, int B, int C, int Bi, int Bg,
                  int64_t P, void *stream);
 
+/* grid_pull fast path: float32, the same spline order (1 = linear, 3 = cubic) on all three axes.
+ * inp is addressed through element strides istride[5] = (batch, channel, x, y, z) -- a channels-last view (e.g. a
+ * permuted displacement field) is read in place; a zero batch stride broadcasts.  grid (B or 1, P, 3) with batch
+ * stride grid_bstride elements; out (B, C, P) contiguous, or (B, P, C) when out_chlast != 0.  Same node indices, bound signs and spline weights as
+ * bfm_interpol (utils/interpol/nd.py:81-150); per tap the three weights are multiplied first.  One batch element
+ * of the input must span fewer than 2^31 elements. */
+int bfm_interpol_pull_fast(const float *inp, const int64_t *istride, const float *grid, int64_t grid_bstride,
+                           float *out, int out_chlast, const int *ishape, int order, const int *bound, int extrapolate,
+                           int B, int C, int64_t P, void *stream);
+
+/* add_identity_grid for 3-D float32 fields: out = disp + voxel index, (B, X, Y, Z, 3) contiguous
+ * utils/interpol/api.py:480-521 */
+int bfm_add_identity_grid(const float *disp, float *out, int B, int X, int Y, int Z, void *stream);
+
 /* spline_coeff: in-place recursive prefilter along one axis of a tensor viewed as (outer, n, inner)
  * utils/interpol/coeff.py:35-316.  bound: 0 zero (=dct1), 1 replicate (=dct2), 2 dct1, 3 dct2, 6 dft. */
 int bfm_spline_filter(void *data, int is_double, int64_t outer, int n, int64_t inner, int bound,
