@@ -8,6 +8,7 @@ the reference's non-textbook clamp / forced-accept logic (dopri5.py:152-169, SUR
 integer parity checks on control flow."""
 import ctypes as C
 
+import numpy as np
 import torch
 
 from ... import _lib
@@ -50,9 +51,12 @@ def _combine(y0, ks, coefs, out_dtype=None):
 
 
 def _scaled(dt, coefs, dtype):
-    """float32 value of (dt * c) as the reference forms it: dt is a 0-dim tensor of the state dtype."""
-    d = torch.tensor(float(dt), dtype=dtype)
-    return [float((d * c).to(torch.float32)) for c in coefs]
+    """float32 value of (dt * c) as the reference forms it: dt is a 0-dim tensor of the state dtype, c a python
+    float (cast to that dtype), the product rounded in that dtype and then to float32 -- evaluated with numpy
+    scalars (same IEEE operations, no tensor construction per coefficient)."""
+    T = np.float64 if dtype == torch.float64 else np.float32
+    d = T(float(dt))
+    return [float(np.float32(d * T(c))) for c in coefs]
 
 
 def _rms(x):
@@ -102,11 +106,18 @@ class Dopri5Solver(_Base):
             yi = _combine(y0, ks, _scaled(dt_state, beta, y0.dtype))
             ks.append(self.f(t0 + alpha * dt_state, yi))
         y1 = yi
-        err = _combine(None, ks, _scaled(dt_state, _C_ERROR, y0.dtype))
-        acc = torch.zeros(1, dtype=torch.float64, device=y0.device)
-        _lib.check(_lib.lib().bfm_rk_error_sum(err.data_ptr(), y0.data_ptr(), y1.data_ptr(),
-                                               1 if y0.dtype == torch.float64 else 0, y0.numel(), float(self.rtol),
-                                               float(self.atol), acc.data_ptr(), stream()))
+        # error estimate (float32 sum of the stages) and its scaled square sum in one pass; err is never stored
+        n = y0.numel()
+        kp = (C.c_void_p * len(ks))(*[k.data_ptr() for k in ks])
+        cf = (C.c_float * len(ks))(*_scaled(dt_state, _C_ERROR, y0.dtype))
+        acc = torch.empty(1, dtype=torch.float64, device=y0.device)
+        aligned = n % 4 == 0 and all(k.data_ptr() % 16 == 0 for k in ks) and y0.data_ptr() % 16 == 0 \
+            and y1.data_ptr() % 16 == 0
+        scratch = None if aligned else torch.empty(n, dtype=torch.float32, device=y0.device)
+        _lib.check(_lib.lib().bfm_rk_error_fused(kp, cf, len(ks), y0.data_ptr(), y1.data_ptr(),
+                                                 1 if y0.dtype == torch.float64 else 0, n, float(self.rtol),
+                                                 float(self.atol), None if scratch is None else scratch.data_ptr(),
+                                                 acc.data_ptr(), stream()))
         ratio = float(acc.item()) / y0.numel()      # the one device->host read of the step
         return y1, ks, ratio, dt_state
 

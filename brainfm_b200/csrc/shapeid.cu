@@ -180,6 +180,131 @@ __global__ void k_rk_error_sum(const float *__restrict__ err, const T *__restric
     }
 }
 
+
+// ---- vectorised variants (4 consecutive elements per thread, every stage load issued before the arithmetic) ----
+template <int NT>
+__device__ __forceinline__ void rk_sum4(const RkArgs &a, int64_t p, float acc[4]) {
+    float4 kv[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) kv[j] = __ldg((const float4 *)(a.k[j] + p));
+    acc[0] = __fmul_rn(a.coef[0], kv[0].x); acc[1] = __fmul_rn(a.coef[0], kv[0].y);
+    acc[2] = __fmul_rn(a.coef[0], kv[0].z); acc[3] = __fmul_rn(a.coef[0], kv[0].w);
+#pragma unroll
+    for (int j = 1; j < NT; ++j) {
+        acc[0] = __fadd_rn(acc[0], __fmul_rn(a.coef[j], kv[j].x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(a.coef[j], kv[j].y));
+        acc[2] = __fadd_rn(acc[2], __fmul_rn(a.coef[j], kv[j].z)); acc[3] = __fadd_rn(acc[3], __fmul_rn(a.coef[j], kv[j].w));
+    }
+}
+template <typename T>
+__device__ __forceinline__ void load4(const T *p, T v[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float *p, float v[4]) {
+    const float4 t = __ldg((const float4 *)p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<double>(const double *p, double v[4]) {
+    const double2 a = __ldg((const double2 *)p), b = __ldg((const double2 *)(p + 2));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float *p, const float v[4]) { *(float4 *)p = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store4(double *p, const double v[4]) {
+    *(double2 *)p = make_double2(v[0], v[1]);
+    *(double2 *)(p + 2) = make_double2(v[2], v[3]);
+}
+
+template <typename T, int NT, bool HAS_Y0>
+__global__ void __launch_bounds__(256) k_rk_combine4(const T *__restrict__ y0, const RkArgs a, int64_t n4,
+                                                     T *__restrict__ out) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n4) return;
+    const int64_t p = 4 * q;
+    float acc[4];
+    rk_sum4<NT>(a, p, acc);
+    T r[4];
+    if (HAS_Y0) {
+        T y[4];
+        load4<T>(y0 + p, y);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = y[e] + (T)acc[e];
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = (T)acc[e];
+    }
+    store4(out + p, r);
+}
+
+// error estimate and its scaled square sum in one pass: err = sum_j coef[j]*k_j is never written
+// (_runge_kutta_step rk_common.py:50-52 + _compute_error_ratio misc.py:146-157)
+template <typename T, int NT>
+__global__ void __launch_bounds__(256) k_rk_error4(const RkArgs a, const T *__restrict__ y0, const T *__restrict__ y1,
+                                                   int64_t n4, double rtol, double atol, double *__restrict__ result) {
+    __shared__ double red[8];
+    double s = 0.0;
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q < n4) {
+        const int64_t p = 4 * q;
+        float acc[4];
+        rk_sum4<NT>(a, p, acc);
+        T u[4], v[4];
+        load4<T>(y0 + p, u);
+        load4<T>(y1 + p, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const T tol = (T)atol + (T)rtol * max(abs(u[e]), abs(v[e]));
+            const T r = (T)acc[e] / tol;
+            s += (double)(r * r);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        atomicAdd(result, s);
+    }
+}
+
+// advection right-hand side, one block per (x plane, chunk of the plane): 32-bit index arithmetic
+template <typename T>
+__global__ void __launch_bounds__(256) k_advect_rhs_p(const T *__restrict__ C, const float *__restrict__ Vx,
+                                                      const float *__restrict__ Vy, const float *__restrict__ Vz, int n0,
+                                                      int n1, int n2, int neumann, float sp0, float sp1, float sp2,
+                                                      float *__restrict__ out) {
+    const int i = blockIdx.y;
+    const int plane = n1 * n2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= plane) return;
+    const int j = q / n2, k = q - j * n2;
+    const int lo = neumann ? 1 : 0;
+    const int hi0 = neumann ? n0 - 2 : n0 - 1, hi1 = neumann ? n1 - 2 : n1 - 1, hi2 = neumann ? n2 - 2 : n2 - 1;
+    auto cl = [&](int v, int hi) { return neumann ? min(max(v, lo), hi) : v; };
+    // clamped coordinates of the centre and of the six neighbours (set_BC: replicate-padded interior)
+    const int ic = cl(i, hi0), jc = cl(j, hi1), kc = cl(k, hi2);
+    const int64_t s0 = plane;
+    auto at = [&](int a, int b, int c) -> T { return __ldg(C + (int64_t)a * s0 + b * n2 + c); };
+    const T c0 = at(ic, jc, kc);
+    const int64_t p = (int64_t)i * s0 + q;
+    const float vx = __ldg(Vx + p), vy = __ldg(Vy + p), vz = __ldg(Vz + p);
+    // forward difference at the last index falls back to the backward one and vice versa (gradient_f / gradient_b)
+    float dx, dy, dz;
+    {
+        const bool fwd = (vx > 0.f) ? (i == 0) : (i != n0 - 1);
+        dx = fwd ? (float)(at(cl(i + 1, hi0), jc, kc) - c0) : (float)(c0 - at(cl(i - 1, hi0), jc, kc));
+    }
+    {
+        const bool fwd = (vy > 0.f) ? (j == 0) : (j != n1 - 1);
+        dy = fwd ? (float)(at(ic, cl(j + 1, hi1), kc) - c0) : (float)(c0 - at(ic, cl(j - 1, hi1), kc));
+    }
+    {
+        const bool fwd = (vz > 0.f) ? (k == 0) : (k != n2 - 1);
+        dz = fwd ? (float)(at(ic, jc, cl(k + 1, hi2)) - c0) : (float)(c0 - at(ic, jc, cl(k - 1, hi2)));
+    }
+    const float cx = __fdiv_rn(dx, sp0), cy = __fdiv_rn(dy, sp1), cz = __fdiv_rn(dz, sp2);
+    out[p] = -__fadd_rn(__fadd_rn(__fmul_rn(vx, cx), __fmul_rn(vy, cy)), __fmul_rn(vz, cz));
+}
+
 static inline unsigned g1d(int64_t n) {
     int64_t g = (n + 255) / 256;
     const int64_t cap = 148LL * 16;
@@ -239,6 +364,13 @@ int bfm_advect_rhs(const void *C, int is_double, const float *Vx, const float *V
     BFM_REQUIRE(shape[0] > 2 && shape[1] > 2 && shape[2] > 2, "bfm_advect_rhs: every axis needs at least 3 samples");
     const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
     cudaStream_t s = (cudaStream_t)stream;
+    const int64_t plane = (int64_t)shape[1] * shape[2];
+    if (plane < (1LL << 30) && shape[0] <= 65535) {
+        const dim3 grid((unsigned)((plane + 255) / 256), (unsigned)shape[0]);
+        if (is_double) k_advect_rhs_p<double><<<grid, 256, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
+        else k_advect_rhs_p<float><<<grid, 256, 0, s>>>((const float *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
+        return check_launch("bfm_advect_rhs");
+    }
     if (is_double) k_advect_rhs<double><<<g1d(n), 256, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
     else k_advect_rhs<float><<<g1d(n), 256, 0, s>>>((const float *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
     return check_launch("bfm_advect_rhs");
@@ -256,6 +388,24 @@ int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, co
         if (j < n_terms && !k_host[j]) return fail(BFM_E_INVALID, "%s", "bfm_rk_combine: null stage");
     }
     cudaStream_t s = (cudaStream_t)stream;
+    if (y0) {
+        BFM_REQUIRE((is_double != 0) == (out_is_double != 0), "bfm_rk_combine: state and output precision must agree");
+    }
+    bool vec = (n % 4) == 0 && ((uintptr_t)out % 16) == 0 && (!y0 || ((uintptr_t)y0 % 16) == 0);
+    for (int j = 0; j < n_terms; ++j) vec = vec && ((uintptr_t)k_host[j] % 16) == 0;
+    if (vec && !(y0 == nullptr && out_is_double)) {
+        const int64_t n4 = n / 4;
+        const unsigned g = (unsigned)((n4 + 255) / 256);
+#define BFM_RK(NT)                                                                                                   \
+    case NT:                                                                                                         \
+        if (!y0) k_rk_combine4<float, NT, false><<<g, 256, 0, s>>>(nullptr, a, n4, (float *)out);                    \
+        else if (is_double) k_rk_combine4<double, NT, true><<<g, 256, 0, s>>>((const double *)y0, a, n4, (double *)out); \
+        else k_rk_combine4<float, NT, true><<<g, 256, 0, s>>>((const float *)y0, a, n4, (float *)out);               \
+        break;
+        switch (n_terms) { BFM_RK(1) BFM_RK(2) BFM_RK(3) BFM_RK(4) BFM_RK(5) BFM_RK(6) BFM_RK(7) BFM_RK(8) }
+#undef BFM_RK
+        return check_launch("bfm_rk_combine");
+    }
     if (!y0) {
         BFM_REQUIRE(!out_is_double, "bfm_rk_combine: the bare float32 sum is written as float32");
         k_rk_combine<float, float><<<g1d(n), 256, 0, s>>>(nullptr, a, n, (float *)out);
@@ -267,6 +417,40 @@ int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, co
         k_rk_combine<float, float><<<g1d(n), 256, 0, s>>>((const float *)y0, a, n, (float *)out);
     }
     return check_launch("bfm_rk_combine");
+}
+
+int bfm_rk_error_fused(const float *const *k_host, const float *coef_host, int n_terms, const void *y0, const void *y1,
+                       int is_double, int64_t n, double rtol, double atol, float *err_scratch, double *result_dev,
+                       void *stream) {
+    BFM_REQUIRE(k_host && coef_host && y0 && y1 && result_dev && n > 0, "bfm_rk_error_fused: bad argument");
+    BFM_REQUIRE(n_terms >= 1 && n_terms <= 8, "bfm_rk_error_fused: 1..8 terms");
+    RkArgs a;
+    a.n_terms = n_terms;
+    bool vec = (n % 4) == 0 && ((uintptr_t)y0 % 16) == 0 && ((uintptr_t)y1 % 16) == 0;
+    for (int j = 0; j < 8; ++j) {
+        a.k[j] = j < n_terms ? k_host[j] : nullptr;
+        a.coef[j] = j < n_terms ? coef_host[j] : 0.f;
+        if (j < n_terms && !k_host[j]) return fail(BFM_E_INVALID, "%s", "bfm_rk_error_fused: null stage");
+        if (j < n_terms) vec = vec && ((uintptr_t)k_host[j] % 16) == 0;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!vec) {                                   // unaligned / ragged: the two-kernel form through err_scratch
+        BFM_REQUIRE(err_scratch, "bfm_rk_error_fused: err_scratch needed for unaligned or ragged inputs");
+        int rc = bfm_rk_combine(nullptr, 0, k_host, coef_host, n_terms, n, err_scratch, 0, stream);
+        if (rc) return rc;
+        return bfm_rk_error_sum(err_scratch, y0, y1, is_double, n, rtol, atol, result_dev, stream);
+    }
+    cudaMemsetAsync(result_dev, 0, sizeof(double), s);
+    const int64_t n4 = n / 4;
+    const unsigned g = (unsigned)((n4 + 255) / 256);
+#define BFM_RE(NT)                                                                                                  \
+    case NT:                                                                                                        \
+        if (is_double) k_rk_error4<double, NT><<<g, 256, 0, s>>>(a, (const double *)y0, (const double *)y1, n4, rtol, atol, result_dev); \
+        else k_rk_error4<float, NT><<<g, 256, 0, s>>>(a, (const float *)y0, (const float *)y1, n4, rtol, atol, result_dev); \
+        break;
+    switch (n_terms) { BFM_RE(1) BFM_RE(2) BFM_RE(3) BFM_RE(4) BFM_RE(5) BFM_RE(6) BFM_RE(7) BFM_RE(8) }
+#undef BFM_RE
+    return check_launch("bfm_rk_error_fused");
 }
 
 int bfm_rk_error_sum(const float *err, const void *y0, const void *y1, int is_double, int64_t n, double rtol,

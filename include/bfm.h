@@ -397,6 +397,13 @@ int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, co
 int bfm_rk_error_sum(const float *err, const void *y0, const void *y1, int is_double, int64_t n, double rtol,
                      double atol, double *result_dev, void *stream);
 
+/* bfm_rk_combine(NULL, ...) + bfm_rk_error_sum in one pass: the error estimate err = sum_j coef[j]*k[j] is formed in
+ * registers and never written.  err_scratch (n floats) is only used when the inputs are not 16-byte aligned or n is
+ * not a multiple of 4 (two-kernel form); may be NULL otherwise. */
+int bfm_rk_error_fused(const float *const *k_host, const float *coef_host, int n_terms, const void *y0, const void *y1,
+                       int is_double, int64_t n, double rtol, double atol, float *err_scratch, double *result_dev,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

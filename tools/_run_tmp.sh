@@ -1,2 +1,2 @@
-python -m pytest tests/test_interpol_gpu.py -x -q 2>&1 | tail -15
-python tools/config_bench.py interpol 2>&1 | tail -3
+python -m pytest tests/test_shapeid_gpu.py -x -q 2>&1 | tail -8
+python tools/shapeid_profile.py 2>&1 | head -12
