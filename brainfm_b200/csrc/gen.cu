@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sampl
 // One banded pass.  Axis 0/1: a thread owns VEC consecutive z outputs (128-bit loads when VEC == 4); the tap
 // weight is uniform across the warp.  Axis 2: a thread owns one output, taps are contiguous.
 template <int VEC>
-__global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restrict__ S, int pass) {
+__global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restrict__ S, int pass, int zk_cap) {
     // persistent blocks: a few hundred per sample, each thread walks its outputs with carry arithmetic; only
     // the descriptor fields this pass needs are read (no 936-byte staging per block)
     const bfm_gen_sample &s = S[blockIdx.y];
@@ -680,8 +680,10 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
     const bfm_band &b = s.band[pass];
     const int axis = b.axis, T = b.T;
     const int o0 = axis == 0 ? b.n_out : sh0, o1 = axis == 1 ? b.n_out : sh1, o2 = axis == 2 ? b.n_out : sh2;
-    if (VEC == 4 && (axis == 2 || (sh2 & 3))) return;        // handled by the scalar instantiation
+    if (VEC == 4 && (axis == 2 || (sh2 & 3))) return;        // handled by the scalar instantiation / k_gen_band_z
     if (VEC == 1 && !(axis == 2 || (sh2 & 3))) return;
+    if (VEC == 1 && axis == 2 && zk_cap > 0 &&
+        ((b.n_out * ((T | 1) + 1) + 8 * (sh2 + b.n_out + 4)) * 4 <= zk_cap)) return;   // k_gen_band_z takes it
     const bool last = (pass == n_band - 1);
     const float *__restrict__ in = pass == 0 ? s.i_bf : s.tmp[(pass - 1) & 1];
     float *__restrict__ out = last ? s.lowres : s.tmp[pass & 1];
@@ -747,6 +749,106 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
         kv += dk; j += dj; i += di;
         if (kv >= o2v) { kv -= o2v; ++j; }
         if (j >= o1) { j -= o1; ++i; }
+    }
+}
+
+
+// Axis-2 (z, contiguous) banded pass.  A warp owns one input row at a time: the row is staged in shared memory with
+// coalesced loads, the band table of the pass (starts + weights, odd pitch => conflict-free) is staged once per
+// persistent block, lane l computes outputs l, l+32, ... from shared memory.  Same tap order and the same
+// counter-based noise mapping (group = output index >> 2) as k_gen_band<1>: results are bit-identical to it.
+__global__ void __launch_bounds__(256) k_gen_band_z(const bfm_gen_sample *__restrict__ S, int pass, int smem_cap) {
+    extern __shared__ float zsm[];
+    const bfm_gen_sample &s = S[blockIdx.y];
+    const int n_band = s.n_band;
+    if (pass >= n_band) return;
+    const bfm_band &b = s.band[pass];
+    if (b.axis != 2) return;
+    int sh0 = s.d.size[0], sh1 = s.d.size[1], sh2 = s.d.size[2];
+    for (int q = 0; q < pass; ++q) {
+        const int ax = s.band[q].axis, no = s.band[q].n_out;
+        if (ax == 0) sh0 = no; else if (ax == 1) sh1 = no; else sh2 = no;
+    }
+    const int T = b.T, Tp = T | 1, n_out = b.n_out, n_in = sh2;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // shared layout: weights [n_out][Tp] | starts [n_out] | per warp: row [n_in] + noise [n_out + 4]
+    float *wsm = zsm;
+    int *ssm = (int *)(wsm + n_out * Tp);
+    float *rows = (float *)(ssm + n_out);
+    const int per_warp = n_in + n_out + 4;
+    if ((n_out * (Tp + 1) + nwarps * per_warp) * 4 > smem_cap) return;      // the host routes this sample to k_gen_band<1>
+    const bool last = (pass == n_band - 1);
+    const float *__restrict__ in = pass == 0 ? s.i_bf : s.tmp[(pass - 1) & 1];
+    float *__restrict__ out = last ? s.lowres : s.tmp[pass & 1];
+    for (int q = threadIdx.x; q < n_out * T; q += blockDim.x) {
+        const int o = q / T, t = q - o * T;
+        wsm[o * Tp + t] = __ldg(b.w + q);
+    }
+    for (int q = threadIdx.x; q < n_out; q += blockDim.x) ssm[q] = __ldg(b.start + q);
+    __syncthreads();
+    float *row = rows + warp * per_warp, *nz = row + n_in;
+    const int zf0 = s.zero_first[0], zf1 = s.zero_first[1], zf2 = s.zero_first[2];
+    const float nstd = s.noise_std;
+    const float *__restrict__ eps = s.eps_noise;
+    const uint64_t seed = s.seed;
+    const int n_rows = sh0 * sh1;
+    // the next row of this warp travels in registers while the current one is being consumed from shared memory
+    constexpr int kPre = 8;                                  // rows up to 32 * kPre floats are prefetched
+    const bool prefetch = n_in <= 32 * kPre;
+    float pre[kPre];
+    const int rstep = gridDim.x * nwarps;
+    auto fetch = [&](int r) {
+        const float *__restrict__ src = in + (size_t)r * n_in;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            const int q = lane + 32 * u;
+            pre[u] = (r < n_rows && q < n_in) ? __ldg(src + q) : 0.f;
+        }
+    };
+    const int r_first = blockIdx.x * nwarps + warp;
+    if (prefetch) fetch(r_first);
+    for (int r = r_first; r < n_rows; r += rstep) {
+        if (prefetch) {
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                const int q = lane + 32 * u;
+                if (q < n_in) row[q] = pre[u];
+            }
+            fetch(r + rstep);
+        } else {
+            const float *__restrict__ src = in + (size_t)r * n_in;
+            for (int q = lane; q < n_in; q += 32) row[q] = __ldg(src + q);
+        }
+        const int op0 = r * n_out;
+        if (last && !eps) {                      // noise of outputs [op0, op0 + n_out): Philox groups of four
+            const int g0 = op0 >> 2, g1 = (op0 + n_out - 1) >> 2;
+            for (int g = g0 + lane; g <= g1; g += 32) {
+                const float4 e = philox_normal4(seed, 1u, (uint64_t)g);
+                const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int o = 4 * g + c - op0;
+                    if (o >= 0 && o < n_out) nz[o] = ev[c];
+                }
+            }
+        }
+        __syncwarp();
+        const int i = r / sh1, j = r - i * sh1;
+        for (int k = lane; k < n_out; k += 32) {
+            const int st = ssm[k];
+            const int t0 = max(0, -st), t1 = min(T, n_in - st);
+            const float *wr = wsm + k * Tp, *x = row + st;
+            float acc = 0.f;
+            for (int t = t0; t < t1; ++t) acc = fmaf(wr[t], x[t], acc);
+            if (last) {
+                if ((zf0 && i == 0) || (zf1 && j == 0) || (zf2 && k == 0)) acc = 0.f;
+                const float e = eps ? __ldg(eps + op0 + k) : nz[k];
+                acc = __fadd_rn(acc, __fmul_rn(nstd, e));                 // utils.py:635-636
+                acc = acc < 0.f ? 0.f : acc;
+            }
+            out[op0 + k] = acc;
+        }
+        __syncwarp();
     }
 }
 
@@ -1067,26 +1169,48 @@ int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, vo
     for (int b = 0; b < B; ++b) maxp = h[b].n_band > maxp ? h[b].n_band : maxp;
     // persistent blocks: ~16 per SM over the whole batch
     const int64_t band_blocks = max((int64_t)8, (int64_t)(16 * 148 + B - 1) / B);
+    const int zk_cap = 96 * 1024;          // shared memory of k_gen_band_z (2 blocks per SM)
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_gen_band_z, cudaFuncAttributeMaxDynamicSharedMemorySize, zk_cap);
+        attr_done = true;
+    }
     for (int pass = 0; pass < maxp; ++pass) {
-        int64_t most4 = 0, most1 = 0;
+        int64_t most4 = 0, most1 = 0, rows_z = 0;
+        int smem_z = 0;
         for (int b = 0; b < B; ++b) {
             if (pass >= h[b].n_band) continue;
             int sh[3] = {h[b].d.size[0], h[b].d.size[1], h[b].d.size[2]};
             for (int q = 0; q < pass; ++q) sh[h[b].band[q].axis] = h[b].band[q].n_out;
-            const int axis = h[b].band[pass].axis;
+            const bfm_band &bd = h[b].band[pass];
+            const int axis = bd.axis;
             const bool scalar = axis == 2 || (sh[2] & 3);
-            sh[axis] = h[b].band[pass].n_out;
+            const int need_z = (bd.n_out * ((bd.T | 1) + 1) + 8 * (sh[2] + bd.n_out + 4)) * 4;
+            if (axis == 2 && need_z <= zk_cap) {
+                rows_z = max(rows_z, (int64_t)sh[0] * sh[1]);
+                smem_z = max(smem_z, need_z);
+                continue;
+            }
+            sh[axis] = bd.n_out;
             const int64_t n = (int64_t)sh[0] * sh[1] * sh[2];
             if (scalar) most1 = n > most1 ? n : most1;
             else most4 = n / 4 > most4 ? n / 4 : most4;
         }
         if (most4 > 0) {
-            k_gen_band<4><<<dim3((unsigned)min((most4 + 255) / 256, band_blocks), B), 256, 0, (cudaStream_t)stream>>>(d, pass);
+            k_gen_band<4><<<dim3((unsigned)min((most4 + 255) / 256, band_blocks), B), 256, 0, (cudaStream_t)stream>>>(d, pass, zk_cap);
             int rc2 = check_launch("bfm_gen_resample");
             if (rc2) return rc2;
         }
         if (most1 > 0) {
-            k_gen_band<1><<<dim3((unsigned)min((most1 + 255) / 256, band_blocks), B), 256, 0, (cudaStream_t)stream>>>(d, pass);
+            k_gen_band<1><<<dim3((unsigned)min((most1 + 255) / 256, band_blocks), B), 256, 0, (cudaStream_t)stream>>>(d, pass, zk_cap);
+            int rc2 = check_launch("bfm_gen_resample");
+            if (rc2) return rc2;
+        }
+        if (rows_z > 0) {
+            // persistent blocks: as many per SM as the shared memory allows (at most 8 = full occupancy)
+            const int per_sm = (int)max((int64_t)1, min((int64_t)8, (int64_t)(200 * 1024) / max(smem_z, 1)));
+            const int64_t zb = max((int64_t)4, (int64_t)(per_sm * 148 + B - 1) / B);
+            k_gen_band_z<<<dim3((unsigned)min((rows_z + 7) / 8, zb), B), 256, smem_z, (cudaStream_t)stream>>>(d, pass, zk_cap);
             int rc2 = check_launch("bfm_gen_resample");
             if (rc2) return rc2;
         }
