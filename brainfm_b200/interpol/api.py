@@ -1,7 +1,9 @@
 """High-level resampling API (mirror of utils/interpol/api.py, resize.py, restrict.py) over libbfm.
 
-Forward semantics only (the generator calls these under no_grad); float32 and float64; 1-D, 2-D and 3-D
-(lower dimensions run through the 3-D kernel with singleton axes).  Input layout as in the reference:
+float32 and float64; 1-D, 2-D and 3-D (lower dimensions run through the 3-D kernel with singleton axes).
+Differentiable like the reference (utils/interpol/autograd.py:125-301): grid_pull / grid_push / grid_count /
+spline_coeff(_nd) carry autograd Functions whose backward passes are the adjoint kernels (pull <-> push, grid
+gradients through the grid_grad kernel); grid_grad itself is forward-only.  Input layout as in the reference:
 input (..., [channel], *spatial) channels-first, grid (..., *spatial_out, dim) in voxel coordinates."""
 import ctypes as C
 import math
@@ -183,6 +185,90 @@ def _pull_raw(input, grid, order, bound, extrapolate, mode=0):
     return out
 
 
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class _Pull(torch.autograd.Function):
+    """grid_pull with its adjoints (utils/interpol/autograd.py:125-155, pushpull.py grid_pull_backward):
+    d/d input = push of the incoming gradient, d/d grid = sum_c grad_c * (spatial gradient of input_c at grid)."""
+
+    @staticmethod
+    def forward(ctx, input, grid, order, bound, ext):
+        ctx.opt = (order, bound, ext)
+        ctx.save_for_backward(input, grid)
+        return _pull_raw(input, grid, order, bound, ext)
+
+    @staticmethod
+    def backward(ctx, grad):
+        input, grid = ctx.saved_tensors
+        order, bound, ext = ctx.opt
+        gi = gg = None
+        grad = grad.contiguous()
+        if ctx.needs_input_grad[0]:
+            gi = _push_raw(grad, grid, list(input.shape[2:]), order, bound, ext).to(input.dtype)
+        if ctx.needs_input_grad[1]:
+            g3 = _pull_raw(input, grid, order, bound, ext, mode=2)             # (B, C, *out, dim)
+            gg = (g3 * grad.unsqueeze(-1)).sum(1).to(grid.dtype)
+        return gi, gg, None, None, None
+
+
+class _Push(torch.autograd.Function):
+    """grid_push (autograd.py:158-188): d/d input = pull of the incoming gradient, d/d grid = sum_c input_c *
+    (spatial gradient of grad_c at grid)."""
+
+    @staticmethod
+    def forward(ctx, input, grid, shape, order, bound, ext):
+        ctx.opt = (order, bound, ext)
+        ctx.save_for_backward(input, grid)
+        return _push_raw(input, grid, list(shape), order, bound, ext)
+
+    @staticmethod
+    def backward(ctx, grad):
+        input, grid = ctx.saved_tensors
+        order, bound, ext = ctx.opt
+        gi = gg = None
+        grad = grad.contiguous()
+        if ctx.needs_input_grad[0]:
+            gi = _pull_raw(grad, grid, order, bound, ext).to(input.dtype)
+        if ctx.needs_input_grad[1]:
+            g3 = _pull_raw(grad, grid, order, bound, ext, mode=2)
+            gg = (g3 * input.unsqueeze(-1)).sum(1).to(grid.dtype)
+        return gi, gg, None, None, None, None
+
+
+class _Count(torch.autograd.Function):
+    """grid_count = push of ones (autograd.py:191-219)."""
+
+    @staticmethod
+    def forward(ctx, grid, shape, order, bound, ext):
+        ctx.opt = (order, bound, ext)
+        ctx.save_for_backward(grid)
+        return _push_raw(None, grid, list(shape), order, bound, ext)
+
+    @staticmethod
+    def backward(ctx, grad):
+        grid, = ctx.saved_tensors
+        order, bound, ext = ctx.opt
+        gg = None
+        if ctx.needs_input_grad[0]:
+            gg = _pull_raw(grad.contiguous(), grid, order, bound, ext, mode=2).sum(1).to(grid.dtype)
+        return gg, None, None, None, None
+
+
+class _Coeff(torch.autograd.Function):
+    """spline_coeff / spline_coeff_nd: the prefilter is symmetric, backward == forward (autograd.py:254-301)."""
+
+    @staticmethod
+    def forward(ctx, input, fn, args):
+        ctx.fn, ctx.args = fn, args
+        return fn(input, *args, inplace=False)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.fn(grad.contiguous(), *ctx.args, inplace=False), None, None
+
+
 def grid_pull(input, grid, interpolation='linear', bound='zero', extrapolate=False, prefilter=False):
     """Sample an image with respect to a deformation field (utils/interpol/api.py:137-200)."""
     _need(grid, 'grid')
@@ -204,7 +290,10 @@ def grid_pull(input, grid, interpolation='linear', bound='zero', extrapolate=Fal
         _need(input, 'input')
         if prefilter:
             input = spline_coeff_nd(input, interpolation=interpolation, bound=bound, dim=dim)
-        out = _pull_raw(input, grid, order, bnd, ext)
+        if _wants_grad(input, grid):
+            out = _Pull.apply(input, grid, order, bnd, ext)
+        else:
+            out = _pull_raw(input, grid, order, bnd, ext)
     return _postproc(out, info, 'pull')
 
 
@@ -212,6 +301,9 @@ def grid_grad(input, grid, interpolation='linear', bound='zero', extrapolate=Fal
     """Sample spatial gradients of an image (utils/interpol/api.py:290-332)."""
     _need(grid, 'grid')
     _need(input, 'input')
+    if _wants_grad(input, grid):
+        raise NotImplementedError("grid_grad is forward-only here (its backward needs spline Hessians); "
+                                  "detach the inputs or call it under torch.no_grad()")
     dim = grid.shape[-1]
     order, bnd, ext = _orders(interpolation, dim), _bounds(bound, dim), _extrap(extrapolate)
     grid, input, info = _preproc(grid, input)
@@ -245,9 +337,14 @@ def grid_push(input, grid, shape=None, interpolation='linear', bound='zero', ext
         shape = tuple(input.shape[2:])
     if list(input.shape[2:]) != list(grid.shape[1:-1]):
         raise ValueError('Input and grid should have the same spatial shape')
-    out = _push_raw(input, grid, list(shape), order, bnd, ext)
-    if prefilter:
-        out = spline_coeff_nd(out, interpolation=interpolation, bound=bound, dim=dim, inplace=True)
+    if _wants_grad(input, grid):
+        out = _Push.apply(input, grid, tuple(shape), order, bnd, ext)
+        if prefilter:
+            out = spline_coeff_nd(out, interpolation=interpolation, bound=bound, dim=dim)
+    else:
+        out = _push_raw(input, grid, list(shape), order, bnd, ext)
+        if prefilter:
+            out = spline_coeff_nd(out, interpolation=interpolation, bound=bound, dim=dim, inplace=True)
     return _postproc(out, info, 'push')
 
 
@@ -259,7 +356,10 @@ def grid_count(grid, shape=None, interpolation='linear', bound='zero', extrapola
     grid, info = _preproc(grid)
     if shape is None:
         shape = tuple(grid.shape[1:-1])
-    out = _push_raw(None, grid, list(shape), order, bnd, ext)
+    if _wants_grad(grid):
+        out = _Count.apply(grid, tuple(shape), order, bnd, ext)
+    else:
+        out = _push_raw(None, grid, list(shape), order, bnd, ext)
     return _postproc(out, info, 'count')
 
 
@@ -282,8 +382,16 @@ _POLES = {
 def spline_coeff(input, interpolation='linear', bound='dct2', dim=-1, inplace=False):
     """Interpolating spline coefficients along one dimension (utils/interpol/api.py:335-383, coeff.py:255-316)."""
     _need(input, 'input')
+    if _wants_grad(input):
+        return _Coeff.apply(input, _spline_coeff_nograd, (interpolation, bound, dim))
+    return _spline_coeff_nograd(input, interpolation, bound, dim, inplace)
+
+
+def _spline_coeff_nograd(input, interpolation='linear', bound='dct2', dim=-1, inplace=False):
     order = _orders(interpolation, 1)[0]
     bnd = _bounds(bound, 1)[0]
+    if input.requires_grad:
+        input = input.detach()
     out = input if (inplace and input.is_contiguous()) else input.clone(memory_format=torch.contiguous_format)
     if order in (0, 1) or out.shape[dim] == 1:
         return out
@@ -306,10 +414,18 @@ def spline_coeff_nd(input, interpolation='linear', bound='dct2', dim=None, inpla
     _need(input, 'input')
     if dim is None:
         dim = input.dim()
+    if _wants_grad(input):
+        return _Coeff.apply(input, _spline_coeff_nd_nograd, (interpolation, bound, dim))
+    return _spline_coeff_nd_nograd(input, interpolation, bound, dim, inplace)
+
+
+def _spline_coeff_nd_nograd(input, interpolation='linear', bound='dct2', dim=None, inplace=False):
+    if input.requires_grad:
+        input = input.detach()
     orders, bnds = _orders(interpolation, dim), _bounds(bound, dim)
     out = input if inplace else input.clone(memory_format=torch.contiguous_format)
     for d, (b, o) in enumerate(zip(bnds, orders)):
-        out = spline_coeff(out, o, b, dim=-dim + d, inplace=True)
+        out = _spline_coeff_nograd(out, o, b, dim=-dim + d, inplace=True)
     return out
 
 
