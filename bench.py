@@ -78,8 +78,14 @@ def peaks():
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe), sampled every 20 ms from BEFORE the warm-up
+    (nvidia-smi needs ~100 ms to come up) until the end of the run.  Every line is time-stamped on arrival;
+    `summary(t0, t1)` reports the samples that fell inside the timed region [t0, t1] and, beside them, all samples
+    taken under load (warm-up through the end-to-end arm) -- the device-resident timed region of the default
+    run lasts only ~30 ms."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -87,7 +93,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -96,22 +102,40 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=3.0):
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+
+    def _stats(self, rows):
+        rows = [r for _, r in rows if len(r) >= 6]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+    def summary(self, t0, t1, load0, load1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        timed = self._stats([r for r in self.rows if t0 <= r[0] <= t1])
+        load = self._stats([r for r in self.rows if load0 <= r[0] <= load1])
+        out = dict(timed if timed["samples"] else load)
+        out["window"] = "timed region" if timed["samples"] else "whole run under load (timed region < sampling interval)"
+        out["timed_region_samples"] = timed["samples"]
+        out["under_load"] = load
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -233,12 +257,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm ----------------
-    for _ in range(args.warmup):
-        ds.generate_batch(idxs)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        ds.generate_batch(idxs)
+    barrier()
+    if rank == 0:
+        sampler.wait_first()
+    for _ in range(args.warmup):           # nvidia-smi came up while rank 0 idled: back under load before timing
+        ds.generate_batch(idxs)
+    barrier()
+    load_t0 = time.perf_counter()
     timers = {}
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -248,10 +278,10 @@ def main():
         ds.generate_batch(idxs, timers=timers)
     e1.record()
     barrier()
-    host_s = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    host_s = t1 - t0
     launches = _lib.launch_count() - l0
     dev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     el = torch.tensor([dev_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -289,6 +319,7 @@ def main():
 
     traffic, traffic_src = ncu_traffic("k_gen_warp<1")
     if args.quick:
+        sampler.stop()
         if rank == 0:
             print(json.dumps({"quick": True, "value": value, "stage_ms_per_step": stage_ms,
                               "host_wall_ms_per_step": 1e3 * host_s / args.steps}), flush=True)
@@ -329,6 +360,11 @@ def main():
     if world > 1:
         dist.all_reduce(el2, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * BATCH / (float(el2.item()) * 1e-3)
+    load_t1 = time.perf_counter()
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t0, t1, load_t0, load_t1)
 
     # ---------------- CPU baseline (oracle port), rank 0 at N=1 only ----------------
     cpu = None

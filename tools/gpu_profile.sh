@@ -7,9 +7,10 @@
 tag=${1:-dev}
 mkdir -p gpurun_out
 python -c 'import torch' >/dev/null 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 30 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/launches_${tag}.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_gen_|k_warp_volume|k_minmax|k_shift' \
-    -s 30 -c 30 -f -o gpurun_out/full_${tag} python bench.py --steps 1 --warmup 3 --quick > gpurun_out/full_${tag}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_gen_' \
+    -s 60 -c 22 -f -o gpurun_out/full_${tag} python bench.py --steps 1 --warmup 3 --quick > gpurun_out/full_${tag}.log 2>&1
+ncu -i gpurun_out/full_${tag}.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.csv 2>/dev/null
 timeout 300 python tools/host_profile.py > gpurun_out/host_${tag}.txt 2>&1
 ls -la gpurun_out
