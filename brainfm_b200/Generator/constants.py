@@ -3,7 +3,7 @@ The site-specific dataset path table of the reference (constants.py:26-259) is o
 from .utils import (add_bias_field, add_gamma_transform, add_noise, read_and_deform_bias_field,
                     read_and_deform_CT, read_and_deform_distance, read_and_deform_image,
                     read_and_deform_pathology, read_and_deform_registration, read_and_deform_segmentation,
-                    resample_resolution)
+                    read_and_deform_surface, resample_resolution)
 
 augmentation_funcs = {
     'gamma': add_gamma_transform,
@@ -22,6 +22,7 @@ processing_funcs = {
     'bias_field': read_and_deform_bias_field,
     'registration': read_and_deform_registration,
     'pathology': read_and_deform_pathology,
+    'surface': read_and_deform_surface,
 }
 
 # frozen copies used to detect whether the stock operators are still registered (fused fast path)

@@ -410,6 +410,38 @@ def read_and_deform_registration(exist_keys, task_name, file_names, setups, defo
     return {'registration': torch.stack(reg, dim=0)}
 
 
+def read_and_deform_surface(exist_keys, task_name, file_name, setups, deform_dict, device, mask=None, size=None,
+                            **kwargs):
+    """White / pial surface vertices carried through the INVERSE deformation (Generator/utils.py:479-533):
+    V <- (V - c2) Ainv^T, V += trilerp(Fneg, V + c2), V += c2; on flip the x coordinate is mirrored and left / right
+    swap.  `deform_dict['Fneg']` is the integrated negative field ('surface' task, datasets.py:214-223).  The
+    faces are returned untouched.  Ainv is formed on the host like the reference's CPU `torch.inverse`."""
+    Fneg, A, c2 = deform_dict['Fneg'], deform_dict['A'], deform_dict['c2']
+    if Fneg is None:
+        raise ValueError("read_and_deform_surface needs deform_dict['Fneg'] (enable the 'surface' task)")
+    if size is None:
+        size = list(Fneg.shape[:3])
+    mat = bio.load_surface(file_name.split('.nii')[0] + '.mat')
+    dev = Fneg.device
+    Ainv = torch.inverse(A.detach().float().cpu()).to(dev)
+    c2 = c2.to(dev).float()
+    out = {}
+    for v, f in (('Vlw', 'Flw'), ('Vrw', 'Frw'), ('Vlp', 'Flp'), ('Vrp', 'Frp')):
+        V = torch.tensor(np.asarray(mat[v]), dtype=torch.float, device=dev)
+        V = V - c2[None, :]
+        V = V @ torch.transpose(Ainv, 0, 1)
+        V = V + fast_3D_interp_torch(Fneg, V[:, 0] + c2[0], V[:, 1] + c2[1], V[:, 2] + c2[2])
+        V = V + c2[None, :]
+        out[v] = V
+        out[f] = torch.tensor(np.asarray(mat[f]), dtype=torch.int, device=dev)
+    if setups['flip']:
+        for v in ('Vlw', 'Vrw', 'Vlp', 'Vrp'):
+            out[v][:, 0] = size[0] - 1 - out[v][:, 0]
+        for a, b in (('Vlw', 'Vrw'), ('Vlp', 'Vrp'), ('Flw', 'Frw'), ('Flp', 'Frp')):
+            out[a], out[b] = out[b], out[a]
+    return {k: out[k] for k in ('Vlw', 'Flw', 'Vrw', 'Frw', 'Vlp', 'Flp', 'Vrp', 'Frp')}
+
+
 def read_and_deform_bias_field(exist_keys, task_name, file_name, setups, deform_dict, device, mask=None, **kwargs):
     """Real bias-field target (Generator/utils.py:473-477; the reference swaps `mask` and `device`, which is
     harmless there only because mask is None)."""

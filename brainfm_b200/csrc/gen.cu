@@ -17,6 +17,8 @@
 // a warp owns several rows so per-k table entries are loaded once, element indices are 32-bit.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace bfm {
 
 constexpr float kBoxDelta = 1e-3f;   // bound on |computed - exact| source coordinate
@@ -1168,7 +1170,8 @@ int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, vo
     int maxp = 0;
     for (int b = 0; b < B; ++b) maxp = h[b].n_band > maxp ? h[b].n_band : maxp;
     // persistent blocks: ~16 per SM over the whole batch
-    const int64_t band_blocks = max((int64_t)8, (int64_t)(16 * 148 + B - 1) / B);
+    static const int bps = getenv("BFM_BAND_BLOCKS_PER_SM") ? atoi(getenv("BFM_BAND_BLOCKS_PER_SM")) : 16;
+    const int64_t band_blocks = max((int64_t)8, (int64_t)((int64_t)bps * 148 + B - 1) / B);
     const int zk_cap = 96 * 1024;          // shared memory of k_gen_band_z (2 blocks per SM)
     static bool attr_done = false;
     if (!attr_done) {

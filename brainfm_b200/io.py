@@ -31,6 +31,22 @@ def register_volume(path, array, affine=None):
     _REGISTRY[path] = Volume(np.asarray(array), affine)
 
 
+_SURFACES = {}
+
+
+def register_surface(path, arrays):
+    """In-memory stand-in for a `<case>.mat` surface file: dict with Vlw/Flw/Vrw/Frw/Vlp/Flp/Vrp/Frp."""
+    _SURFACES[path] = {k: np.asarray(v) for k, v in arrays.items()}
+
+
+def load_surface(path):
+    """The eight arrays of a surface file (scipy.io.loadmat in the reference, Generator/utils.py:483)."""
+    if path in _SURFACES:
+        return _SURFACES[path]
+    from scipy.io.matlab import loadmat
+    return loadmat(path)
+
+
 def clear_registry():
     _REGISTRY.clear()
 

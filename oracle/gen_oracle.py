@@ -99,6 +99,27 @@ def sample_trilinear(X, I, J, K, default=0.0):
     return out[..., 0] if C == 1 else out
 
 
+def surface_deform(mat, A, c2, Fneg, flip, size):
+    """read_and_deform_surface (Generator/utils.py:479-533): vertices through the inverse affine and the integrated
+    negative field; x mirrored and left / right swapped on flip; faces untouched."""
+    Ainv = torch.inverse(A)
+    out = {}
+    for v, f in (("Vlw", "Flw"), ("Vrw", "Frw"), ("Vlp", "Flp"), ("Vrp", "Frp")):
+        V = torch.tensor(np.asarray(mat[v]), dtype=torch.float)
+        V = V - c2[None, :]
+        V = V @ torch.transpose(Ainv, 0, 1)
+        V = V + sample_trilinear(Fneg, V[:, 0] + c2[0], V[:, 1] + c2[1], V[:, 2] + c2[2])
+        V = V + c2[None, :]
+        out[v] = V
+        out[f] = torch.tensor(np.asarray(mat[f]), dtype=torch.int)
+    if flip:
+        for v in ("Vlw", "Vrw", "Vlp", "Vrp"):
+            out[v][:, 0] = size[0] - 1 - out[v][:, 0]
+        for a, b in (("Vlw", "Vrw"), ("Vlp", "Vrp"), ("Flw", "Frw"), ("Flp", "Frp")):
+            out[a], out[b] = out[b], out[a]
+    return out
+
+
 def zoom_tables(n_in, factor, n_out, dtype64=False):
     """1-D coordinate / index / weight tables of the separable zoom (Generator/utils.py:205-236).
     float32 `torch.arange` by default; the float64 numpy variant is the one
@@ -462,6 +483,9 @@ class GeneratorOracle:
                 continue
             if task == "pathology":
                 T.update(self.target_pathology(setups))
+                continue
+            if task == "surface":            # registered, but never in `modalities` (datasets.py:621-631)
+                T["surface"] = 0.0
                 continue
             fn = {"CT": self.target_ct, "segmentation": self.target_segmentation,
                   "distance": self.target_distance, "registration": self.target_registration,
