@@ -75,6 +75,8 @@ class BaseGen(Dataset):
         self._info = {}                # t1 path -> modality table
         self._inputs = {}              # volume path -> (img, aff, res)
         self._c2 = {}                  # source shape -> centre (float32)
+        self._hemis = {}               # (segmentation path, registration path) -> left-hemisphere mask
+        self.hemis_mask = None
         self.write_bflog = None        # None: follow the task list; True/False: force
         self.prepare_tasks()
         self.prepare_paths()
@@ -304,9 +306,20 @@ class BaseGen(Dataset):
         return (xx2, yy2, zz2, *plan.bbox_host())
 
     def get_left_hemis_mask(self, grid):
-        if self.synth_args.left_hemis_only:
-            raise NotImplementedError("left_hemis_only is not supported")
-        self.hemis_mask = None
+        """Left-hemisphere mask (datasets.py:251-262): (lut[seg] > 0) & (MNI x < 0).  The reference evaluates it on
+        the bounding-box crop of every sample; here it is a FULL-volume uint8 device tensor computed once per
+        subject (the kernels index the full source volume, and the crop of the full mask is the crop's mask)."""
+        if not self.synth_args.left_hemis_only:
+            self.hemis_mask = None
+            return
+        key = (self.modalities['segmentation'], self.modalities['registration'][0])
+        hit = self._hemis.get(key)
+        if hit is None:
+            S = self.cache.get(key[0], 'i32')
+            X = self.cache.get(key[1], 'f32')
+            hit = ((self.lut[S.long()] > 0) & (X < 0)).to(torch.uint8)
+            self._hemis[key] = hit
+        self.hemis_mask = hit
 
     # ---- targets (datasets.py:593-631) -------------------------------------------------------------
     def read_and_deform_target(self, idx, exist_keys, task_name, input_mode, setups, deform_dict, linear_weights=None):
@@ -620,7 +633,15 @@ class BaseGen(Dataset):
         return results
 
     def _labels(self):
-        return self.cache.get(self.modalities['Gen'], 'gen')
+        lab = self.cache.get(self.modalities['Gen'], 'gen')
+        if self.hemis_mask is None:
+            return lab
+        key = ('gen_masked', self.modalities['Gen'])          # G[hemis_mask == 0] = 0 (datasets.py:367-368)
+        hit = self._hemis.get(key)
+        if hit is None:
+            hit = torch.where(self.hemis_mask != 0, lab, torch.zeros((), dtype=lab.dtype, device=lab.device))
+            self._hemis[key] = hit.contiguous()
+        return self._hemis[key]
 
     def _want_bflog(self, input_mode):
         if self.write_bflog is not None:
@@ -766,11 +787,13 @@ class BaseGen(Dataset):
         deform_dict = self.generate_deformation(setups, img.shape, arena=arena, lazy=True)
         self.get_left_hemis_mask(None)
         return dict(idx=idx, dataset_name=dataset_name, case_name=case_name, input_mode=input_mode, img=img, res=res,
-                    age=age, setups=setups, deform=deform_dict, modalities=dict(self.modalities))
+                    age=age, setups=setups, deform=deform_dict, modalities=dict(self.modalities),
+                    hemis_mask=self.hemis_mask)
 
     def _targets(self, ctx, default):
         """Per-sample target kernels (needs the bounding box on the device)."""
         self.modalities = ctx['modalities']
+        self.hemis_mask = ctx.get('hemis_mask')
         idx, input_mode, setups, deform_dict = ctx['idx'], ctx['input_mode'], ctx['setups'], ctx['deform']
         target = ctx.get('target')
         if target is None:
@@ -826,7 +849,7 @@ class BaseGen(Dataset):
 
     def _real_input(self, input_mode, setups, deform_dict, res, target):
         from .utils import read_and_deform
-        I, _ = read_and_deform(self.modalities[input_mode], torch.float, deform_dict, self.device, None)
+        I, _ = read_and_deform(self.modalities[input_mode], torch.float, deform_dict, self.device, self.hemis_mask)
         return self.augment_sample(None, I, setups, deform_dict, res, target,
                                    pathol_direction=self.get_pathology_direction(input_mode), input_mode=input_mode)
 

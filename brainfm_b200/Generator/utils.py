@@ -324,8 +324,6 @@ def read_and_deform(file_name, dtype, deform_dict, device, mask, default_value_l
                     deform_mode='linear', mean=0., scale=1., minmax_out=None):
     """Crop-read + trilinear warp of one volume (Generator/utils.py:296-321), fused into one gather kernel
     over the device-resident volume (no host crop, no H2D per sample)."""
-    if mask is not None:
-        raise NotImplementedError("left-hemisphere masks are not supported")
     if default_value_linear_mode is not None and default_value_linear_mode != 'max':
         raise ValueError('Not support default_value_linear_mode:', default_value_linear_mode)
     if deform_mode != 'linear':
@@ -336,6 +334,18 @@ def read_and_deform(file_name, dtype, deform_dict, device, mask, default_value_l
     vol = _cache(plan.device).get(file_name, 'f32')
     if list(vol.shape[:3]) != plan.src:
         raise ValueError("volume shape %s does not match the deformation's source shape %s" % (tuple(vol.shape), plan.src))
+    if mask is not None:
+        # left hemisphere only (utils.py:307-311): I -= mean; I /= scale; I[mask == 0] = 0 on a (padded) copy of the
+        # volume -- `mask` is the full-volume mask of BaseGen.get_left_hemis_mask
+        if tuple(mask.shape) != tuple(vol.shape):
+            raise ValueError("mask shape %s does not match the volume %s" % (tuple(mask.shape), tuple(vol.shape)))
+        pad = int(vol.shape[1]) * int(vol.shape[2]) + int(vol.shape[2]) + 1
+        buf = torch.zeros(vol.numel() + pad, dtype=torch.float32, device=plan.device)
+        view = buf[:vol.numel()].view(vol.shape)
+        torch.sub(vol, float(mean), out=view)
+        view.div_(float(scale))
+        view[mask == 0] = 0
+        vol, mean, scale = view, 0., 1.
     out = torch.empty(plan.size, dtype=torch.float32, device=plan.device)
     scratch = torch.empty(1, dtype=torch.float32, device=plan.device)
     _lib.check(_lib.lib().bfm_warp_volume(C.byref(plan.struct), plan.bbox_ptr, vol.data_ptr(), float(mean),
@@ -389,13 +399,18 @@ def read_and_deform_distance(exist_keys, task_name, file_names, setups, deform_d
                              **kwargs):
     """Four surface-distance maps, default = crop max, L/R swap on flip, / scaling, clamp
     (Generator/utils.py:366-392)."""
+    if mask is not None:                                   # left hemisphere only: two maps (utils.py:373-374)
+        file_names = file_names[:2]
     maps = [read_and_deform(f, torch.float, deform_dict, device, mask, default_value_linear_mode='max', mean=128.,
                             scale=20)[0] for f in file_names]
-    lp, lw, rp, rw = maps
-    if setups['flip']:
-        lp, rp = _normalise_flip(rp, True, minmax=False), _normalise_flip(lp, True, minmax=False)
-        lw, rw = _normalise_flip(rw, True, minmax=False), _normalise_flip(lw, True, minmax=False)
-    Idef = torch.stack([lp, lw, rp, rw], dim=0)
+    if mask is not None:
+        Idef = torch.stack(maps, dim=0)
+    else:
+        lp, lw, rp, rw = maps
+        if setups['flip']:
+            lp, rp = _normalise_flip(rp, True, minmax=False), _normalise_flip(lp, True, minmax=False)
+            lw, rw = _normalise_flip(rw, True, minmax=False), _normalise_flip(lw, True, minmax=False)
+        Idef = torch.stack([lp, lw, rp, rw], dim=0)
     Idef /= deform_dict['scaling_factor_distances']
     Idef = torch.clamp(Idef, min=-cfg.max_surf_distance, max=cfg.max_surf_distance)
     return {'distance': Idef}
@@ -455,10 +470,10 @@ def read_and_deform_segmentation(exist_keys, task_name, file_name, setups, defor
                                  onehotmatrix=None, lut=None, vflip=None, **kwargs):
     """Nearest-neighbour label warp -> LUT -> one-hot -> flip + L/R channel swap -> channels first
     (Generator/utils.py:394-424), one integer kernel, bit-exact."""
-    if mask is not None:
-        raise NotImplementedError("left-hemisphere masks are not supported")
     plan = _plan_of(deform_dict)
     S = _cache(plan.device).get(file_name, 'i32')
+    if mask is not None:                                   # S[mask == 0] = 0 (utils.py:400-401)
+        S = torch.where(mask != 0, S, torch.zeros((), dtype=S.dtype, device=S.device)).contiguous()
     n_classes = int(onehotmatrix.shape[0])
     if cfg is not None and cfg.generator.deform_one_hots:
         onehot = onehotmatrix[lut[S.long()]]

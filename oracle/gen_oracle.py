@@ -33,6 +33,7 @@ LABELS_BRAINSEG_EXTRACEREBRAL = [0, 11, 12, 13, 16, 31, 32, 33, 34, 35, 36, 37, 
                                  1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 14, 15, 17, 47, 49, 51, 53, 55,
                                  18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 48, 50, 52, 54, 56]
 N_NEUTRAL = 20
+LABELS_BRAINSEG_LEFT = [0, 1, 2, 3, 4, 7, 8, 9, 10, 14, 15, 17, 31, 34, 36, 38, 40, 42]       # constants.py:289
 CT_GROUPS = {
     "darker": [4, 5, 14, 15, 24, 31, 72],
     "dark": [2, 7, 16, 77, 30],
@@ -284,7 +285,9 @@ class GeneratorOracle:
         self.tasks = [k for k, v in vars(cfg.task).items() if v]
         if "bias_field" in self.tasks and "segmentation" not in self.tasks:
             self.tasks.append("segmentation")          # datasets.py:125-127
-        labels = LABELS_BRAINSEG_EXTRACEREBRAL
+        # datasets.py:165-171: the left-hemisphere label list when left_hemis_only
+        labels = LABELS_BRAINSEG_LEFT if getattr(self.g, "left_hemis_only", False) else LABELS_BRAINSEG_EXTRACEREBRAL
+        self.hemis_mask = None
         self.lut = torch.zeros(10000, dtype=torch.long)
         for i, l in enumerate(labels):
             self.lut[l] = i
@@ -377,6 +380,8 @@ class GeneratorOracle:
         I = torch.nan_to_num(self._crop(arr, (D["lo"], D["hi"])))
         I -= mean
         I /= scale
+        if self.hemis_mask is not None:                  # utils.py:310-311
+            I[self.hemis_mask == 0] = 0
         dv = torch.max(I) if default_max else 0.0
         return sample_trilinear(I, *D["rel"], default=dv)
 
@@ -395,12 +400,16 @@ class GeneratorOracle:
         return {"CT": I[None]}
 
     def target_distance(self, setups, D):
-        lp, lw, rp, rw = [self._warp(v, D, default_max=True, mean=128.0, scale=20) for v in
-                          self.vol["distance"]]
-        if setups["flip"]:
-            lp, rp = torch.flip(rp, [0]), torch.flip(lp, [0])
-            lw, rw = torch.flip(rw, [0]), torch.flip(lw, [0])
-        I = torch.stack([lp, lw, rp, rw], 0)
+        if self.hemis_mask is not None:                  # left hemisphere only: two maps (utils.py:373-374)
+            lp, lw = [self._warp(v, D, default_max=True, mean=128.0, scale=20) for v in self.vol["distance"][:2]]
+            I = torch.stack([lp, lw], 0)
+        else:
+            lp, lw, rp, rw = [self._warp(v, D, default_max=True, mean=128.0, scale=20) for v in
+                              self.vol["distance"]]
+            if setups["flip"]:
+                lp, rp = torch.flip(rp, [0]), torch.flip(lp, [0])
+                lw, rw = torch.flip(rw, [0]), torch.flip(lw, [0])
+            I = torch.stack([lp, lw, rp, rw], 0)
         I /= D["scaling_factor_distances"]
         m = self.cfg.max_surf_distance
         return {"distance": torch.clamp(I, min=-m, max=m)}
@@ -419,6 +428,8 @@ class GeneratorOracle:
 
     def target_segmentation(self, setups, D):
         S = self._crop(self.vol["segmentation"], (D["lo"], D["hi"]), dtype=torch.int32)
+        if self.hemis_mask is not None:                  # utils.py:400-401
+            S[self.hemis_mask == 0] = 0
         if self.g.deform_one_hots:
             oh = sample_trilinear(self.eye[self.lut[S.long()]], *D["rel"])
         else:
@@ -527,6 +538,8 @@ class GeneratorOracle:
         mu, sg = self.contrast(setups["photo_mode"])
         G = self._crop(self.vol["Gen"], (D["lo"], D["hi"]))
         G[G == 77] = 2
+        if self.hemis_mask is not None:                  # datasets.py:367-368
+            G[self.hemis_mask == 0] = 0
         Gr = torch.round(G).long()
         eps = torch.randn(Gr.shape, dtype=torch.float32); self.log.append(("gmm.eps", eps.clone()))
         S = mu[Gr] + sg[Gr] * eps
@@ -647,6 +660,14 @@ class GeneratorOracle:
         shp = np.asarray(self.vol["Gen"]).shape
         setups = self.setup()
         D = self.deformation(setups, shp)
+        self.hemis_mask = None
+        if getattr(self.g, "left_hemis_only", False):    # get_left_hemis_mask (datasets.py:251-262)
+            S = self._crop(self.vol["segmentation"], (D["lo"], D["hi"]), dtype=torch.int32)
+            S = self.lut[S.long()]
+            (x1, y1, z1), (x2, y2, z2) = D["lo"], D["hi"]
+            X = torch.squeeze(torch.from_numpy(np.asarray(self.vol["registration"][0])[x1:x2, y1:y2, z1:z2]
+                                               .astype(np.float64)))
+            self.hemis_mask = ((S > 0) & (X < 0)).int()
         target = self.targets(setups, D)
         if not self.brain_id:
             self._merge(self.cfg.synth_image_generator)

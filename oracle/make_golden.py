@@ -57,6 +57,10 @@ CASES = {
     "g64_brainid_s6": (64, 96, "brain", 6, {"generator.all_samples": 3, "generator.mild_samples": 1}, [],
                        "brain_id", 2),
     "g160_s0": (160, 192, "brain", 0, {}, [], "default", 4),
+    # left hemisphere only: photo mode forced, no flip, source masked by (left label) & (MNI x < 0), left label list
+    "g64_left_s9": (64, 96, "brain", 9, {"generator.left_hemis_only": True, "task.segmentation": True,
+                                         "task.distance": True, "task.registration": True},
+                    ["distance", "mni"], "default", 2),
     # pathology: random Perlin shape encoded into the synthetic image.  The reference's branch only runs when the
     # crop covers the whole output shape (datasets.py:391-398 index the deformed image with crop-shaped masks),
     # hence source shape == output shape here.
@@ -79,6 +83,12 @@ def build_volumes(src, kind, extra):
         vols["distance"] = [ti.smooth_image(shp, 0.3 * i) for i in range(4)]
     if "registration" in extra:
         vols["registration"] = [ti.smooth_image(shp, 0.7 * i) * 50 for i in range(3)]
+    if "mni" in extra:           # signed MNI-like coordinates: x < 0 on one side of a wavy mid-sagittal surface
+        ax = np.arange(src, dtype=np.float32) - (src - 1) / 2
+        base = [ax[:, None, None], ax[None, :, None], ax[None, None, :]]
+        wob = [ti.smooth_image(shp, 0.7 * i) for i in range(3)]
+        vols["registration"] = [(base[i] + 3 * (wob[i] - wob[i].mean()) / wob[i].std()).astype(np.float32)
+                                for i in range(3)]
     return vols
 
 
