@@ -98,8 +98,53 @@ def shapeid_cfg(n=192):
                       "reference_cpu_s_8_threads": 95.6 if n == 192 else None}))
 
 
+def brainid_cfg(n_items=2, steps=30):
+    """configs[4] (a): BrainIDGen stream -- one deformation and one set of targets per item, all_samples = 4
+    contrasts (2 mild + 2 severe, demo_synth.yaml:100-101) of 160^3 each; 2 items = 8 samples per step."""
+    import tempfile
+    import bench
+    from brainfm_b200 import io as bio
+    from brainfm_b200.Generator import BrainIDGen
+    dev = torch.device("cuda", 0)
+    subs = bench.make_inputs(n_items)
+    root = tempfile.mkdtemp(prefix="bfm_brainid_")
+    names = []
+    for s, v in enumerate(subs):
+        stem = os.path.join(root, "HCP.sub%02d." % s)
+        bio.register_volume(stem + "T1w.nii", v["T1"])
+        bio.register_volume(stem + "generation_labels.nii", v["Gen"])
+        names.append(stem + "T1w.nii")
+    with open(os.path.join(root, "train.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    cfg = bench.bench_cfg()
+    cfg.split_root = root
+    cfg.dataset_option = "brain_id"
+    cfg.generator.all_samples, cfg.generator.mild_samples = 4, 2
+    ds = BrainIDGen(cfg, dev)
+    ds.write_bflog = True
+    np.random.seed(7)
+    idxs = list(range(n_items))
+    for _ in range(5):
+        items = ds.generate_batch(idxs)
+    assert ds._native is not None and len(items[0][4]) == 4
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ds.generate_batch(idxs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(json.dumps({"config": "BrainIDGen stream 160^3, all_samples 4 (configs[4]a)", "items_per_step": n_items,
+                      "samples_per_step": 4 * n_items, "ms_per_step": ms,
+                      "samples_per_s": 4 * n_items / ms * 1e3, "items_per_s": n_items / ms * 1e3,
+                      "planner": "native"}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["interpol", "shapeid"]
+    which = sys.argv[1:] or ["interpol", "shapeid", "brainid"]
+    if "brainid" in which:
+        brainid_cfg()
     if "interpol" in which:
         interpol_cfg(int(os.environ.get("INTERPOL_N", "256")))
     if "shapeid" in which:
