@@ -664,6 +664,16 @@ __global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sampl
     else warp_rows<NAUX, MIX, 0>(sh, t1F, t1B, rpb);
 }
 
+
+// Undegraded resolution class (resolution == thickness == the training resolution: identity band, new_size == size):
+// the banded pass is a copy and the zoom back is the identity (weights exactly 1 and 0), so those samples take
+// k_gen_identity -- noise + clamp straight from i_bf into `out` -- instead of the band and upsample kernels.
+__host__ __device__ __forceinline__ bool is_identity_sample(const bfm_gen_sample &s) {
+    return s.n_band == 1 && s.band[0].T == 1 && s.band[0].build == 0 && s.x_count == 0 &&
+           s.new_size[0] == s.d.size[0] && s.new_size[1] == s.d.size[1] && s.new_size[2] == s.d.size[2] &&
+           ((s.d.size[1] * s.d.size[2]) & 3) == 0;
+}
+
 // ---------------------------------------------------------------------------------------------- resample
 // One banded pass.  Axis 0/1: a thread owns VEC consecutive z outputs (128-bit loads when VEC == 4); the tap
 // weight is uniform across the warp.  Axis 2: a thread owns one output, taps are contiguous.
@@ -673,7 +683,7 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
     // the descriptor fields this pass needs are read (no 936-byte staging per block)
     const bfm_gen_sample &s = S[blockIdx.y];
     const int n_band = s.n_band;
-    if (pass >= n_band) return;
+    if (pass >= n_band || is_identity_sample(s)) return;
     int sh0 = s.d.size[0], sh1 = s.d.size[1], sh2 = s.d.size[2];
     for (int q = 0; q < pass; ++q) {
         const int ax = s.band[q].axis, no = s.band[q].n_out;
@@ -763,7 +773,7 @@ __global__ void __launch_bounds__(256) k_gen_band_z(const bfm_gen_sample *__rest
     extern __shared__ float zsm[];
     const bfm_gen_sample &s = S[blockIdx.y];
     const int n_band = s.n_band;
-    if (pass >= n_band) return;
+    if (pass >= n_band || is_identity_sample(s)) return;
     const bfm_band &b = s.band[pass];
     if (b.axis != 2) return;
     int sh0 = s.d.size[0], sh1 = s.d.size[1], sh2 = s.d.size[2];
@@ -854,6 +864,52 @@ __global__ void __launch_bounds__(256) k_gen_band_z(const bfm_gen_sample *__rest
     }
 }
 
+
+// out (unnormalised, at its flipped position) = max(0, i_bf + noise_std * eps) with the strict `>0` masks, plus the
+// global maximum: what k_gen_band_z (identity band) followed by k_gen_upsample (identity zoom) produce, in one pass.
+// Same operations, same counter-based noise (group = voxel index >> 2): bit-identical to the two-kernel form.
+__global__ void __launch_bounds__(256) k_gen_identity(const bfm_gen_sample *__restrict__ S) {
+    __shared__ float red[8];
+    const bfm_gen_sample &s = S[blockIdx.z];
+    if (!is_identity_sample(s)) return;
+    const int s0 = s.d.size[0], s1 = s.d.size[1], s2 = s.d.size[2], plane = s1 * s2;
+    const int i = blockIdx.y;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    float hi = 0.f;
+    if (i < s0 && q < plane) {
+        const int io = s.flip ? s0 - 1 - i : i;
+        const int op = i * plane + q;                       // voxel index on the (low-res == training) grid
+        const float4 x = __ldg((const float4 *)(s.i_bf + op));
+        float v[4] = {x.x, x.y, x.z, x.w};
+        float e[4];
+        if (s.eps_noise) {
+            const float4 t = __ldg((const float4 *)(s.eps_noise + op));
+            e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+        } else {
+            const float4 t = philox_normal4(s.seed, 1u, (uint64_t)(op >> 2));
+            e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+        }
+        const int j = q / s2, k = q - j * s2;               // s2 % 4 == 0 is not required: recompute per element
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int jc = (q + c) / s2, kc = (q + c) - jc * s2;
+            if ((s.zero_first[0] && i == 0) || (s.zero_first[1] && jc == 0) || (s.zero_first[2] && kc == 0)) v[c] = 0.f;
+            v[c] = __fadd_rn(v[c], __fmul_rn(s.noise_std, e[c]));
+            v[c] = v[c] < 0.f ? 0.f : v[c];
+            hi = fmaxf(hi, v[c]);
+        }
+        (void)j; (void)k;
+        *(float4 *)(s.out + (size_t)io * plane + q) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) hi = fmaxf(hi, red[w]);
+        atomicMax((int *)s.maxval, __float_as_int(hi));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- finish
 // myzoom_torch(lowres, 1/factors) back to the training grid (datasets.py:337-340), in the same persistent-k
 // layout as the warp kernel: block = (i, kUR rows j), thread = k.  The first zoom pass (axis 0) of the low-res
@@ -873,6 +929,7 @@ __global__ void __launch_bounds__(256) k_gen_upsample(const bfm_gen_sample *__re
     }
     stage_desc(&sd, S + blockIdx.z);
     const bfm_gen_sample &s = sd;
+    if (is_identity_sample(s)) return;                  // k_gen_identity (resample stage) already wrote `out`
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const int s0 = s.d.size[0], s1 = s.d.size[1], s2 = s.d.size[2];
     const int ly = s.new_size[1], lz = s.new_size[2];
@@ -1178,11 +1235,26 @@ int bfm_gen_resample(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, vo
         cudaFuncSetAttribute(k_gen_band_z, cudaFuncAttributeMaxDynamicSharedMemorySize, zk_cap);
         attr_done = true;
     }
+    {
+        int64_t plane = 0;
+        int s0 = 0;
+        for (int b = 0; b < B; ++b)
+            if (is_identity_sample(h[b])) {
+                plane = max(plane, (int64_t)h[b].d.size[1] * h[b].d.size[2]);
+                s0 = max(s0, h[b].d.size[0]);
+            }
+        if (plane > 0) {
+            if (s0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_resample: grid too large");
+            k_gen_identity<<<dim3((unsigned)((plane / 4 + 255) / 256), s0, B), 256, 0, (cudaStream_t)stream>>>(d);
+            int rc2 = check_launch("bfm_gen_resample");
+            if (rc2) return rc2;
+        }
+    }
     for (int pass = 0; pass < maxp; ++pass) {
         int64_t most4 = 0, most1 = 0, rows_z = 0;
         int smem_z = 0;
         for (int b = 0; b < B; ++b) {
-            if (pass >= h[b].n_band) continue;
+            if (pass >= h[b].n_band || is_identity_sample(h[b])) continue;
             int sh[3] = {h[b].d.size[0], h[b].d.size[1], h[b].d.size[2]};
             for (int q = 0; q < pass; ++q) sh[h[b].band[q].axis] = h[b].band[q].n_out;
             const bfm_band &bd = h[b].band[pass];

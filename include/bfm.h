@@ -194,7 +194,8 @@ typedef struct bfm_gen_sample {
     int flip;
     /* resolution degradation: up to 3 banded passes, executed in the given order */
     bfm_band band[3];
-    int n_band;
+    int n_band;             /* n_band == 1 with band[0].T == 1, build == 0 and new_size == size denotes the undegraded
+                               class (identity band, identity zoom): bfm_gen_resample then writes `out` directly */
     int zero_first[3];      /* strict `>0` mask of identity axes */
     float noise_std;
     const float *eps_noise; /* injected, low-res shaped, or NULL => Philox */

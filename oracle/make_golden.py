@@ -57,6 +57,8 @@ CASES = {
     "g64_brainid_s6": (64, 96, "brain", 6, {"generator.all_samples": 3, "generator.mild_samples": 1}, [],
                        "brain_id", 2),
     "g160_s0": (160, 192, "brain", 0, {}, [], "default", 4),
+    # undegraded resolution class (identity band + identity zoom), no flip, with the super-resolution residual
+    "g64_ident_s23": (64, 96, "brain", 23, {"task.super_resolution": True}, [], "default", 2),
     # left hemisphere only: photo mode forced, no flip, source masked by (left label) & (MNI x < 0), left label list
     "g64_left_s9": (64, 96, "brain", 9, {"generator.left_hemis_only": True, "task.segmentation": True,
                                          "task.distance": True, "task.registration": True},

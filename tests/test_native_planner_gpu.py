@@ -13,7 +13,7 @@ from tests.test_gen_parity_gpu import _compare
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g160_s0"]
+CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g160_s0", "g64_ident_s23"]
 
 
 def _read(ds, ptr, n, dtype):
