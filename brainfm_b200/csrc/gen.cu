@@ -32,11 +32,19 @@ __device__ __forceinline__ void stage_desc(bfm_gen_sample *dst, const bfm_gen_sa
 }
 
 // ---------------------------------------------------------------------------------------------- bbox
+// Samples of one item (BrainIDGen: several contrasts, one deformation) share ONE bounding box: the box is computed
+// by the first of them only -- the in-place float -> int conversions of decide / finish must run exactly once.
+__device__ __forceinline__ bool bbox_follower(const bfm_gen_sample *__restrict__ S, int b) {
+    return b > 0 && S[b].bbox == S[b - 1].bbox;
+}
+
 __global__ void k_gen_bbox_init(const bfm_gen_sample *__restrict__ S) {
     int *bb = S[blockIdx.x].bbox;
-    if (threadIdx.x < 3) bb[threadIdx.x] = 0x7f7fffff;
-    else if (threadIdx.x < 6) bb[threadIdx.x] = 0;
-    else if (threadIdx.x == 6) bb[6] = 1;                   // 1 = full scan still required
+    if (!bbox_follower(S, blockIdx.x)) {
+        if (threadIdx.x < 3) bb[threadIdx.x] = 0x7f7fffff;
+        else if (threadIdx.x < 6) bb[threadIdx.x] = 0;
+        else if (threadIdx.x == 6) bb[6] = 1;               // 1 = full scan still required
+    }
     if (threadIdx.x == 7) *S[blockIdx.x].maxval = 0.f;      // chain values are >= 0 after the noise clamp
     if (threadIdx.x >= 8 && threadIdx.x < 8 + 2 * S[blockIdx.x].n_aux) {
         const int q = threadIdx.x - 8;
@@ -175,6 +183,7 @@ __device__ __forceinline__ void block_minmax_atomic(float lo[3], float hi[3], in
 
 __global__ void __launch_bounds__(256) k_gen_bbox_cand(const bfm_gen_sample *__restrict__ S) {
     __shared__ bfm_gen_sample sd;
+    if (bbox_follower(S, blockIdx.y)) return;
     stage_desc(&sd, S + blockIdx.y);
     const bfm_deform &d = sd.d;
     if (d.F_full || d.ncand[0] <= 0) return;                // no structure to exploit: full scan
@@ -201,6 +210,7 @@ __global__ void __launch_bounds__(256) k_gen_bbox_cand(const bfm_gen_sample *__r
 }
 
 __global__ void k_gen_bbox_decide(const bfm_gen_sample *__restrict__ S) {
+    if (bbox_follower(S, blockIdx.x)) return;
     const bfm_gen_sample &s = S[blockIdx.x];
     int *bb = s.bbox;
     __shared__ int ambiguous;
@@ -229,6 +239,7 @@ __global__ void k_gen_bbox_decide(const bfm_gen_sample *__restrict__ S) {
 __global__ void __launch_bounds__(kRowWarps * 32) k_gen_bbox_full(const bfm_gen_sample *__restrict__ S, int fstride) {
     extern __shared__ float smem[];
     __shared__ bfm_gen_sample sd;
+    if (bbox_follower(S, blockIdx.y)) return;
     if (S[blockIdx.y].bbox[6] == 0) return;                  // candidate result was provably exact
     stage_desc(&sd, S + blockIdx.y);
     const bfm_deform &d = sd.d;
@@ -236,20 +247,25 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_bbox_full(const bfm_gen_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *smF = smem + warp * kRowsPerWarp * fstride;
     const int n_rows = g.s0 * g.s1;
-    const int row0 = (blockIdx.x * kRowWarps + warp) * kRowsPerWarp;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {0.f, 0.f, 0.f};
-    if (row0 < n_rows) {
-        deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
-                                  [&](int, int, int, int, int, float px, float py, float pz) {
-                                      lo[0] = fminf(lo[0], px); hi[0] = fmaxf(hi[0], px);
-                                      lo[1] = fminf(lo[1], py); hi[1] = fmaxf(hi[1], py);
-                                      lo[2] = fminf(lo[2], pz); hi[2] = fmaxf(hi[2], pz);
-                                  });
+    // persistent blocks (the scan is rarely needed: an early exit must not cost a launch of thousands of blocks)
+    for (int chunk = blockIdx.x; chunk * kRowWarps * kRowsPerWarp < n_rows; chunk += gridDim.x) {
+        const int row0 = (chunk * kRowWarps + warp) * kRowsPerWarp;
+        if (row0 < n_rows) {
+            deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
+                                      [&](int, int, int, int, int, float px, float py, float pz) {
+                                          lo[0] = fminf(lo[0], px); hi[0] = fmaxf(hi[0], px);
+                                          lo[1] = fminf(lo[1], py); hi[1] = fmaxf(hi[1], py);
+                                          lo[2] = fminf(lo[2], pz); hi[2] = fmaxf(hi[2], pz);
+                                      });
+        }
+        __syncwarp();
     }
     block_minmax_atomic(lo, hi, sd.bbox);
 }
 
 __global__ void k_gen_bbox_finish(const bfm_gen_sample *__restrict__ S) {
+    if (bbox_follower(S, blockIdx.x)) return;
     int *bb = S[blockIdx.x].bbox;
     if (bb[6] == 0) return;
     __syncthreads();
@@ -1098,7 +1114,8 @@ int bfm_gen_bbox(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
     k_gen_bbox_decide<<<B, 32, 0, s>>>(d);
     const int fstride = max_fstride(h, B);
     const size_t smem = (size_t)kRowWarps * kRowsPerWarp * fstride * sizeof(float);
-    k_gen_bbox_full<<<dim3(rows_grid(h), B), kRowWarps * 32, smem, s>>>(d, fstride);
+    const unsigned full_blocks = min(rows_grid(h), (unsigned)max(8, (4 * 148 + B - 1) / B));
+    k_gen_bbox_full<<<dim3(full_blocks, B), kRowWarps * 32, smem, s>>>(d, fstride);
     k_gen_bbox_finish<<<B, 32, 0, s>>>(d);
     g_launches.fetch_add(most > 0 ? 4 : 3);
     return check_launch("bfm_gen_bbox");

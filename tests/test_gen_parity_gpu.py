@@ -134,3 +134,28 @@ def test_slab_mode_two_ranks():
                             os.path.join(root, "tests", "_slab_worker.py"), name],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["g64_s0", "g64_s2", "g160_s0"])
+def test_full_bbox_scan_equals_candidate_result(name):
+    """bfm_gen_bbox: with the candidate lists disabled (ncand = 0) the persistent full scan must give the same six
+    integers as the candidate-voxel evaluation (and as the oracle)."""
+    import ctypes as C
+    from brainfm_b200 import _lib
+    item, orc = oracle_case(name)
+    got, ds, draws = cuda_case(name, orc.log, planner='python')
+    descs, d_dev, B = ds._last_descs
+    want = orc.deform["lo"] + orc.deform["hi"]
+    assert ds.last_deform["_plan"].bbox_host() == want
+    copy = (_lib.GenSample * B)()
+    C.memmove(C.addressof(copy), C.addressof(descs), C.sizeof(copy))
+    bb = torch.zeros(8 * B, dtype=torch.int32, device="cuda")
+    for b in range(B):
+        copy[b].d.ncand[:] = [0, 0, 0]
+        copy[b].bbox = bb.data_ptr() + 32 * b
+    host = np.frombuffer(copy, dtype=np.uint8).copy()
+    dev = torch.from_numpy(host).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib().bfm_gen_bbox(C.addressof(copy), dev.data_ptr(), B, st))
+    torch.cuda.synchronize()
+    assert bb[:6].tolist() == want

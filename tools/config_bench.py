@@ -98,7 +98,7 @@ def shapeid_cfg(n=192):
                       "reference_cpu_s_8_threads": 95.6 if n == 192 else None}))
 
 
-def brainid_cfg(n_items=2, steps=30):
+def brainid_cfg(n_items=2, steps=100):
     """configs[4] (a): BrainIDGen stream -- one deformation and one set of targets per item, all_samples = 4
     contrasts (2 mild + 2 severe, demo_synth.yaml:100-101) of 160^3 each; 2 items = 8 samples per step."""
     import tempfile
