@@ -454,7 +454,10 @@ __device__ __forceinline__ float fast_pow(float x, float g) { return ex2_approx(
 // carry tail padding and only finite values so that 0 * neighbour == 0.
 // The coordinate path keeps the reference's separately rounded operations (bit-exact coordinates); the
 // interpolation of VALUES uses a + w*(b-a) with one FMA per lerp (<= 1 ulp from the reference's w0*a + w1*b).
-constexpr int kWR = 4;            // rows per barrier
+#ifndef WARP_ROWS
+#define WARP_ROWS 4
+#endif
+constexpr int kWR = WARP_ROWS;    // rows per barrier
 #ifndef WARP_PIPE
 #define WARP_PIPE 2
 #endif
