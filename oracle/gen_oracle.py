@@ -576,6 +576,18 @@ class GeneratorOracle:
         S[S < 0.] = 0.
         return self.augment(S, setups, "synth", target, direction)
 
+    def real(self, input_mode, setups, D, target):
+        """Real-image input (augment_sample, datasets.py:306-320): raw crop (no nan_to_num, no clamp at 0),
+        hemisphere mask, trilinear warp, CT window; pathology direction fixed by the modality (datasets.py:520-528)."""
+        I = self._crop(self.vol[input_mode], (D["lo"], D["hi"]))
+        if self.hemis_mask is not None:
+            I[self.hemis_mask == 0] = 0
+        I = sample_trilinear(I, *D["rel"])
+        if input_mode == "CT":
+            I = torch.clamp(I, min=0., max=80.)
+        direction = input_mode in ("T2", "FLAIR")
+        return self.augment(I, setups, input_mode, target, direction)
+
     # -- augmentation chain (datasets.py:306-354, utils.py:568-638) ----------------------------
     def op_gamma(self, I, aux, setups):
         n = np.random.randn(1)[0]; self.log.append(("gamma.n", n))
@@ -584,6 +596,9 @@ class GeneratorOracle:
 
     def op_bias_field(self, I, aux, setups):
         g = self.g
+        if getattr(self, "_mode", "synth") == "CT":      # utils.py:575-577: no bias field on CT
+            aux["high_res"] = I
+            return I
         u = np.random.rand(1); self.log.append(("bf.scale", u))
         s = g.bf_scale_min + u * (g.bf_scale_max - g.bf_scale_min)
         small = np.round(s * np.array(self.size)).astype(int).tolist()
@@ -630,6 +645,7 @@ class GeneratorOracle:
                 target["pathology"] = 0.0
                 target["pathology_prob"] = 0.0
         aux = {}
+        self._mode = input_mode
         steps = self.aug_steps["synth"] if input_mode == "synth" else self.aug_steps["real"]
         table = {"gamma": self.op_gamma, "bias_field": self.op_bias_field, "resample": self.op_resample,
                  "noise": self.op_noise}
@@ -656,8 +672,15 @@ class GeneratorOracle:
     # -- __getitem__ (datasets.py:638-681, 700-757) --------------------------------------------
     def sample(self):
         self.log = []
-        u = np.random.rand(); self.log.append(("input.mode", u))     # read_input :572 (synth forced)
-        shp = np.asarray(self.vol["Gen"]).shape
+        u = np.random.rand(); self.log.append(("input.mode", u))     # read_input (datasets.py:563-588)
+        probs = vars(getattr(self.cfg.modality_probs, self.dataset_name))
+        input_mode = "synth"
+        for m in ("T1", "T2", "FLAIR", "CT"):
+            if u < probs[m] and m in self.vol:
+                input_mode = m
+                break
+        self.input_mode = input_mode
+        shp = np.asarray(self.vol["Gen" if input_mode == "synth" else input_mode]).shape
         setups = self.setup()
         D = self.deformation(setups, shp)
         self.hemis_mask = None
@@ -669,15 +692,19 @@ class GeneratorOracle:
                                                .astype(np.float64)))
             self.hemis_mask = ((S > 0) & (X < 0)).int()
         target = self.targets(setups, D)
+        def one():
+            if input_mode == "synth":
+                self._merge(self.cfg.synth_image_generator)
+                return self.synth(setups, D, target)
+            self._merge(self.cfg.real_image_generator)           # datasets.py:666-669, 737-745
+            return self.real(input_mode, setups, D, target)
         if not self.brain_id:
-            self._merge(self.cfg.synth_image_generator)
-            sample = self.synth(setups, D, target)
+            sample = one()
         else:
             sample = []
             for i in range(self.g.all_samples):
                 self._merge(self.cfg.mild_generator if i < self.g.mild_samples else self.cfg.severe_generator)
-                self._merge(self.cfg.synth_image_generator)
-                sample.append(self.synth(setups, D, target))
+                sample.append(one())
         if not isinstance(target.get("pathology"), torch.Tensor):
             target["pathology"] = 0.0
             target["pathology_prob"] = 0.0
@@ -685,7 +712,7 @@ class GeneratorOracle:
             target["pathology"] = torch.flip(target["pathology"], [1])
             target["pathology_prob"] = torch.flip(target["pathology_prob"], [1])
         self.setups, self.deform = setups, D
-        return 1, self.dataset_name, "synth", target, sample
+        return 1, self.dataset_name, input_mode, target, sample
 
 
 def seed_all(s):

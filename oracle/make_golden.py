@@ -59,6 +59,11 @@ CASES = {
     "g160_s0": (160, 192, "brain", 0, {}, [], "default", 4),
     # undegraded resolution class (identity band + identity zoom), no flip, with the super-resolution residual
     "g64_ident_s23": (64, 96, "brain", 23, {"task.super_resolution": True}, [], "default", 2),
+    # real-image inputs (read_input draws the modality): T1 with the default tasks, T2 with every image target
+    "g64_realT1_s14": (64, 96, "brain", 14, {"modality_probs.HCP.T1": 1.0, "task.super_resolution": True}, [],
+                       "default", 2),
+    "g64_realT2_s15": (64, 96, "brain", 15, {"modality_probs.HCP.T2": 1.0, "task.T1": True, "task.T2": True},
+                       ["T2"], "default", 2),
     # left hemisphere only: photo mode forced, no flip, source masked by (left label) & (MNI x < 0), left label list
     "g64_left_s9": (64, 96, "brain", 9, {"generator.left_hemis_only": True, "task.segmentation": True,
                                          "task.distance": True, "task.registration": True},

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g64_full_s4", "g160_s0", "g64_pathol_s7",
-         "g64_pathol_s12", "g64_left_s9", "g64_ident_s23"]
+         "g64_pathol_s12", "g64_left_s9", "g64_ident_s23", "g64_realT1_s14", "g64_realT2_s15"]
 
 
 def _compare(ref, got, name):
@@ -59,7 +59,8 @@ def test_brainid_batch_matches_oracle():
     _compare(mg.flatten(item), mg.flatten(got), name)
 
 
-@pytest.mark.parametrize("name", ["g64_s0", "g64_full_s4", "g160_s0", "g64_pathol_s7", "g64_left_s9", "g64_ident_s23"])
+@pytest.mark.parametrize("name", ["g64_s0", "g64_full_s4", "g160_s0", "g64_pathol_s7", "g64_left_s9", "g64_ident_s23", "g64_realT1_s14",
+                                  "g64_realT2_s15"])
 def test_chain_matches_reference_fixture(name):
     """Directly against the fixture the unmodified reference produced (strided sub-sample + sums)."""
     gold = np.load(os.path.join(GOLD, name + ".npz"))
