@@ -387,25 +387,29 @@ class BaseGen(Dataset):
                                                     for k in _STOCK_STEPS)
                 and not self.synth_args.bspline_zooming)
 
-    def _plan_synth(self, setups, target, arena=None):
+    def _plan_synth(self, setups, target, arena=None, real=False):
         """Draws of generate_sample + the stock augmentation chain, in the reference's order
         (datasets.py:357-428, utils.py:568-638).  With an arena the array-shaped draws (mean/std tables, bias
         grid) are written straight into the pinned plan arena and `p` carries their device addresses."""
         cfg, rng, size = self.gen_args.generator, self.rng, self.size
-        p = {}
-        if arena is not None:
-            p['musigma_dev'], ms = arena.alloc_tensor((2, 256))
-            p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'], out=ms)
+        p = {'real': real}
+        if real:
+            # real-image input (augment_sample, datasets.py:306-336): no contrast, no GMM noise, no mixing draw
+            p['mu'] = p['sigma'] = p['eps_gmm'] = p['mix'] = None
         else:
-            p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'])
-        p['eps_gmm'] = rng.field_randn("gmm.eps")
-        p['mix'] = None
-        if rng.rand("mix.u") < self.gen_args.mix_synth_prob:
-            v = rng.torch_rand("mix.v", 4)
-            v[2] = 0 if 'T2' not in self.modalities else v[2]
-            v[3] = 0 if 'FLAIR' not in self.modalities else v[3]
-            v /= torch.sum(v)
-            p['mix'] = v
+            if arena is not None:
+                p['musigma_dev'], ms = arena.alloc_tensor((2, 256))
+                p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'], out=ms)
+            else:
+                p['mu'], p['sigma'] = self.get_contrast(setups['photo_mode'])
+            p['eps_gmm'] = rng.field_randn("gmm.eps")
+            p['mix'] = None
+            if rng.rand("mix.u") < self.gen_args.mix_synth_prob:
+                v = rng.torch_rand("mix.v", 4)
+                v[2] = 0 if 'T2' not in self.modalities else v[2]
+                v[3] = 0 if 'FLAIR' not in self.modalities else v[3]
+                v /= torch.sum(v)
+                p['mix'] = v
         # gamma
         p['gamma'] = np.float32(np.exp(cfg.gamma_std * rng.randn1("gamma.n")))
         # bias field
@@ -481,20 +485,25 @@ class BaseGen(Dataset):
         for b, job in enumerate(jobs):
             s, p, plan = descs[b], job['p'], job['plan']
             s.d = plan.struct
-            lab = job['labels']
-            s.labels = lab.data_ptr()
-            s.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
-            if 'musigma_dev' in p:
-                s.mu, s.sigma = p['musigma_dev'], p['musigma_dev'] + 1024
+            if p.get('real'):
+                # the warp gathers straight from the cached (finite, padded) real volume; nothing is synthesised
+                s.real_input = 1
+                s.syn = job['real_vol'].data_ptr()
             else:
-                s.mu = arena.put(p['mu'].numpy())
-                s.sigma = arena.put(p['sigma'].numpy())
-            if p['eps_gmm'] is not None:
-                e = p['eps_gmm'].to(dev).contiguous()
-                keep.append(e)
-                s.eps_gmm = e.data_ptr()
+                lab = job['labels']
+                s.labels = lab.data_ptr()
+                s.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
+                if 'musigma_dev' in p:
+                    s.mu, s.sigma = p['musigma_dev'], p['musigma_dev'] + 1024
+                else:
+                    s.mu = arena.put(p['mu'].numpy())
+                    s.sigma = arena.put(p['sigma'].numpy())
+                if p['eps_gmm'] is not None:
+                    e = p['eps_gmm'].to(dev).contiguous()
+                    keep.append(e)
+                    s.eps_gmm = e.data_ptr()
+                s.syn = p_syn + 4 * b * src_pad
             s.seed = int(p['seed'])
-            s.syn = p_syn + 4 * b * src_pad
             s.bbox = plan.bbox_ptr
             if p['mix'] is not None:
                 for q in range(4):
@@ -648,9 +657,11 @@ class BaseGen(Dataset):
             return bool(self.write_bflog)
         return 'bias_field' in self.tasks and input_mode != 'CT'
 
-    def _job(self, setups, deform_dict, target, p):
-        return dict(plan=deform_dict['_plan'], flip=setups['flip'], labels=self._labels(), p=p, target=target,
-                    modalities=dict(self.modalities), want_bflog=self._want_bflog('synth'),
+    def _job(self, setups, deform_dict, target, p, input_mode='synth'):
+        real = input_mode != 'synth'
+        return dict(plan=deform_dict['_plan'], flip=setups['flip'], labels=None if real else self._labels(), p=p,
+                    real_vol=self.cache.get(self.modalities[input_mode], 'f32') if real else None,
+                    target=target, modalities=dict(self.modalities), want_bflog=self._want_bflog(input_mode),
                     want_residual='super_resolution' in self.tasks)
 
     # ---- reference-shaped sample generation ---------------------------------------------------------
@@ -863,12 +874,21 @@ class BaseGen(Dataset):
         self.last_setups, self.last_deform = setups, ctx['deform']
         return self.datasets_num, ctx['dataset_name'], ctx['input_mode'], target, sample
 
-    def _fast_ok(self, input_mode):
-        return input_mode == 'synth' and self._stock_chain('synth') and 'pathology' not in self.tasks
+    def _fast_ok(self, input_mode, src_shape=None):
+        """Fused chain: synthetic inputs, and real T1 / T2 / FLAIR inputs (CT has its own window and no bias field)
+        whose volume has the shape of the deformation's source grid, with the stock augmentation chain."""
+        if 'pathology' in self.tasks:
+            return False
+        if input_mode == 'synth':
+            return self._stock_chain('synth')
+        if input_mode not in ('T1', 'T2', 'FLAIR') or self.hemis_mask is not None or not self._stock_chain(input_mode):
+            return False
+        vol = self.cache.get(self.modalities[input_mode], 'f32')
+        return src_shape is None or list(vol.shape[:3]) == [int(v) for v in src_shape[:3]]
 
-    def _gen_arg_sets(self):
-        """Parameter overrides applied before each sample of an item (datasets.py:668, 728-745)."""
-        return [[self.synth_image_args]]
+    def _gen_arg_sets(self, input_mode='synth'):
+        """Parameter overrides applied before each sample of an item (datasets.py:664-669, 728-745)."""
+        return [[self.synth_image_args if input_mode == 'synth' else self.real_image_args]]
 
     _default_target = staticmethod(lambda: None)
     _list_samples = False
@@ -884,17 +904,19 @@ class BaseGen(Dataset):
         for n, idx in enumerate(indices):
             ctx = self._prologue_host(idx, arena)
             ctxs.append(ctx)
-            if not self._fast_ok(ctx['input_mode']):
+            mode = ctx['input_mode']
+            if not self._fast_ok(mode, ctx['img'].shape):
                 slow[n] = True
                 spans.append((0, 0))
                 continue
             ctx['target'] = defaultdict(self._default_target)
             first = len(jobs)
-            for arg_sets in self._gen_arg_sets():
+            for arg_sets in self._gen_arg_sets(mode):
                 for a in arg_sets:
                     self.update_gen_args(a)
                 jobs.append(self._job(ctx['setups'], ctx['deform'], ctx['target'],
-                                      self._plan_synth(ctx['setups'], ctx['target'], arena)))
+                                      self._plan_synth(ctx['setups'], ctx['target'], arena, real=mode != 'synth'),
+                                      mode))
             spans.append((first, len(jobs)))
             aux = self._fused_image_targets(ctx, jobs[first:])
             if aux:
@@ -964,6 +986,7 @@ class BrainIDGen(BaseGen):
         self.mild_generator_args = gen_args.mild_generator
         self.severe_generator_args = gen_args.severe_generator
 
-    def _gen_arg_sets(self):
-        return [[self.mild_generator_args if i < self.mild_samples else self.severe_generator_args,
-                 self.synth_image_args] for i in range(self.all_samples)]
+    def _gen_arg_sets(self, input_mode='synth'):
+        last = self.synth_image_args if input_mode == 'synth' else self.real_image_args
+        return [[self.mild_generator_args if i < self.mild_samples else self.severe_generator_args, last]
+                for i in range(self.all_samples)]

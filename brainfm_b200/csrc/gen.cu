@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) k_gen_gmm_planes(const bfm_gen_sample *__
     __shared__ float lut[512];
     const bfm_gen_sample *sp = S + blockIdx.z;
     const int n0 = sp->d.src[0], n1 = sp->d.src[1], n2 = sp->d.src[2];
-    if (n2 & 3) return;                                            // handled by k_gen_gmm
+    if ((n2 & 3) || sp->real_input) return;                        // handled by k_gen_gmm / nothing to synthesise
     const int *bb = sp->bbox;
     const int b0 = bb[0], b1 = bb[1], b2 = bb[2], e0 = bb[3], e1 = bb[4], e2 = bb[5];
     const int x = b0 + blockIdx.y;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) k_gen_gmm(const bfm_gen_sample *__restric
     stage_desc(&sd, S + blockIdx.y);
     const bfm_gen_sample &s = sd;
     const int n0 = s.d.src[0], n1 = s.d.src[1], n2 = s.d.src[2];
-    if ((n2 & 3) == 0) return;                       // handled by k_gen_gmm_planes
+    if ((n2 & 3) == 0 || s.real_input) return;       // handled by k_gen_gmm_planes / nothing to synthesise
     const int total = n0 * n1 * n2;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int blk0 = blockIdx.x * blockDim.x * 4;
@@ -524,6 +524,7 @@ __device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B
     const float *__restrict__ mix0 = s.mix[0], *__restrict__ mix1 = s.mix[1], *__restrict__ mix2 = s.mix[2];
     const float mw0 = s.mixw[0], mw1 = s.mixw[1], mw2 = s.mixw[2], mw3 = s.mixw[3];
     const float gamma = s.gamma;
+    const bool real_in = s.real_input != 0;
     float *__restrict__ i_bf = s.i_bf;
     float *__restrict__ bfl = bw ? s.bflog_out : nullptr;
     const float *__restrict__ asrc[NAUX > 0 ? NAUX : 1];
@@ -621,7 +622,7 @@ __device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B
                         if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[pr]));
                         if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[pr]));
                     }
-                    v = fmaxf(v, 0.f);                                // datasets.py:411
+                    if (!real_in) v = fmaxf(v, 0.f);                  // datasets.py:411 (synthetic images only)
                     // gamma: 300 * (I/300) ** gamma                  utils.py:568-572
                     v = 300.f * fast_pow(v * (1.f / 300.f), gamma);
                     // bias field: I * exp(zoom(BFsmall))             utils.py:574-589
@@ -1070,8 +1071,11 @@ static int check_batch(const bfm_gen_sample *h, const bfm_gen_sample *d, int B) 
             return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen: deformation small grid too deep");
         if (s.bfsmall && (s.bs[2] > kMaxSmallZ || s.bs[2] <= 0))
             return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen: bias small grid too deep");
-        if (!s.labels || !s.mu || !s.sigma || !s.syn || !s.bbox || !s.i_bf || !s.lowres || !s.maxval || !s.out)
+        if (!s.syn || !s.bbox || !s.i_bf || !s.lowres || !s.maxval || !s.out ||
+            (!s.real_input && (!s.labels || !s.mu || !s.sigma)))
             return fail(BFM_E_INVALID, "%s", "bfm_gen: null buffer");
+        if (s.real_input && s.mix[0])
+            return fail(BFM_E_INVALID, "%s", "bfm_gen: real-image inputs are not mixed");
         if (s.n_band < 1 || s.n_band > 3) return fail(BFM_E_INVALID, "%s", "bfm_gen: n_band must be 1..3");
         if (s.d.size[0] != h[0].d.size[0] || s.d.size[1] != h[0].d.size[1] || s.d.size[2] != h[0].d.size[2])
             return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen: all samples of a batch share the output size");
@@ -1130,6 +1134,7 @@ int bfm_gen_gmm(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *s
     int64_t flat_groups = 0, plane_groups = 0;
     int max_n0 = 0;
     for (int b = 0; b < B; ++b) {
+        if (h[b].real_input) continue;
         const int *n = h[b].d.src;
         if (n[2] & 3) {
             const int64_t g = ((int64_t)n[0] * n[1] * n[2] + 3) / 4;

@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 4
+#define BFM_ABI_VERSION 5
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -229,6 +229,11 @@ typedef struct bfm_gen_sample {
        Generator/utils.py:584) -- the pointers must then address writable device scratch. */
     int gen_small;
     float fs_std, bf_std;
+    /* Real-image input (BaseGen.augment_sample with input_mode T1 / T2 / FLAIR, Generator/datasets.py:306-316): `syn`
+       is the real source volume itself (f32, finite, followed by >= src[1]*src[2]+src[2]+1 readable floats, never
+       written), the GMM stage is skipped (labels / mu / sigma may be NULL) and the warped value is NOT clamped at 0
+       before the gamma transform. */
+    int real_input;
 } bfm_gen_sample;
 
 /* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,

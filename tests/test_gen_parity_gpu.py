@@ -160,3 +160,14 @@ def test_full_bbox_scan_equals_candidate_result(name):
     _lib.check(_lib.lib().bfm_gen_bbox(C.addressof(copy), dev.data_ptr(), B, st))
     torch.cuda.synchronize()
     assert bb[:6].tolist() == want
+
+
+@pytest.mark.parametrize("name,mode", [("g64_realT1_s14", "T1"), ("g64_realT2_s15", "T2")])
+def test_real_inputs_take_the_fused_chain(name, mode):
+    """Real T1 / T2 / FLAIR inputs run through the fused chain (real_input descriptors, no GMM stage), not op by op."""
+    item, orc = oracle_case(name)
+    got, ds, draws = cuda_case(name, orc.log, planner='python')
+    assert got[2] == mode == item[2]
+    descs, _, B = ds._last_descs
+    assert B == 1 and descs[0].real_input == 1 and descs[0].labels is None
+    _compare(mg.flatten(item), mg.flatten(got), name)
