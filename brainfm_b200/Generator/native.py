@@ -1,11 +1,12 @@
 """Batched planning through the native host planner (libbfm `bfm_plan_batch`, csrc/planner.cu).
 
 `BaseGen.generate_batch` plans every item in Python (draws from the numpy/torch global generators in the
-reference's order, ~250 us per sample).  When nothing in the configuration needs Python per sample -- synthetic
-inputs only, stock augmentation chain, no mixing with real modalities, no pathology / surface task, no random
-shift -- the whole batch is planned by ONE call into the library instead: the same arithmetic in C, draws from
-an in-library Philox stream keyed on (seed, item counter) (the seed itself is one draw of numpy's global
-generator, so `np.random.seed` still makes a run reproducible), small random grids drawn on the device.
+reference's order, ~250 us per sample).  When nothing in the configuration needs Python per sample -- synthetic or
+real T1 / T2 / FLAIR inputs (drawn per item like read_input), stock augmentation chain, no mixing with real
+modalities, no CT input, no pathology / surface task, no random shift -- the whole batch is planned by ONE call into
+the library instead: the same arithmetic in C, draws from an in-library Philox stream keyed on (seed, item counter)
+(the seed itself is one draw of numpy's global generator, so `np.random.seed` still makes a run reproducible), small
+random grids drawn on the device.
 With a `ReplayDraws` source the planner runs in replay mode and consumes the recorded draws (parity tests).
 """
 import ctypes as C
@@ -52,8 +53,20 @@ class NativePlanner:
         return True
 
     def item_ok(self, input_prob, modalities):
-        """Only synthetic inputs: no real modality of this subject can be drawn as the input (datasets.py:572-580)."""
-        return not any(input_prob.get(m, 0) > 0 and m in modalities for m in ('T1', 'T2', 'FLAIR', 'CT'))
+        """Inputs the library plans: synthetic, and real T1 / T2 / FLAIR volumes of the label map's shape.  A subject
+        whose CT can be drawn as the input (datasets.py:581-583) is planned in Python."""
+        ds = self.ds
+        if input_prob.get('CT', 0) > 0 and 'CT' in modalities:
+            return False
+        if any(input_prob.get(m, 0) > 0 and m in modalities for m in ('T1', 'T2', 'FLAIR')):
+            if not ds._stock_chain('real'):
+                return False
+            shape = list(ds.cache.get(modalities['Gen'], 'gen').shape[:3])
+            for m in ('T1', 'T2', 'FLAIR'):
+                if input_prob.get(m, 0) > 0 and m in modalities and \
+                        list(ds.cache.get(modalities[m], 'f32').shape[:3]) != shape:
+                    return False
+        return True
 
     # ---- configuration (built once) ------------------------------------------------------------------
     def _build_cfg(self):
@@ -75,14 +88,16 @@ class NativePlanner:
                 grp[l] = g
         C.memmove(cfg.ct_group, grp.ctypes.data, 256)
         # per-sample parameter ranges: generator values with the overrides of each sample applied in order
-        sets = ds._gen_arg_sets()
-        cfg.n_samples = len(sets)
-        for k, overrides in enumerate(sets):
-            vals = dict(vars(ds.gen_args.generator))
-            for o in overrides:
-                vals.update(vars(o))
-            for f, _ in _lib.PlanAug._fields_:
-                setattr(cfg.aug[k], f, float(vals[f]))
+        base = dict(vars(ds.gen_args.generator))           # snapshot: update_gen_args mutates the shared namespace
+        for mode, dst in (('synth', cfg.aug), ('T1', cfg.aug_real)):
+            sets = ds._gen_arg_sets(mode)
+            cfg.n_samples = len(sets)
+            vals = dict(base)
+            for k, overrides in enumerate(sets):
+                for o in overrides:                         # overrides accumulate from sample to sample, like
+                    vals.update(vars(o))                    # update_gen_args on the shared namespace (datasets.py:634-636)
+                for f, _ in _lib.PlanAug._fields_:
+                    setattr(dst[k], f, float(vals[f]))
         # zoom-table directories
         tables = ds.tables
         tables.prebuild(size)
@@ -137,6 +152,12 @@ class NativePlanner:
             it.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
             src = [int(v) for v in lab.shape[:3]]
             it.src[:] = src
+            for q, m in enumerate(('T1', 'T2', 'FLAIR', 'CT')):
+                it.input_prob[q] = float(input_prob.get(m, 0))
+            for q, m in enumerate(('T1', 'T2', 'FLAIR')):
+                if m in mods and input_prob.get(m, 0) > 0:
+                    it.real_vol[q] = ds.cache.get(mods[m], 'f32').data_ptr()
+            it.has_ct = int('CT' in mods)
             aux = ds._fused_aux_volumes(mods, src)
             it.n_aux = len(aux)
             for c, (key, vol) in enumerate(aux):
@@ -229,7 +250,8 @@ class NativePlanner:
             setups = {'resolution': np.array(inf.resolution[:]), 'thickness': np.array(inf.thickness[:]),
                       'photo_mode': bool(inf.photo_mode), 'pathol_mode': False, 'pathol_random_shape': False,
                       'spac': inf.spac if inf.photo_mode else None, 'flip': bool(inf.flip), 'hemis': 'both'}
-            ctxs.append(dict(idx=idx, dataset_name=dataset_name, case_name=_case_name(t1_path), input_mode='synth',
+            ctxs.append(dict(idx=idx, dataset_name=dataset_name, case_name=_case_name(t1_path),
+                             input_mode=('synth', 'T1', 'T2', 'FLAIR')[inf.input_mode],
                              age=age, setups=setups, modalities=mods, aux=aux, src=src, n=n))
         need_plans = other_targets or any(len(c['aux']) < sum(1 for k in ('T1', 'T2', 'FLAIR') if k in c['modalities'])
                                           for c in ctxs)
@@ -266,15 +288,15 @@ class NativePlanner:
                 if key in fused:
                     target[key] = fused[key]
                 elif key in ctx['modalities']:
-                    target.update(ds.read_and_deform_target(ctx['idx'], target.keys(), key, 'synth', ctx['setups'],
-                                                            deform))
+                    target.update(ds.read_and_deform_target(ctx['idx'], target.keys(), key, ctx['input_mode'],
+                                                            ctx['setups'], deform))
                 else:
                     target[key] = 0.
             if other_targets:
                 for task_name in ds.tasks:
                     if task_name in K.processing_funcs.keys() and task_name not in ('T1', 'T2', 'FLAIR'):
-                        target.update(ds.read_and_deform_target(ctx['idx'], target.keys(), task_name, 'synth',
-                                                                ctx['setups'], deform))
+                        target.update(ds.read_and_deform_target(ctx['idx'], target.keys(), task_name,
+                                                                ctx['input_mode'], ctx['setups'], deform))
             target['pathology'] = 0.
             target['pathology_prob'] = 0.
             targets.append(target)
@@ -303,7 +325,7 @@ class NativePlanner:
             sample = results[n * ns:(n + 1) * ns] if ds._list_samples else results[n * ns]
             if ctx['age'] is not None:
                 target['age'] = ctx['age']
-            tuples.append((ds.datasets_num, ctx['dataset_name'], 'synth', target, sample))
+            tuples.append((ds.datasets_num, ctx['dataset_name'], ctx['input_mode'], target, sample))
         if ctxs:
             ds.last_setups, ds.last_deform = ctxs[-1]['setups'], ctxs[-1]['deform']
         self.last = dict(descs=descs, descs_dev=d_dev, info=info, total=total, keep=(out, bfl, res, aux_all, keep),

@@ -69,14 +69,15 @@ class PlanCfg(C.Structure):
                 ("max_rotation", c_d), ("max_shear", c_d), ("max_scaling", c_d),
                 ("nonlin_scale_min", c_d), ("nonlin_scale_max", c_d), ("nonlin_std_max", c_d),
                 ("ct_prob", c_d), ("mix_synth_prob", c_d), ("ct_group", C.c_int8 * 256), ("n_samples", c_i),
-                ("aug", PlanAug * PLAN_MAX_SAMPLES),
+                ("aug", PlanAug * PLAN_MAX_SAMPLES), ("aug_real", PlanAug * PLAN_MAX_SAMPLES),
                 ("fwd", c_p * 3), ("inv", c_p * 3), ("ends", c_p * 3), ("ident_start", c_p), ("ident_w", c_p)]
 
 
 class PlanItem(C.Structure):
     _fields_ = [("labels", c_p), ("label_is_u8", c_i), ("src", c_i * 3), ("n_aux", c_i),
                 ("aux_src", c_p * MAX_AUX), ("aux_out", c_p * MAX_AUX), ("aux_raw", c_p * MAX_AUX),
-                ("eps_gmm", c_p * PLAN_MAX_SAMPLES), ("eps_noise", c_p * PLAN_MAX_SAMPLES)]
+                ("eps_gmm", c_p * PLAN_MAX_SAMPLES), ("eps_noise", c_p * PLAN_MAX_SAMPLES),
+                ("input_prob", c_d * 4), ("real_vol", c_p * 3), ("has_ct", c_i)]
 
 
 class PlanOut(C.Structure):
@@ -85,7 +86,7 @@ class PlanOut(C.Structure):
 
 
 class PlanInfo(C.Structure):
-    _fields_ = [("photo_mode", c_i), ("flip", c_i), ("spac", c_d), ("resolution", c_d * 3), ("thickness", c_d * 3),
+    _fields_ = [("input_mode", c_i), ("photo_mode", c_i), ("flip", c_i), ("spac", c_d), ("resolution", c_d * 3), ("thickness", c_d * 3),
                 ("scaling_factor_distances", c_d), ("A", c_f * 9), ("c2", c_f * 3), ("fs", c_i * 3),
                 ("new_size", (c_i * 3) * PLAN_MAX_SAMPLES)]
 

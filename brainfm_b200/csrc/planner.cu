@@ -160,8 +160,17 @@ struct ItemSetup {
 int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_out *outs, Draws &dr, uint64_t seed,
               uint64_t sample0, ArenaCursor &ar, bfm_gen_sample *descs, bfm_plan_info &info, bool native) {
     const int *size = cfg.size;
-    // ---- read_input (datasets.py:572): the input-mode draw; only synthetic inputs are planned here
-    (void)dr.rand();
+    // ---- read_input (datasets.py:563-588): first modality with u < prob whose volume exists, else synthetic
+    int mode = 0;
+    {
+        const double u = dr.rand();
+        if (u < it.input_prob[0] && it.real_vol[0]) mode = 1;
+        else if (u < it.input_prob[1] && it.real_vol[1]) mode = 2;
+        else if (u < it.input_prob[2] && it.real_vol[2]) mode = 3;
+        else if (u < it.input_prob[3] && it.has_ct)
+            return fail(BFM_E_UNSUPPORTED, "%s", "bfm_plan_batch: CT inputs are not planned natively");
+    }
+    info.input_mode = mode;
     // ---- get_setup_params (datasets.py:466-493)
     ItemSetup st;
     st.photo = cfg.low_res_only ? false : dr.rand() < cfg.photo_prob;
@@ -232,7 +241,7 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
 
     // ---- samples of this item
     for (int k = 0; k < cfg.n_samples; ++k) {
-        const bfm_plan_aug &ag = cfg.aug[k];
+        const bfm_plan_aug &ag = mode ? cfg.aug_real[k] : cfg.aug[k];
         bfm_gen_sample &s = descs[k];
         const bfm_plan_out &o = outs[k];
         std::memset(&s, 0, sizeof(s));
@@ -257,6 +266,12 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         } else {
             for (int a = 0; a < 3; ++a) { d.cand[a] = cfg.ends[a]; d.ncand[a] = 2; }
         }
+        if (mode) {
+            // real-image input (augment_sample, datasets.py:306-336): gather straight from the volume; no contrast,
+            // no GMM noise, no mixing draw
+            s.real_input = 1;
+            s.syn = const_cast<float *>(it.real_vol[mode - 1]);
+        } else {
         s.labels = it.labels;
         s.label_is_u8 = it.label_is_u8;
         // ---- get_contrast (datasets.py:430-464): float32 like the torch tensors
@@ -305,6 +320,7 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         // ---- mixing draw (datasets.py:379): planned only for mix_synth_prob == 0
         if (dr.rand() < cfg.mix_synth_prob)
             return fail(BFM_E_UNSUPPORTED, "%s", "bfm_plan_batch: mixing with real modalities is not planned natively");
+        }
         // ---- gamma (utils.py:568-572)
         s.gamma = (float)std::exp(ag.gamma_std * dr.randn());
         // ---- bias field (utils.py:574-585)
@@ -378,7 +394,8 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         s.seed = native ? splitmix64(seed ^ splitmix64(0x5eedull + sample0 + k)) : 0;
         // ---- buffers
         s.flip = st.flip;
-        s.syn = o.syn; s.i_bf = o.i_bf; s.tmp[0] = o.tmp[0]; s.tmp[1] = o.tmp[1]; s.lowres = o.lowres;
+        if (!mode) s.syn = o.syn;
+        s.i_bf = o.i_bf; s.tmp[0] = o.tmp[0]; s.tmp[1] = o.tmp[1]; s.lowres = o.lowres;
         s.out = o.out; s.bflog_out = o.bflog_out; s.residual = o.residual;
         if (k == 0) {
             s.n_aux = it.n_aux;

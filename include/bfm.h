@@ -289,7 +289,8 @@ typedef struct bfm_plan_cfg {
     double ct_prob, mix_synth_prob;
     int8_t ct_group[256];           /* -1, or 0..3 = darker, dark, bright, brighter (constants.py) */
     int n_samples;                  /* samples per item: 1 (BaseGen) or all_samples (BrainIDGen) */
-    bfm_plan_aug aug[BFM_PLAN_MAX_SAMPLES];
+    bfm_plan_aug aug[BFM_PLAN_MAX_SAMPLES];        /* synthetic inputs (generator + [mild|severe] + synth_image_generator) */
+    bfm_plan_aug aug_real[BFM_PLAN_MAX_SAMPLES];   /* real-image inputs (... + real_image_generator) */
     /* directories indexed by n_in = 0..size[a]: fwd = zoom by size/n_in (small grids -> training grid),
        inv = zoom by 1/(n_in/size) (low-res grid -> training grid) */
     const bfm_zoom_axis *fwd[3];
@@ -310,6 +311,13 @@ typedef struct bfm_plan_item {
     /* replay mode only: injected volume-sized normal fields of each sample (device) */
     const float *eps_gmm[BFM_PLAN_MAX_SAMPLES];
     const float *eps_noise[BFM_PLAN_MAX_SAMPLES];
+    /* read_input (Generator/datasets.py:563-588): the input is the first of T1, T2, FLAIR, CT with u < input_prob[m]
+       whose volume exists, else synthetic.  real_vol[m]: device volume of T1 / T2 / FLAIR with the source shape
+       (f32, finite, padded like aux_src) or NULL when the subject does not have it; has_ct != 0 makes a CT draw
+       fail with BFM_E_UNSUPPORTED (CT inputs are planned in Python). */
+    double input_prob[4];
+    const float *real_vol[3];
+    int has_ct;
 } bfm_plan_item;
 
 typedef struct bfm_plan_out {       /* per SAMPLE buffers (device), caller allocated */
@@ -318,6 +326,7 @@ typedef struct bfm_plan_out {       /* per SAMPLE buffers (device), caller alloc
 } bfm_plan_out;
 
 typedef struct bfm_plan_info {      /* what the host needs to know about a planned ITEM */
+    int input_mode;                 /* 0 synth, 1 T1, 2 T2, 3 FLAIR */
     int photo_mode, flip;
     double spac, resolution[3], thickness[3], scaling_factor_distances;
     float A[9], c2[3];

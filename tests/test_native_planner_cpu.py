@@ -17,7 +17,7 @@ from tests._harness import oracle_case
 FAKE = 0x7f0000000000          # "device" addresses: never dereferenced by the planner
 
 
-def make_cfg(size, gen, mix=0.0, aug_sets=None):
+def make_cfg(size, gen, mix=0.0, aug_sets=None, real_sets=None):
     cfg = _lib.PlanCfg()
     cfg.size[:] = size
     cfg.res[:] = [1.0, 1.0, 1.0]
@@ -34,6 +34,7 @@ def make_cfg(size, gen, mix=0.0, aug_sets=None):
     for k, vals in enumerate(aug_sets):
         for f, _ in _lib.PlanAug._fields_:
             setattr(cfg.aug[k], f, float(vals[f]))
+            setattr(cfg.aug_real[k], f, float((real_sets or aug_sets)[k][f]))
     keep = []
     for ax in range(3):
         n = size[ax]
@@ -49,13 +50,18 @@ def make_cfg(size, gen, mix=0.0, aug_sets=None):
     return cfg, keep
 
 
-def plan(cfg, n_items, src, seed=1, counter=0, replay=None, capacity=1 << 20):
+def plan(cfg, n_items, src, seed=1, counter=0, replay=None, capacity=1 << 20, input_prob=None, real_vol=None,
+         has_ct=0):
     L = _lib.lib()
     ns = cfg.n_samples
     items = (_lib.PlanItem * n_items)()
     for it in items:
         it.labels, it.label_is_u8 = FAKE, 1
         it.src[:] = src
+        if input_prob is not None:
+            it.input_prob[:] = input_prob
+            it.real_vol[:] = real_vol
+            it.has_ct = has_ct
     outs = (_lib.PlanOut * (n_items * ns))()
     for o in outs:
         o.out = o.syn = o.i_bf = o.lowres = FAKE
@@ -193,3 +199,32 @@ def test_unsupported_and_invalid_inputs_fail_loudly():
         plan(cfg, 4, [64] * 3, capacity=4096)          # arena too small
     with pytest.raises(ValueError):
         plan(cfg, 1, [64] * 3, replay=np.zeros(5))     # replay array exhausted
+
+
+def test_real_input_modes_are_drawn_like_read_input():
+    """read_input (datasets.py:563-588): first of T1 / T2 / FLAIR with u < prob whose volume exists; real-input samples
+    carry no contrast tables, gather from the modality's volume and use the real-image noise range."""
+    args = mg.cfg_for(64, {}, "default", ref=False)
+    gen = dict(vars(args.generator))
+    syn = dict(gen); syn.update(vars(args.synth_image_generator))
+    real = dict(gen); real.update(vars(args.real_image_generator))
+    cfg, keep = make_cfg([64] * 3, args.generator, aug_sets=[syn], real_sets=[real])
+    vols = [FAKE + 0x1000, 0, FAKE + 0x3000]                 # the subject has T1 and FLAIR, no T2
+    counts = np.zeros(4)
+    for rep in range(120):
+        r = plan(cfg, 8, [64] * 3, seed=21, counter=8 * rep, input_prob=[0.25, 0.5, 0.75, 0.0], real_vol=vols)
+        for q in range(8):
+            inf, s = r['info'][q], r['descs'][q]
+            counts[inf.input_mode] += 1
+            if inf.input_mode:
+                assert s.real_input == 1 and s.syn == vols[inf.input_mode - 1] and not s.mu and not s.labels
+                assert 0.0 <= s.noise_std <= 0.02 + 1e-9
+            else:
+                assert s.real_input == 0 and s.syn == FAKE and s.mu and 5.0 <= s.noise_std <= 15.0
+    frac = counts / counts.sum()
+    assert counts[2] == 0                                    # no T2 volume: never drawn
+    assert abs(frac[1] - 0.25) < 0.05 and abs(frac[3] - 0.5) < 0.06 and abs(frac[0] - 0.25) < 0.05
+    # a CT draw is refused (planned in Python)
+    with pytest.raises(NotImplementedError):
+        for rep in range(50):
+            plan(cfg, 8, [64] * 3, seed=3, counter=8 * rep, input_prob=[0, 0, 0, 0.9], real_vol=[0, 0, 0], has_ct=1)

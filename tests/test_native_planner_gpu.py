@@ -13,7 +13,8 @@ from tests.test_gen_parity_gpu import _compare
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g160_s0", "g64_ident_s23"]
+CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g160_s0", "g64_ident_s23", "g64_realT1_s14",
+         "g64_realT2_s15"]
 
 
 def _read(ds, ptr, n, dtype):
@@ -33,7 +34,7 @@ def _scalars(s):
                 label_is_u8=s.label_is_u8, gamma=s.gamma, bs=list(s.bs), btab=[list(s.btab.lo), list(s.btab.wh)],
                 flip=s.flip, band=band, n_band=s.n_band, zero_first=list(s.zero_first), noise_std=s.noise_std,
                 new_size=list(s.new_size), utab=[list(s.utab.lo), list(s.utab.wh)], n_aux=s.n_aux,
-                mixw=list(s.mixw))
+                mixw=list(s.mixw), real_input=s.real_input)
 
 
 @pytest.mark.parametrize("name", CASES + ["g64_brainid_s6"])
@@ -45,7 +46,8 @@ def test_replayed_native_plan_equals_python_plan(name):
     for q in range(n_py):
         s = py_descs[q]
         nf = s.d.fs[0] * s.d.fs[1] * s.d.fs[2] * 3
-        py.append((_scalars(s), _read(ds_py, s.mu, 512, torch.float32), _read(ds_py, s.d.fsmall, nf, torch.float32),
+        py.append((_scalars(s), None if s.real_input else _read(ds_py, s.mu, 512, torch.float32),
+                   _read(ds_py, s.d.fsmall, nf, torch.float32),
                    _read(ds_py, s.bfsmall, s.bs[0] * s.bs[1] * s.bs[2], torch.float32)))
     _, ds_c, draws = cuda_case(name, orc.log, planner='native')
     assert draws.done()
@@ -58,7 +60,8 @@ def test_replayed_native_plan_equals_python_plan(name):
         for k in ref_sc:
             assert got_sc[k] == ref_sc[k], (name, q, k, got_sc[k], ref_sc[k])
         nf = s.d.fs[0] * s.d.fs[1] * s.d.fs[2] * 3
-        assert np.array_equal(_read(ds_c, s.mu, 512, torch.float32), ref_ms), (name, q, "mu/sigma tables")
+        if not s.real_input:
+            assert np.array_equal(_read(ds_c, s.mu, 512, torch.float32), ref_ms), (name, q, "mu/sigma tables")
         assert np.array_equal(_read(ds_c, s.d.fsmall, nf, torch.float32), ref_f), (name, q, "deformation grid")
         assert np.array_equal(_read(ds_c, s.bfsmall, s.bs[0] * s.bs[1] * s.bs[2], torch.float32), ref_b), (name, q)
 
@@ -146,3 +149,45 @@ def test_native_matches_python_planner_statistics():
     assert 0.55 < lowz / n < 0.95                           # 1 - 0.8 * 0.25 = 0.8 of the samples are degraded
     assert 0.7 < min(gam) and max(gam) < 1.5 and abs(np.mean(np.log(gam))) < 0.03
     assert 5.0 <= min(nz) and max(nz) <= 15.0
+
+
+def test_native_mode_draws_real_inputs():
+    """modality_probs T1 = 0.5 (the reference's default table has real-image inputs for every dataset): the library
+    planner draws the input mode per item; real and synthetic samples share one batched launch."""
+    import bench
+    from brainfm_b200 import io as bio
+    from brainfm_b200.Generator import BaseGen
+    bio.clear_registry()
+    old = bench.SIZE
+    bench.SIZE = 64
+    try:
+        import tempfile, os
+        subs = bench.make_inputs(4)
+        root = tempfile.mkdtemp(prefix="bfm_mix_")
+        names = []
+        for s, v in enumerate(subs):
+            stem = os.path.join(root, "HCP.sub%02d." % s)
+            bio.register_volume(stem + "T1w.nii", v["T1"])
+            bio.register_volume(stem + "generation_labels.nii", v["Gen"])
+            names.append(stem + "T1w.nii")
+        with open(os.path.join(root, "train.txt"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        cfg = bench.bench_cfg()
+        cfg.split_root = root
+        cfg.modality_probs.HCP.T1 = 0.5
+        ds = BaseGen(cfg, "cuda", planner='native')
+    finally:
+        bench.SIZE = old
+    np.random.seed(5)
+    modes = []
+    for rep in range(12):
+        items = ds.generate_batch([0, 1, 2, 3])
+        for it in items:
+            modes.append(it[2])
+            x = it[4]['input']
+            assert torch.isfinite(x).all() and float(x.min()) >= 0 and abs(float(x.max()) - 1) < 1e-6
+        descs = ds._native.last['descs']
+        for q, it in enumerate(items):
+            assert descs[q].real_input == (1 if it[2] == 'T1' else 0)
+    assert set(modes) == {'synth', 'T1'}
+    assert 0.25 < modes.count('T1') / len(modes) < 0.75

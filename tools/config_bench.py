@@ -141,8 +141,38 @@ def brainid_cfg(n_items=2, steps=100):
                       "planner": "native"}))
 
 
+def realmix_cfg(steps=100):
+    """The bench configuration with the reference's default input table for HCP-like data: a real T1 input with
+    probability 0.5, a synthetic one otherwise (cfgs/generator/default.yaml:14-22), planned natively."""
+    import bench
+    dev = torch.device("cuda", 0)
+    ds = bench.build_dataset(bench.make_inputs(bench.BATCH), dev)
+    ds.gen_args.modality_probs.HCP.T1 = 0.5
+    ds.input_prob = vars(ds.gen_args.modality_probs)
+    np.random.seed(3)
+    idxs = list(range(bench.BATCH))
+    n_real = 0
+    for _ in range(5):
+        ds.generate_batch(idxs)
+    assert ds._native is not None
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        items = ds.generate_batch(idxs)
+        n_real += sum(1 for it in items if it[2] != 'synth')
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(json.dumps({"config": "BaseGen batch 8x160^3, real T1 input with probability 0.5", "ms_per_step": ms,
+                      "samples_per_s": bench.BATCH / ms * 1e3, "real_fraction": n_real / (steps * bench.BATCH),
+                      "planner": "native"}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["interpol", "shapeid", "brainid"]
+    which = sys.argv[1:] or ["interpol", "shapeid", "brainid", "realmix"]
+    if "realmix" in which:
+        realmix_cfg()
     if "brainid" in which:
         brainid_cfg()
     if "interpol" in which:
