@@ -330,12 +330,14 @@ def main():
     # (brainfm_b200.pipeline.HostPipeline): the upload of step k+1 and the download of step k-1 overlap the
     # generation of step k, so consecutive steps alternate between two sets of 8 subjects.
     from brainfm_b200.pipeline import HostPipeline
-    host_lab = [torch.from_numpy(s["Gen"].astype(np.uint8)).pin_memory() for s in subs]
-    host_t1 = [torch.from_numpy(s["T1"]).pin_memory() for s in subs]
+    # host side of a step: one pinned (8, 160^3) uint8 label batch and one pinned (8, 160^3) float32 T1 batch (what a
+    # collating loader hands over); each is ONE host->device DMA, the results come back as one (8, 1, 160^3) DMA
     sets = [list(range(0, BATCH)), list(range(BATCH, 2 * BATCH))]
-    uploads = [[u for s in st for u in ((ds.names[0][s][:-7] + "generation_labels.nii", "gen", host_lab[s]),
-                                        (ds.names[0][s], "f32", host_t1[s]))] for st in sets]
-    h2d = sum(t.numel() * t.element_size() for t in host_lab[:BATCH]) + sum(t.numel() * 4 for t in host_t1[:BATCH])
+    host_lab = [torch.from_numpy(np.stack([subs[s]["Gen"].astype(np.uint8) for s in st])).pin_memory() for st in sets]
+    host_t1 = [torch.from_numpy(np.stack([subs[s]["T1"] for s in st])).pin_memory() for st in sets]
+    uploads = [[([ds.names[0][s][:-7] + "generation_labels.nii" for s in st], "gen", host_lab[q]),
+                ([ds.names[0][s] for s in st], "f32", host_t1[q])] for q, st in enumerate(sets)]
+    h2d = host_lab[0].numel() * host_lab[0].element_size() + host_t1[0].numel() * host_t1[0].element_size()
     d2h = BATCH * SIZE ** 3 * 4
     pipe = HostPipeline(ds, depth=3)
 
@@ -348,7 +350,23 @@ def main():
         for t in tickets:
             t.wait()
 
+    # warm-up of the end-to-end arm (untimed): the first passes on a fresh box run at a fraction of the steady PCIe
+    # rate (first touch of ~0.8 GB of pinned memory, link and clock ramp-up), so keep going until two consecutive
+    # blocks of 8 steps agree within 5 % (at most ~4 s)
     e2e_run(4)
+    prev, t_begin, series = None, time.perf_counter(), []
+    while time.perf_counter() - t_begin < 4.0:
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        e2e_run(8)
+        torch.cuda.synchronize()
+        cur = (time.perf_counter() - w0) / 8
+        series.append(round(1e3 * cur, 3))
+        if prev is not None and abs(cur - prev) <= 0.05 * prev and len(series) >= 3:
+            break
+        prev = cur
+    if rank == 0:
+        print("e2e warm-up ms/step per block of 8: %s" % series, file=sys.stderr, flush=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -582,6 +582,7 @@ class BaseGen(Dataset):
             # key order of the reference's sample dict (datasets.py:345-352)
             results.append({k: sample[k] for k in ('high_res_residual', 'input', 'bias_field_log') if k in sample})
         self._keep = keep
+        self._last_out = out
         return descs, results
 
     def _run_chain(self, jobs, arena, targets_fn=None, timers=None):

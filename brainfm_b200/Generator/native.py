@@ -331,6 +331,7 @@ class NativePlanner:
         self.last = dict(descs=descs, descs_dev=d_dev, info=info, total=total, keep=(out, bfl, res, aux_all, keep),
                          arena_slot=arena.cur)
         ds._last_descs = (descs, d_dev, total)
+        ds._last_out = out
         return tuples
 
     def _deform_dict(self, ctx, desc, inf, arena):

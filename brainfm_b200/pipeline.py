@@ -8,6 +8,7 @@ their sum (PCIe is full duplex; the copy engines run beside the SMs).
 
     pipe = HostPipeline(ds)
     t = pipe.submit(indices, uploads=[(path, kind, pinned_host_tensor), ...])   # asynchronous
+    #   or batched: uploads=[([path0, path1, ...], kind, pinned (n, *shape) tensor)] -- one DMA per kind
     ...
     items, host_out = t.wait()      # host_out: pinned (B, 1, *size) float32 'input' volumes
 
@@ -39,6 +40,20 @@ class HostPipeline:
         self._slot_events = []           # download event of the last use of each slot
         self._next = 0
         self._last_reader = {}           # (path, kind) -> event of the last batch that read the volume
+        self._stages = {}                # batched-upload staging buffers on the device
+
+    def _stage(self, kind, host):
+        """Device staging buffer of a batched upload: a ring of two per (kind, shape), so that the DMA of step k+1 can
+        run while the device-to-device copies of step k (compute stream) still read the other one."""
+        key = (kind, tuple(host.shape), host.dtype)
+        ring = self._stages.get(key)
+        if ring is None:
+            ring = {"next": 0, "slots": [{"buf": torch.empty(host.shape, dtype=host.dtype, device=self.device),
+                                          "free": None} for _ in range(2)]}
+            self._stages[key] = ring
+        slot = ring["slots"][ring["next"]]
+        ring["next"] ^= 1
+        return slot["buf"], slot
 
     def _slot(self, shape):
         if not self._slots:
@@ -58,37 +73,71 @@ class HostPipeline:
         ds = self.ds
         main = torch.cuda.current_stream(self.device)
         # 1. uploads on the copy-in stream (after the last reader of each destination volume)
+        flat = []                                         # (path, kind) of every uploaded volume
+        staged = []                                       # batched uploads: (paths, kind, staging buffer, slot)
         if uploads:
             with torch.cuda.stream(self.copy_in):
                 for path, kind, host in uploads:
-                    ev = self._last_reader.get((path, kind))
-                    if ev is not None:
-                        self.copy_in.wait_event(ev)
-                    ds.cache.upload(path, kind, host)     # copies only: the copy stream never waits for an SM
+                    if isinstance(path, (list, tuple)):
+                        # batched host buffer (len(paths), *volume shape): ONE host->device DMA into a staging buffer
+                        # on the copy stream (nothing else is queued there, so the copy engine never idles between
+                        # steps); the device-to-device copies into the cached volumes follow on the compute stream.
+                        # With one DMA per volume the engine idles 40-50 us between copies whenever the download
+                        # direction is busy too.
+                        stage, slot = self._stage(kind, host)
+                        if slot["free"] is not None:
+                            self.copy_in.wait_event(slot["free"])     # device copies of two steps ago are done
+                        stage.copy_(host, non_blocking=True)
+                        staged.append((list(path), kind, stage, slot))
+                        flat += [(p, kind) for p in path]
+                    else:
+                        ev = self._last_reader.get((path, kind))
+                        if ev is not None:
+                            self.copy_in.wait_event(ev)
+                        ds.cache.upload(path, kind, host)     # copies only: the copy stream never waits for an SM
+                        flat.append((path, kind))
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.copy_in)
             main.wait_event(ev_in)
-            for path, kind, _ in uploads:
-                ds.cache.sanitize(path, kind)             # nan_to_num on the compute stream
+            for paths, kind, stage, slot in staged:       # compute stream: ordered after the previous batch's reads
+                for p, part in zip(paths, stage.unbind(0)):
+                    ds.cache.upload(p, kind, part)
+                slot["free"] = torch.cuda.Event()
+                slot["free"].record(main)
+            for p, kind in flat:
+                ds.cache.sanitize(p, kind)                # nan_to_num on the compute stream
         # 2. generation on the caller's stream
         items = ds.generate_batch(list(indices))
         ev_done = torch.cuda.Event()
         ev_done.record(main)
-        for path, kind, _ in uploads:
-            self._last_reader[(path, kind)] = ev_done
+        for key in flat:
+            self._last_reader[key] = ev_done
         # 3. download on the copy-out stream
         outs = [it[4][self.key] if not isinstance(it[4], list) else torch.cat([s[self.key] for s in it[4]], 0)
                 for it in items]
         shape = (sum(o.shape[0] for o in outs), *outs[0].shape[1:])
         k = self._slot(shape)
         host = self._slots[k]
+        whole = getattr(ds, '_last_out', None) if self.key == 'input' else None
+        if whole is not None:
+            n = 1
+            for v in shape:
+                n *= int(v)
+            if whole.numel() != n or not whole.is_contiguous() or whole.data_ptr() != outs[0].data_ptr():
+                whole = None
+            else:
+                whole = whole.view(shape)
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(ev_done)
-            row = 0
-            for o in outs:
-                host[row:row + o.shape[0]].copy_(o, non_blocking=True)
-                o.record_stream(self.copy_out)
-                row += o.shape[0]
+            if whole is not None:                         # the batch's volumes are one tensor: one DMA
+                host.copy_(whole, non_blocking=True)
+                whole.record_stream(self.copy_out)
+            else:
+                row = 0
+                for o in outs:
+                    host[row:row + o.shape[0]].copy_(o, non_blocking=True)
+                    o.record_stream(self.copy_out)
+                    row += o.shape[0]
             ev_out = torch.cuda.Event()
             ev_out.record(self.copy_out)
         self._slot_events[k] = ev_out

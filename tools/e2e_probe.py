@@ -51,11 +51,18 @@ def main():
     ds = bench.build_dataset(subs, dev)
     np.random.seed(1000)
     torch.manual_seed(1000)
-    host_lab = [torch.from_numpy(s["Gen"].astype(np.uint8)).pin_memory() for s in subs]
-    host_t1 = [torch.from_numpy(s["T1"]).pin_memory() for s in subs]
     sets = [list(range(0, B)), list(range(B, 2 * B))]
-    uploads = [[u for s in st for u in ((ds.names[0][s][:-7] + "generation_labels.nii", "gen", host_lab[s]),
-                                        (ds.names[0][s], "f32", host_t1[s]))] for st in sets]
+    if "--per-volume" in sys.argv:      # one DMA per volume (16 per step) instead of one per kind (2 per step)
+        host_lab = [torch.from_numpy(s["Gen"].astype(np.uint8)).pin_memory() for s in subs]
+        host_t1 = [torch.from_numpy(s["T1"]).pin_memory() for s in subs]
+        uploads = [[u for s in st for u in ((ds.names[0][s][:-7] + "generation_labels.nii", "gen", host_lab[s]),
+                                            (ds.names[0][s], "f32", host_t1[s]))] for st in sets]
+    else:
+        host_lab = [torch.from_numpy(np.stack([subs[s]["Gen"].astype(np.uint8) for s in st])).pin_memory()
+                    for st in sets]
+        host_t1 = [torch.from_numpy(np.stack([subs[s]["T1"] for s in st])).pin_memory() for st in sets]
+        uploads = [[([ds.names[0][s][:-7] + "generation_labels.nii" for s in st], "gen", host_lab[q]),
+                    ([ds.names[0][s] for s in st], "f32", host_t1[q])] for q, st in enumerate(sets)]
     pipe = HostPipeline(ds, depth=3)
     if "--trace" in sys.argv:
         from torch.profiler import profile, ProfilerActivity
