@@ -237,9 +237,19 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the communicator comes up: send fd 1 to stderr meanwhile, so
+        # that stdout carries nothing but the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from brainfm_b200 import _lib
     n_subjects = 2 * BATCH          # the end-to-end arm alternates between two sets of subjects
