@@ -194,6 +194,30 @@ def config_dict():
                    "fields: in-kernel Philox4x32-10"}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned host buffers of the end-to-end
+    arm (first touch) and the planner live next to the GPU's PCIe root.  Returns the node, or None if unknown."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def build_dataset(subs, device, planner="auto"):
     from brainfm_b200 import io as bio
@@ -235,6 +259,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("BFM_NO_NUMA_BIND") else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when the communicator comes up: send fd 1 to stderr meanwhile, so
