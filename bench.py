@@ -259,7 +259,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("BFM_NO_NUMA_BIND") else None
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("BFM_NUMA_BIND") else None   # opt-in
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when the communicator comes up: send fd 1 to stderr meanwhile, so
