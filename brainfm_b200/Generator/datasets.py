@@ -850,6 +850,8 @@ class BaseGen(Dataset):
         if ok:
             if self._native is None:
                 self._native = NativePlanner(self)
+            else:
+                self._native.refresh()
             for idx in indices:
                 _, input_prob, t1_path, _ = self.idx_to_path(int(idx))
                 if not self._native.item_ok(input_prob, self.get_info(t1_path)):

@@ -36,7 +36,32 @@ class NativePlanner:
         self.seed = None
         self._keep = []
         self.cfg = self._build_cfg()
+        self._fp = self.fingerprint()
         self.last = None
+
+    _KEYS = ('photo_prob', 'pathology_prob', 'random_shape_prob', 'flip_prob', 'max_rotation', 'max_shear',
+             'max_scaling', 'nonlin_scale_min', 'nonlin_scale_max', 'nonlin_std_max', 'ct_prob', 'low_res_only',
+             'nonlinear_transform')
+
+    def fingerprint(self):
+        """The parameter values the cached bfm_plan_cfg was built from; `refresh()` rebuilds it when the caller has
+        changed gen_args since (curricula, update_gen_args with new values)."""
+        ds = self.ds
+        a = ds.synth_args
+        fp = [getattr(a, k) for k in self._KEYS] + [ds.gen_args.mix_synth_prob, tuple(ds.size)]
+        for mode in ('synth', 'T1'):
+            for overrides in ds._gen_arg_sets(mode):
+                for o in overrides:
+                    fp.append(tuple(sorted(vars(o).items())))
+        base = vars(ds.gen_args.generator)
+        fp += [base[f] for f in ('gamma_std', 'bf_scale_min', 'bf_scale_max', 'bf_std_min', 'bf_std_max')]
+        return fp
+
+    def refresh(self):
+        fp = self.fingerprint()
+        if fp != self._fp:
+            self.cfg = self._build_cfg()
+            self._fp = fp
 
     # ---- eligibility ------------------------------------------------------------------------------
     @staticmethod

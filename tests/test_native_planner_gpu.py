@@ -191,3 +191,17 @@ def test_native_mode_draws_real_inputs():
             assert descs[q].real_input == (1 if it[2] == 'T1' else 0)
     assert set(modes) == {'synth', 'T1'}
     assert 0.25 < modes.count('T1') / len(modes) < 0.75
+
+
+def test_native_planner_follows_changed_gen_args():
+    """The cached bfm_plan_cfg is rebuilt when the caller changes generator parameters between batches."""
+    ds = _native_dataset()
+    np.random.seed(2)
+    ds.generate_batch([0, 1, 2, 3])
+    assert any(ds._native.last['descs'][q].gamma != 1.0 for q in range(4))
+    ds.gen_args.generator.gamma_std = 0.0
+    ds.gen_args.generator.flip_prob = -100.0          # randn() < -100 never holds
+    ds.generate_batch([0, 1, 2, 3])
+    torch.cuda.synchronize()
+    for q in range(4):
+        assert ds._native.last['descs'][q].gamma == 1.0 and ds._native.last['descs'][q].flip == 0
