@@ -412,7 +412,10 @@ class BaseGen(Dataset):
                 p['mix'] = v
         # gamma
         p['gamma'] = np.float32(np.exp(cfg.gamma_std * rng.randn1("gamma.n")))
-        # bias field
+        # bias field (none for CT inputs, utils.py:575-577)
+        if real == 'CT':
+            p['bfsmall'], p['bf_shape'] = None, None
+            return self._plan_tail(p, setups, cfg, rng, size)
         bf_scale = cfg.bf_scale_min + float(rng.rand1("bf.scale")[0]) * (cfg.bf_scale_max - cfg.bf_scale_min)
         small = [int(round(bf_scale * n)) for n in size]                    # np.round: half to even, like round()
         if setups['photo_mode']:
@@ -425,6 +428,9 @@ class BaseGen(Dataset):
             bf = rng.torch_randn("bf.field", small)
         p['bfsmall'] = bf.mul_(std).numpy()                                  # float32(std) * randn, in float32
         p['bf_shape'] = small
+        return self._plan_tail(p, setups, cfg, rng, size)
+
+    def _plan_tail(self, p, setups, cfg, rng, size):
         # resample
         res = self.res_training_data
         stds = (0.85 + 0.3 * rng.rand("rs.u")) * np.log(5) / np.pi * setups['thickness'] / res
@@ -487,7 +493,7 @@ class BaseGen(Dataset):
             s.d = plan.struct
             if p.get('real'):
                 # the warp gathers straight from the cached (finite, padded) real volume; nothing is synthesised
-                s.real_input = 1
+                s.real_input = 2 if p['real'] == 'CT' else 1
                 s.syn = job['real_vol'].data_ptr()
             else:
                 lab = job['labels']
@@ -510,9 +516,10 @@ class BaseGen(Dataset):
                     s.mixw[q] = float(p['mix'][q])
             s.gamma = float(p['gamma'])
             bfs = p['bfsmall']
-            s.bfsmall = p['bfsmall_dev'] if 'bfsmall_dev' in p else arena.put(bfs)
-            s.bs[:] = bfs.shape
-            s.btab = tables.zoom_tab(bfs.shape, size)
+            if bfs is not None:
+                s.bfsmall = p['bfsmall_dev'] if 'bfsmall_dev' in p else arena.put(bfs)
+                s.bs[:] = bfs.shape
+                s.btab = tables.zoom_tab(bfs.shape, size)
             s.i_bf = p_ibf + 4 * b * N
             sample = {}
             if job['want_bflog']:
@@ -654,6 +661,8 @@ class BaseGen(Dataset):
         return self._hemis[key]
 
     def _want_bflog(self, input_mode):
+        if input_mode == 'CT':                          # no bias field on CT (utils.py:575-577, datasets.py:351)
+            return False
         if self.write_bflog is not None:
             return bool(self.write_bflog)
         return 'bias_field' in self.tasks and input_mode != 'CT'
@@ -878,13 +887,14 @@ class BaseGen(Dataset):
         return self.datasets_num, ctx['dataset_name'], ctx['input_mode'], target, sample
 
     def _fast_ok(self, input_mode, src_shape=None):
-        """Fused chain: synthetic inputs, and real T1 / T2 / FLAIR inputs (CT has its own window and no bias field)
-        whose volume has the shape of the deformation's source grid, with the stock augmentation chain."""
+        """Fused chain: synthetic inputs, and real T1 / T2 / FLAIR / CT inputs whose volume has the shape of the
+        deformation's source grid, with the stock augmentation chain."""
         if 'pathology' in self.tasks:
             return False
         if input_mode == 'synth':
             return self._stock_chain('synth')
-        if input_mode not in ('T1', 'T2', 'FLAIR') or self.hemis_mask is not None or not self._stock_chain(input_mode):
+        if input_mode not in ('T1', 'T2', 'FLAIR', 'CT') or self.hemis_mask is not None or \
+                not self._stock_chain(input_mode):
             return False
         vol = self.cache.get(self.modalities[input_mode], 'f32')
         return src_shape is None or list(vol.shape[:3]) == [int(v) for v in src_shape[:3]]
@@ -918,7 +928,8 @@ class BaseGen(Dataset):
                 for a in arg_sets:
                     self.update_gen_args(a)
                 jobs.append(self._job(ctx['setups'], ctx['deform'], ctx['target'],
-                                      self._plan_synth(ctx['setups'], ctx['target'], arena, real=mode != 'synth'),
+                                      self._plan_synth(ctx['setups'], ctx['target'], arena,
+                                                       real=mode if mode != 'synth' else False),
                                       mode))
             spans.append((first, len(jobs)))
             aux = self._fused_image_targets(ctx, jobs[first:])

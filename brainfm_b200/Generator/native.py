@@ -2,8 +2,8 @@
 
 `BaseGen.generate_batch` plans every item in Python (draws from the numpy/torch global generators in the
 reference's order, ~250 us per sample).  When nothing in the configuration needs Python per sample -- synthetic or
-real T1 / T2 / FLAIR inputs (drawn per item like read_input), stock augmentation chain, no mixing with real
-modalities, no CT input, no pathology / surface task, no random shift -- the whole batch is planned by ONE call into
+real T1 / T2 / FLAIR / CT inputs (drawn per item like read_input), stock augmentation chain, no mixing with real
+modalities, no pathology / surface task, no random shift -- the whole batch is planned by ONE call into
 the library instead: the same arithmetic in C, draws from an in-library Philox stream keyed on (seed, item counter)
 (the seed itself is one draw of numpy's global generator, so `np.random.seed` still makes a run reproducible), small
 random grids drawn on the device.
@@ -78,16 +78,13 @@ class NativePlanner:
         return True
 
     def item_ok(self, input_prob, modalities):
-        """Inputs the library plans: synthetic, and real T1 / T2 / FLAIR volumes of the label map's shape.  A subject
-        whose CT can be drawn as the input (datasets.py:581-583) is planned in Python."""
+        """Inputs the library plans: synthetic, and real T1 / T2 / FLAIR / CT volumes of the label map's shape."""
         ds = self.ds
-        if input_prob.get('CT', 0) > 0 and 'CT' in modalities:
-            return False
-        if any(input_prob.get(m, 0) > 0 and m in modalities for m in ('T1', 'T2', 'FLAIR')):
+        if any(input_prob.get(m, 0) > 0 and m in modalities for m in ('T1', 'T2', 'FLAIR', 'CT')):
             if not ds._stock_chain('real'):
                 return False
             shape = list(ds.cache.get(modalities['Gen'], 'gen').shape[:3])
-            for m in ('T1', 'T2', 'FLAIR'):
+            for m in ('T1', 'T2', 'FLAIR', 'CT'):
                 if input_prob.get(m, 0) > 0 and m in modalities and \
                         list(ds.cache.get(modalities[m], 'f32').shape[:3]) != shape:
                     return False
@@ -182,7 +179,8 @@ class NativePlanner:
             for q, m in enumerate(('T1', 'T2', 'FLAIR')):
                 if m in mods and input_prob.get(m, 0) > 0:
                     it.real_vol[q] = ds.cache.get(mods[m], 'f32').data_ptr()
-            it.has_ct = int('CT' in mods)
+            if 'CT' in mods and input_prob.get('CT', 0) > 0:
+                it.ct_vol = ds.cache.get(mods['CT'], 'f32').data_ptr()
             aux = ds._fused_aux_volumes(mods, src)
             it.n_aux = len(aux)
             for c, (key, vol) in enumerate(aux):
@@ -276,7 +274,7 @@ class NativePlanner:
                       'photo_mode': bool(inf.photo_mode), 'pathol_mode': False, 'pathol_random_shape': False,
                       'spac': inf.spac if inf.photo_mode else None, 'flip': bool(inf.flip), 'hemis': 'both'}
             ctxs.append(dict(idx=idx, dataset_name=dataset_name, case_name=_case_name(t1_path),
-                             input_mode=('synth', 'T1', 'T2', 'FLAIR')[inf.input_mode],
+                             input_mode=('synth', 'T1', 'T2', 'FLAIR', 'CT')[inf.input_mode],
                              age=age, setups=setups, modalities=mods, aux=aux, src=src, n=n))
         need_plans = other_targets or any(len(c['aux']) < sum(1 for k in ('T1', 'T2', 'FLAIR') if k in c['modalities'])
                                           for c in ctxs)
@@ -341,7 +339,7 @@ class NativePlanner:
             if res_v is not None:
                 s['high_res_residual'] = res_v[q_]
             s['input'] = out_v[q_]
-            if bfl_v is not None:
+            if bfl_v is not None and info[q_ // ns].input_mode != 4:      # no bias field on CT inputs
                 s['bias_field_log'] = bfl_v[q_]
             results.append(s)
         tuples = []

@@ -77,7 +77,7 @@ class PlanItem(C.Structure):
     _fields_ = [("labels", c_p), ("label_is_u8", c_i), ("src", c_i * 3), ("n_aux", c_i),
                 ("aux_src", c_p * MAX_AUX), ("aux_out", c_p * MAX_AUX), ("aux_raw", c_p * MAX_AUX),
                 ("eps_gmm", c_p * PLAN_MAX_SAMPLES), ("eps_noise", c_p * PLAN_MAX_SAMPLES),
-                ("input_prob", c_d * 4), ("real_vol", c_p * 3), ("has_ct", c_i)]
+                ("input_prob", c_d * 4), ("real_vol", c_p * 3), ("ct_vol", c_p)]
 
 
 class PlanOut(C.Structure):

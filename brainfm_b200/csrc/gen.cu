@@ -524,7 +524,7 @@ __device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B
     const float *__restrict__ mix0 = s.mix[0], *__restrict__ mix1 = s.mix[1], *__restrict__ mix2 = s.mix[2];
     const float mw0 = s.mixw[0], mw1 = s.mixw[1], mw2 = s.mixw[2], mw3 = s.mixw[3];
     const float gamma = s.gamma;
-    const bool real_in = s.real_input != 0;
+    const int real_in = s.real_input;
     float *__restrict__ i_bf = s.i_bf;
     float *__restrict__ bfl = bw ? s.bflog_out : nullptr;
     const float *__restrict__ asrc[NAUX > 0 ? NAUX : 1];
@@ -622,7 +622,8 @@ __device__ __forceinline__ void warp_rows(WarpShared &sh, float *t1F, float *t1B
                         if (mix1) v = __fadd_rn(v, __fmul_rn(mw2, mix1[pr]));
                         if (mix2) v = __fadd_rn(v, __fmul_rn(mw3, mix2[pr]));
                     }
-                    if (!real_in) v = fmaxf(v, 0.f);                  // datasets.py:411 (synthetic images only)
+                    if (real_in == 0) v = fmaxf(v, 0.f);              // datasets.py:411 (synthetic images only)
+                    else if (real_in == 2) v = fminf(fmaxf(v, 0.f), 80.f);   // CT window (datasets.py:318-319)
                     // gamma: 300 * (I/300) ** gamma                  utils.py:568-572
                     v = 300.f * fast_pow(v * (1.f / 300.f), gamma);
                     // bias field: I * exp(zoom(BFsmall))             utils.py:574-589

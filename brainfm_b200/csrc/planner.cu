@@ -167,8 +167,7 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         if (u < it.input_prob[0] && it.real_vol[0]) mode = 1;
         else if (u < it.input_prob[1] && it.real_vol[1]) mode = 2;
         else if (u < it.input_prob[2] && it.real_vol[2]) mode = 3;
-        else if (u < it.input_prob[3] && it.has_ct)
-            return fail(BFM_E_UNSUPPORTED, "%s", "bfm_plan_batch: CT inputs are not planned natively");
+        else if (u < it.input_prob[3] && it.ct_vol) mode = 4;
     }
     info.input_mode = mode;
     // ---- get_setup_params (datasets.py:466-493)
@@ -269,8 +268,8 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         if (mode) {
             // real-image input (augment_sample, datasets.py:306-336): gather straight from the volume; no contrast,
             // no GMM noise, no mixing draw
-            s.real_input = 1;
-            s.syn = const_cast<float *>(it.real_vol[mode - 1]);
+            s.real_input = mode == 4 ? 2 : 1;
+            s.syn = const_cast<float *>(mode == 4 ? it.ct_vol : it.real_vol[mode - 1]);
         } else {
         s.labels = it.labels;
         s.label_is_u8 = it.label_is_u8;
@@ -323,12 +322,14 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         }
         // ---- gamma (utils.py:568-572)
         s.gamma = (float)std::exp(ag.gamma_std * dr.randn());
-        // ---- bias field (utils.py:574-585)
+        // ---- bias field (utils.py:574-585); none for CT inputs (utils.py:575-577)
+        float bf_std = 0.f;
+        if (mode != 4) {
         const double bscale = ag.bf_scale_min + dr.rand() * (ag.bf_scale_max - ag.bf_scale_min);
         int bs[3];
         for (int a = 0; a < 3; ++a) bs[a] = (int)round_half_even(bscale * size[a]);
         if (st.photo) bs[1] = (int)round_half_even(size[1] / st.spac);
-        const float bf_std = (float)(ag.bf_std_min + (ag.bf_std_max - ag.bf_std_min) * dr.rand());
+        bf_std = (float)(ag.bf_std_min + (ag.bf_std_max - ag.bf_std_min) * dr.rand());
         for (int a = 0; a < 3; ++a) {
             if (bs[a] < 1 || bs[a] > size[a] || !cfg.fwd[a][bs[a]].valid)
                 return failf(BFM_E_UNSUPPORTED, "bfm_plan_batch: no zoom table for the %d -> %d bias grid", bs[a], size[a]);
@@ -344,7 +345,8 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
             for (int64_t q = 0; q < n; ++q) bf[q] = dr.randf() * bf_std;
             s.bfsmall = (const float *)(ar.dev + off);
         }
-        s.gen_small = native ? ((k == 0 && cfg.nonlinear_transform ? 1 : 0) | 2) : 0;
+        }
+        s.gen_small = native ? ((k == 0 && cfg.nonlinear_transform ? 1 : 0) | (mode != 4 ? 2 : 0)) : 0;
         s.fs_std = fs_std;
         s.bf_std = bf_std;
         // ---- resample (utils.py:591-609)
@@ -396,7 +398,7 @@ int plan_item(const bfm_plan_cfg &cfg, const bfm_plan_item &it, const bfm_plan_o
         s.flip = st.flip;
         if (!mode) s.syn = o.syn;
         s.i_bf = o.i_bf; s.tmp[0] = o.tmp[0]; s.tmp[1] = o.tmp[1]; s.lowres = o.lowres;
-        s.out = o.out; s.bflog_out = o.bflog_out; s.residual = o.residual;
+        s.out = o.out; s.bflog_out = mode == 4 ? nullptr : o.bflog_out; s.residual = o.residual;
         if (k == 0) {
             s.n_aux = it.n_aux;
             for (int c = 0; c < it.n_aux; ++c) {
@@ -465,7 +467,7 @@ extern "C" int bfm_plan_batch(const bfm_plan_cfg *cfg, int n_items, const bfm_pl
                 else
                     s.d.fsmall = descs_host[q - q % ns].d.fsmall;      // one deformation per item
             }
-            s.bfsmall = (const float *)(ar.dev + ar.take(4 * (int64_t)s.bs[0] * s.bs[1] * s.bs[2]));
+            if (s.bs[0] > 0) s.bfsmall = (const float *)(ar.dev + ar.take(4 * (int64_t)s.bs[0] * s.bs[1] * s.bs[2]));
         }
         if (q % ns != 0) {                                             // samples of an item share the deformation:
             s.bbox = descs_host[q - q % ns].bbox;                      // one bounding box

@@ -232,7 +232,8 @@ typedef struct bfm_gen_sample {
     /* Real-image input (BaseGen.augment_sample with input_mode T1 / T2 / FLAIR, Generator/datasets.py:306-316): `syn`
        is the real source volume itself (f32, finite, followed by >= src[1]*src[2]+src[2]+1 readable floats, never
        written), the GMM stage is skipped (labels / mu / sigma may be NULL) and the warped value is NOT clamped at 0
-       before the gamma transform. */
+       before the gamma transform.  2 = CT input: the warped value is clamped to [0, 80] (datasets.py:318-319) and
+       there is no bias field (bfsmall == NULL, Generator/utils.py:575-577). */
     int real_input;
 } bfm_gen_sample;
 
@@ -313,11 +314,11 @@ typedef struct bfm_plan_item {
     const float *eps_noise[BFM_PLAN_MAX_SAMPLES];
     /* read_input (Generator/datasets.py:563-588): the input is the first of T1, T2, FLAIR, CT with u < input_prob[m]
        whose volume exists, else synthetic.  real_vol[m]: device volume of T1 / T2 / FLAIR with the source shape
-       (f32, finite, padded like aux_src) or NULL when the subject does not have it; has_ct != 0 makes a CT draw
-       fail with BFM_E_UNSUPPORTED (CT inputs are planned in Python). */
+       (f32, finite, padded like aux_src) or NULL when the subject does not have it; ct_vol likewise for CT
+       (window [0, 80], no bias field, no bias_field_log output). */
     double input_prob[4];
     const float *real_vol[3];
-    int has_ct;
+    const float *ct_vol;
 } bfm_plan_item;
 
 typedef struct bfm_plan_out {       /* per SAMPLE buffers (device), caller allocated */
@@ -326,7 +327,7 @@ typedef struct bfm_plan_out {       /* per SAMPLE buffers (device), caller alloc
 } bfm_plan_out;
 
 typedef struct bfm_plan_info {      /* what the host needs to know about a planned ITEM */
-    int input_mode;                 /* 0 synth, 1 T1, 2 T2, 3 FLAIR */
+    int input_mode;                 /* 0 synth, 1 T1, 2 T2, 3 FLAIR, 4 CT */
     int photo_mode, flip;
     double spac, resolution[3], thickness[3], scaling_factor_distances;
     float A[9], c2[3];

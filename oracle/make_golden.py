@@ -64,6 +64,7 @@ CASES = {
                        "default", 2),
     "g64_realT2_s15": (64, 96, "brain", 15, {"modality_probs.HCP.T2": 1.0, "task.T1": True, "task.T2": True},
                        ["T2"], "default", 2),
+    "g64_realCT_s16": (64, 96, "brain", 16, {"modality_probs.HCP.CT": 1.0, "task.CT": True}, ["CT"], "default", 2),
     # left hemisphere only: photo mode forced, no flip, source masked by (left label) & (MNI x < 0), left label list
     "g64_left_s9": (64, 96, "brain", 9, {"generator.left_hemis_only": True, "task.segmentation": True,
                                          "task.distance": True, "task.registration": True},

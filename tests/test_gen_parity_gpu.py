@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g64_full_s4", "g160_s0", "g64_pathol_s7",
-         "g64_pathol_s12", "g64_left_s9", "g64_ident_s23", "g64_realT1_s14", "g64_realT2_s15"]
+         "g64_pathol_s12", "g64_left_s9", "g64_ident_s23", "g64_realT1_s14", "g64_realT2_s15", "g64_realCT_s16"]
 
 
 def _compare(ref, got, name):
@@ -60,7 +60,7 @@ def test_brainid_batch_matches_oracle():
 
 
 @pytest.mark.parametrize("name", ["g64_s0", "g64_full_s4", "g160_s0", "g64_pathol_s7", "g64_left_s9", "g64_ident_s23", "g64_realT1_s14",
-                                  "g64_realT2_s15"])
+                                  "g64_realT2_s15", "g64_realCT_s16"])
 def test_chain_matches_reference_fixture(name):
     """Directly against the fixture the unmodified reference produced (strided sub-sample + sums)."""
     gold = np.load(os.path.join(GOLD, name + ".npz"))
@@ -162,12 +162,12 @@ def test_full_bbox_scan_equals_candidate_result(name):
     assert bb[:6].tolist() == want
 
 
-@pytest.mark.parametrize("name,mode", [("g64_realT1_s14", "T1"), ("g64_realT2_s15", "T2")])
+@pytest.mark.parametrize("name,mode", [("g64_realT1_s14", "T1"), ("g64_realT2_s15", "T2"), ("g64_realCT_s16", "CT")])
 def test_real_inputs_take_the_fused_chain(name, mode):
     """Real T1 / T2 / FLAIR inputs run through the fused chain (real_input descriptors, no GMM stage), not op by op."""
     item, orc = oracle_case(name)
     got, ds, draws = cuda_case(name, orc.log, planner='python')
     assert got[2] == mode == item[2]
     descs, _, B = ds._last_descs
-    assert B == 1 and descs[0].real_input == 1 and descs[0].labels is None
+    assert B == 1 and descs[0].real_input == (2 if mode == 'CT' else 1) and descs[0].labels is None
     _compare(mg.flatten(item), mg.flatten(got), name)

@@ -51,7 +51,7 @@ def make_cfg(size, gen, mix=0.0, aug_sets=None, real_sets=None):
 
 
 def plan(cfg, n_items, src, seed=1, counter=0, replay=None, capacity=1 << 20, input_prob=None, real_vol=None,
-         has_ct=0):
+         ct_vol=0):
     L = _lib.lib()
     ns = cfg.n_samples
     items = (_lib.PlanItem * n_items)()
@@ -61,7 +61,7 @@ def plan(cfg, n_items, src, seed=1, counter=0, replay=None, capacity=1 << 20, in
         if input_prob is not None:
             it.input_prob[:] = input_prob
             it.real_vol[:] = real_vol
-            it.has_ct = has_ct
+            it.ct_vol = ct_vol
     outs = (_lib.PlanOut * (n_items * ns))()
     for o in outs:
         o.out = o.syn = o.i_bf = o.lowres = FAKE
@@ -224,7 +224,17 @@ def test_real_input_modes_are_drawn_like_read_input():
     frac = counts / counts.sum()
     assert counts[2] == 0                                    # no T2 volume: never drawn
     assert abs(frac[1] - 0.25) < 0.05 and abs(frac[3] - 0.5) < 0.06 and abs(frac[0] - 0.25) < 0.05
-    # a CT draw is refused (planned in Python)
-    with pytest.raises(NotImplementedError):
-        for rep in range(50):
-            plan(cfg, 8, [64] * 3, seed=3, counter=8 * rep, input_prob=[0, 0, 0, 0.9], real_vol=[0, 0, 0], has_ct=1)
+    # CT inputs: window flag, no bias grid, no bias_field_log output
+    n_ct = 0
+    for rep in range(20):
+        r = plan(cfg, 8, [64] * 3, seed=3, counter=8 * rep, input_prob=[0, 0, 0, 0.9], real_vol=[0, 0, 0],
+                 ct_vol=FAKE + 0x5000)
+        for q in range(8):
+            inf, s = r['info'][q], r['descs'][q]
+            if inf.input_mode == 4:
+                n_ct += 1
+                assert s.real_input == 2 and s.syn == FAKE + 0x5000 and not s.bfsmall and not s.bflog_out
+                assert list(s.bs) == [0, 0, 0] and s.gen_small in (0, 1)
+            else:
+                assert inf.input_mode == 0 and s.bfsmall
+    assert 0.8 < n_ct / 160 < 0.98

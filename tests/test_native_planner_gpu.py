@@ -14,7 +14,7 @@ from tests.test_gen_parity_gpu import _compare
 pytestmark = pytest.mark.gpu
 
 CASES = ["g64_s0", "g64_s1", "g64_s2", "g64_s3", "g64_s5_lowres", "g160_s0", "g64_ident_s23", "g64_realT1_s14",
-         "g64_realT2_s15"]
+         "g64_realT2_s15", "g64_realCT_s16"]
 
 
 def _read(ds, ptr, n, dtype):
@@ -48,7 +48,7 @@ def test_replayed_native_plan_equals_python_plan(name):
         nf = s.d.fs[0] * s.d.fs[1] * s.d.fs[2] * 3
         py.append((_scalars(s), None if s.real_input else _read(ds_py, s.mu, 512, torch.float32),
                    _read(ds_py, s.d.fsmall, nf, torch.float32),
-                   _read(ds_py, s.bfsmall, s.bs[0] * s.bs[1] * s.bs[2], torch.float32)))
+                   _read(ds_py, s.bfsmall, s.bs[0] * s.bs[1] * s.bs[2], torch.float32) if s.bfsmall else None))
     _, ds_c, draws = cuda_case(name, orc.log, planner='native')
     assert draws.done()
     c_descs, _, n_c = ds_c._last_descs
@@ -63,7 +63,10 @@ def test_replayed_native_plan_equals_python_plan(name):
         if not s.real_input:
             assert np.array_equal(_read(ds_c, s.mu, 512, torch.float32), ref_ms), (name, q, "mu/sigma tables")
         assert np.array_equal(_read(ds_c, s.d.fsmall, nf, torch.float32), ref_f), (name, q, "deformation grid")
-        assert np.array_equal(_read(ds_c, s.bfsmall, s.bs[0] * s.bs[1] * s.bs[2], torch.float32), ref_b), (name, q)
+        if ref_b is None:
+            assert not s.bfsmall
+        else:
+            assert np.array_equal(_read(ds_c, s.bfsmall, s.bs[0] * s.bs[1] * s.bs[2], torch.float32), ref_b), (name, q)
 
 
 @pytest.mark.parametrize("name", CASES)
