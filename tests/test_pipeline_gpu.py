@@ -69,3 +69,21 @@ def test_pipeline_in_flight_batches_do_not_clobber_each_other():
     assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
     for o in outs:
         assert torch.isfinite(o).all() and float(o.min()) >= 0 and abs(float(o.amax()) - 1) < 1e-6
+
+
+def test_default_dataloader_collation_like_the_reference_trainer():
+    """The reference consumes the dataset through torch's DataLoader with default collation and num_workers 0
+    (train.py:133-137; MetricLogger indexes dataset_name[0], input_mode[0]): the 5-tuple must collate."""
+    from torch.utils.data import DataLoader
+    ds, subs = _dataset()
+    np.random.seed(4)
+    loader = DataLoader(ds, batch_size=2, shuffle=False, num_workers=0)
+    n = 0
+    for datasets_num, dataset_name, input_mode, target, sample in loader:
+        assert dataset_name[0] == 'HCP' and input_mode[0] == 'synth'
+        assert tuple(sample['input'].shape) == (2, 1, 48, 48, 48) and sample['input'].is_cuda
+        assert tuple(sample['bias_field_log'].shape) == (2, 1, 48, 48, 48)
+        assert tuple(target['T1'].shape) == (2, 1, 48, 48, 48)
+        assert len(target['name']) == 2
+        n += 1
+    assert n == 2 and len(ds) == 4
