@@ -23,12 +23,15 @@ import torch.distributed as dist
 
 from .. import _lib, parallel as par
 from ..plan import band_host, resample_coords_host, zoom_tables_host
-from .utils import _stream, pack_to_device
+from .utils import _stream
 
 
-def _band_axis(x, axis, n_out, start, w, T):
-    keep, (p_start, p_w) = pack_to_device([np.ascontiguousarray(start, dtype=np.int32),
-                                           np.ascontiguousarray(w, dtype=np.float32)], x.device)
+def _band_axis(x, axis, n_out, start, w, T, arena):
+    # tables through the pinned plan arena (asynchronous upload): a pageable host->device copy would wait for all
+    # queued GPU work every time and serialise host and device
+    p_start = arena.put(np.ascontiguousarray(start, dtype=np.int32))
+    p_w = arena.put(np.ascontiguousarray(w, dtype=np.float32))
+    arena.commit()
     shape = list(x.shape)
     out_shape = list(shape)
     out_shape[axis] = int(n_out)
@@ -76,7 +79,6 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     job['plan'].have_bbox = True
     _lib.check(L.bfm_gen_gmm(h, d_dev, 1, st))
     _lib.check(L.bfm_gen_warp(h, d_dev, 1, st))
-    arena.mark_done()
     N = s0 * s1 * s2
     i_bf = ds._ws['i_bf'][:N].view(s0, s1, s2)[c0:c1]
 
@@ -99,10 +101,10 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
             needed.append([owned[r][0], owned[r][0]])
     ext = par.exchange_planes(i_bf, owned, needed, rank, world, group)
     ob, oe = low_owned[rank]
-    x = _band_axis(ext, 0, oe - ob, start[ob:oe] - needed[rank][0], w[ob:oe], T)
+    x = _band_axis(ext, 0, oe - ob, start[ob:oe] - needed[rank][0], w[ob:oe], T, arena)
     for ax in (1, 2):
         st_a, w_a, T_a = band_host(size[ax], new[ax], stds[ax])
-        x = _band_axis(x, ax, new[ax], st_a, w_a, T_a)
+        x = _band_axis(x, ax, new[ax], st_a, w_a, T_a, arena)
     # ---- noise (add_noise, utils.py:633-638): injected draws are sliced, otherwise a per-rank stream
     if p['eps_noise'] is not None:
         eps = p['eps_noise'][ob:oe].to(x.device)
@@ -123,7 +125,8 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     nb = need_low[rank][0]
     t0 = (tabs[0][0][c0:c1] - nb, tabs[0][1][c0:c1] - nb, tabs[0][2][c0:c1], tabs[0][3][c0:c1])
     flat = [np.ascontiguousarray(t) for t in t0] + [t for tab in tabs[1:] for t in tab]
-    keep, addr = pack_to_device(flat, low.device)
+    addr = [arena.put(np.ascontiguousarray(t)) for t in flat]
+    arena.commit()
     out = torch.empty((c1 - c0, s1, s2), dtype=torch.float32, device=low.device)
     if out.numel():
         args = [lext.data_ptr(), lext.shape[0], new[1], new[2], 1]
@@ -134,10 +137,14 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     mx = out.max().reshape(1) if out.numel() else torch.zeros(1, device=low.device)
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    out = out * torch.reciprocal(mx)
+    # one pass: I / max and the flip of the slab's planes (bfm_shift_scale_flip: true division like the reference)
+    if out.numel():
+        fin = torch.empty_like(out)
+        _lib.check(L.bfm_shift_scale_flip(out.data_ptr(), fin.data_ptr(), c1 - c0, s1 * s2, None, mx.data_ptr(), 1.0,
+                                          1 if flip else 0, _stream()))
+        out = fin
     sample = {}
     if flip:
-        out = torch.flip(out, [0])
         x0, x1 = s0 - c1, s0 - c0
     else:
         x0, x1 = c0, c1
@@ -145,5 +152,6 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     if 'bias_field_log' in results[0]:
         sample['bias_field_log'] = results[0]['bias_field_log'][:, x0:x1]
     sample['x_range'] = (x0, x1)
+    arena.mark_done()
     ds.last_setups, ds.last_deform = setups, ctx['deform']
     return sample

@@ -120,6 +120,45 @@ __global__ void k_band_axis(const float *__restrict__ in, float *__restrict__ ou
     }
 }
 
+// Axis 0 / 1 with n2 % 4 == 0: one thread = 4 consecutive z outputs (128-bit loads and stores; the tap weight is
+// uniform across the four).  Same tap order and the same noise mapping as k_band_axis: bit-identical results.
+__global__ void __launch_bounds__(256) k_band_axis4(const float *__restrict__ in, float *__restrict__ out, int n0,
+                                                    int n1, int n2, int axis, int n_out,
+                                                    const int *__restrict__ start, const float *__restrict__ w, int T,
+                                                    float noise_std, const float *__restrict__ eps, uint64_t seed) {
+    const int o0 = axis == 0 ? n_out : n0, o1 = axis == 1 ? n_out : n1, o2v = n2 >> 2;
+    const int64_t total = (int64_t)o0 * o1 * o2v;
+    const int64_t stride = axis == 0 ? (int64_t)n1 * n2 : n2;
+    const int n_in = axis == 0 ? n0 : n1;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int kv = (int)(p % o2v);
+        const int64_t r = p / o2v;
+        const int j = (int)(r % o1), i = (int)(r / o1);
+        const int q = axis == 0 ? i : j;
+        const int s = __ldg(start + q);
+        const int64_t base = axis == 0 ? ((int64_t)s * n1 + j) * n2 + 4 * kv : ((int64_t)i * n1 + s) * n2 + 4 * kv;
+        const float *wr = w + (int64_t)q * T;
+        const int t0 = max(0, -s), t1 = min(T, n_in - s);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int t = t0; t < t1; ++t) {
+            const float wt = __ldg(wr + t);
+            const float4 x = __ldg((const float4 *)(in + base + t * stride));
+            a0 = fmaf(wt, x.x, a0); a1 = fmaf(wt, x.y, a1); a2 = fmaf(wt, x.z, a2); a3 = fmaf(wt, x.w, a3);
+        }
+        const int64_t op = ((int64_t)i * o1 + j) * n2 + 4 * kv;
+        if (noise_std >= 0.f) {
+            float4 e;
+            if (eps) e = __ldg((const float4 *)(eps + op));
+            else e = philox_normal4(seed, 1u, (uint64_t)op >> 2);
+            a0 = __fadd_rn(a0, __fmul_rn(noise_std, e.x)); a1 = __fadd_rn(a1, __fmul_rn(noise_std, e.y));
+            a2 = __fadd_rn(a2, __fmul_rn(noise_std, e.z)); a3 = __fadd_rn(a3, __fmul_rn(noise_std, e.w));
+            a0 = a0 < 0.f ? 0.f : a0; a1 = a1 < 0.f ? 0.f : a1; a2 = a2 < 0.f ? 0.f : a2; a3 = a3 < 0.f ? 0.f : a3;
+        }
+        *(float4 *)(out + op) = make_float4(a0, a1, a2, a3);
+    }
+}
+
 __global__ void k_blur_axis(const float *__restrict__ in, float *__restrict__ out, int n0, int n1, int n2,
                             int axis, const float *__restrict__ taps, int half) {
     const int64_t total = (int64_t)n0 * n1 * n2;
@@ -504,6 +543,12 @@ int bfm_band_axis(const float *in, float *out, const int *in_shape, int axis, in
     int o[3] = {in_shape[0], in_shape[1], in_shape[2]};
     o[axis] = n_out;
     const int64_t n = (int64_t)o[0] * o[1] * o[2];
+    if (axis != 2 && (in_shape[2] & 3) == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+        (!eps || ((uintptr_t)eps % 16) == 0)) {
+        k_band_axis4<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(in, out, in_shape[0], in_shape[1], in_shape[2],
+                                                                        axis, n_out, start, w, T, noise_std, eps, seed);
+        return check_launch("bfm_band_axis");
+    }
     k_band_axis<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, out, in_shape[0], in_shape[1], in_shape[2], axis,
                                                                n_out, start, w, T, noise_std, eps, seed);
     return check_launch("bfm_band_axis");
