@@ -72,6 +72,8 @@ class BaseGen(Dataset):
         self.arena = Arena(self.device)
         self.tables = device_tables(self.device)
         self._ws = {}                  # persistent device scratch of the fused chain (see _workspace)
+        # float2 {synthetic, T1} pairs in `syn` + k_gen_warp_pk for samples with one fused target (bfm.h: syn_pair_ok)
+        self.pair_mode = os.environ.get('BFM_PAIR_MODE', '1') != '0'
         self._info = {}                # t1 path -> modality table
         self._inputs = {}              # volume path -> (img, aff, res)
         self._c2 = {}                  # source shape -> centre (float32)
@@ -474,7 +476,7 @@ class BaseGen(Dataset):
         # persistent scratch: syn is zero-initialised once and afterwards only ever holds finite values
         src_pad = max(int(np.prod(j['plan'].src)) + j['plan'].src[1] * j['plan'].src[2] + j['plan'].src[2] + 1
                       for j in jobs)
-        src_pad = (src_pad + 3) // 4 * 4
+        src_pad = 2 * ((src_pad + 3) // 4 * 4)         # room for float2 {synthetic, T1} pairs (syn_pair_ok)
         syn_ws = self._workspace('syn', B * src_pad, zero=True)
         if self._ws.get('syn_stride') != src_pad:      # slots moved: stale data no longer lines up, start clean
             if 'syn_stride' in self._ws:
@@ -509,6 +511,7 @@ class BaseGen(Dataset):
                     keep.append(e)
                     s.eps_gmm = e.data_ptr()
                 s.syn = p_syn + 4 * b * src_pad
+                s.syn_pair_ok = 1 if self.pair_mode else 0
             s.seed = int(p['seed'])
             s.bbox = plan.bbox_ptr
             if p['mix'] is not None:

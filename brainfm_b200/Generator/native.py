@@ -194,6 +194,8 @@ class NativePlanner:
         bfl = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_bflog else None
         res = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_res else None
         aux_all = torch.empty((n_aux_total, 1, *size), dtype=torch.float32, device=dev) if n_aux_total else None
+        # syn holds float2 {synthetic, T1} pairs for samples with one fused target (bfm_gen_sample.syn_pair_ok)
+        src_pad *= 2
         syn_ws = ds._workspace('syn', total * src_pad, zero=True)
         if ds._ws.get('syn_stride') != src_pad:
             if 'syn_stride' in ds._ws:
@@ -204,7 +206,7 @@ class NativePlanner:
         p_low = ds._workspace('lowres', total * N).data_ptr()
         p_raw = ds._workspace('aux_raw', n_aux_total * N).data_ptr() if n_aux_total else 0
         outs = (_lib.PlanOut * total)()
-        o_np = np.frombuffer(outs, dtype=np.uint64).reshape(total, 8)
+        o_np = np.frombuffer(outs, dtype=np.uint64).reshape(total, 9)
         q = np.arange(total, dtype=np.uint64)
         step = np.uint64(4 * N)
         o_np[:, 0] = np.uint64(out.data_ptr()) + q * step
@@ -215,6 +217,7 @@ class NativePlanner:
         o_np[:, 5] = np.uint64(p_tmp) + (2 * q) * step
         o_np[:, 6] = np.uint64(p_tmp) + (2 * q + 1) * step
         o_np[:, 7] = np.uint64(p_low) + q * step
+        o_np[:, 8] = 1 if ds.pair_mode else 0
         k_aux = 0
         for n in range(B):
             it = items[n]

@@ -23,6 +23,14 @@ namespace bfm {
 
 constexpr float kBoxDelta = 1e-3f;   // bound on |computed - exact| source coordinate
 
+// Pair mode (bfm_gen_sample.syn_pair_ok): the GMM stage writes float2 {synthetic, aux_src[0]} per source voxel and
+// k_gen_warp_pk gathers both volumes with one 64-bit load per trilinear tap.
+constexpr int kPkNodes = 48;         // z nodes (+1 duplicate of the last) of a small grid that fit k_gen_warp_pk
+__host__ __device__ __forceinline__ bool use_pairs(const bfm_gen_sample &s) {
+    return s.syn_pair_ok && s.n_aux == 1 && !s.mix[0] && !s.real_input && !(s.d.src[2] & 3) && !s.d.F_full &&
+           (!s.d.fsmall || s.d.fs[2] < kPkNodes) && (!s.bfsmall || s.bs[2] < kPkNodes);
+}
+
 __device__ __forceinline__ void stage_desc(bfm_gen_sample *dst, const bfm_gen_sample *src) {
     const int n = (int)(sizeof(bfm_gen_sample) / 4);
     const uint32_t *s = (const uint32_t *)src;
@@ -311,6 +319,7 @@ __global__ void __launch_bounds__(256) k_gen_gmm_planes(const bfm_gen_sample *__
     const int is_u8 = sp->label_is_u8;
     const uint64_t seed = sp->seed;
     float *__restrict__ syn = sp->syn;
+    const float *__restrict__ pair_src = use_pairs(*sp) ? sp->aux_src[0] : nullptr;
     const int c1 = e1 - b1, c2 = e2 - b2;
     for (int f = threadIdx.x; f < items; f += blockDim.x) {
         const int z = zg << 2;
@@ -344,7 +353,14 @@ __global__ void __launch_bounds__(256) k_gen_gmm_planes(const bfm_gen_sample *__
         }
         // positions just outside the crop are never gathered with a non-zero weight; writing them keeps the
         // store 128-bit (the values are finite, which is all the warp kernel's always-read hi taps need)
-        *(float4 *)(syn + p0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (pair_src) {                  // pair mode: {synthetic, real-image target} per voxel
+            const float4 t = __ldg((const float4 *)(pair_src + p0));
+            float4 *dst = (float4 *)(syn + 2 * (size_t)p0);
+            dst[0] = make_float4(o[0], t.x, o[1], t.y);
+            dst[1] = make_float4(o[2], t.z, o[3], t.w);
+        } else {
+            *(float4 *)(syn + p0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
         y += dy; zg += dz;
         if (zg >= zg0 + wz) { zg -= wz; ++y; }
     }
@@ -674,7 +690,7 @@ __global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sampl
     __shared__ WarpShared sh;
     {   // each instantiation handles the samples of its own kind
         const bfm_gen_sample *sp = S + blockIdx.z;
-        if ((sp->mix[0] != nullptr) != MIX || sp->n_aux != NAUX) return;
+        if ((sp->mix[0] != nullptr) != MIX || sp->n_aux != NAUX || use_pairs(*sp)) return;
         const int nx = sp->x_count > 0 ? sp->x_count : sp->d.size[0];
         if ((int)blockIdx.y >= nx || (int)blockIdx.x * rpb >= sp->d.size[1]) return;
     }
@@ -683,6 +699,257 @@ __global__ void __launch_bounds__(256, WARP_MINB) k_gen_warp(const bfm_gen_sampl
     if (sh.sd.d.F_full) warp_rows<NAUX, MIX, 2>(sh, t1F, t1B, rpb);
     else if (sh.sd.d.fsmall) warp_rows<NAUX, MIX, 1>(sh, t1F, t1B, rpb);
     else warp_rows<NAUX, MIX, 0>(sh, t1F, t1B, rpb);
+}
+
+
+// ---------------------------------------------------------------------------------------------- warp, pair mode
+// Same arithmetic as warp_rows<1, false, FIELD> for the common sample kind (synthetic input + one real-image target, no
+// mixing), reorganised around what the ncu captures of k_gen_warp<1,0> showed (83 % of the L1 data-pipe wavefront
+// peak, 220 instructions per voxel):
+//   * the GMM stage leaves {synthetic, target} float2 PAIRS per source voxel, so a trilinear tap is ONE 64-bit load for
+//     both volumes (8 load requests per voxel instead of 16), and the loaded register pair is directly the operand of
+//     the packed f32x2 lerps (14 FFMA2/FADD2 per voxel instead of 28 scalar FFMA/FADD);
+//   * a thread evaluates TWO rows (j, j+1) at a time and carries their coordinates as f32x2 pairs: the third zoom pass
+//     and the affine map are 27 packed instructions per row pair instead of 54 scalar ones.  The reference's separately
+//     rounded `w0*a + w1*b` is FMUL2, FMUL2, FFMA2(x, one, y) -- `one` is an opaque 1.0f kernel parameter because ptxas
+//     contracts mul.rn.f32x2 + add.rn.f32x2 into a single FFMA2 (tools/micro/f32x2.cu) -- so coordinates stay bit-exact;
+//   * second-pass rows are stored node-major with the two rows of a pair interleaved and the last node duplicated
+//     (hi == lo + 1 always): the third pass reads 2 x (LDS.128 + LDS.64) per row pair instead of 12 LDS.32, the bias
+//     field 2 LDS.64 instead of 4 LDS.32;
+//   * the per-sample affine constants come through the kernel parameters (constant bank -> uniform registers, used as
+//     broadcast operands of the packed instructions).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float2 upk2(u64 v) { float2 o; asm("mov.b64 {%0,%1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(v)); return o; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 f2u(float2 v) { return pk2(v.x, v.y); }
+
+struct PkSample { float A[9], c2[3], ctr[3], gamma; };
+constexpr int kPkBatch = 16;
+struct PkParams {
+    PkSample s[kPkBatch];
+    float one;          // 1.0f, opaque to ptxas
+    int base;           // first sample of this launch
+};
+
+struct PkShared {
+    bfm_gen_sample sd;
+    float f2[2][kWR / 2][kPkNodes][8];    // node-major: {c0 r0, c0 r1, c1 r0, c1 r1, c2 r0, c2 r1, -, -}
+    float b2[2][kWR / 2][kPkNodes][2];    // {r0, r1}
+    float red[8][2];
+};
+
+template <int FIELD>
+__device__ __forceinline__ void warp_rows_pk(PkShared &sh, float *t1F, float *t1B, int rpb, const PkSample &c,
+                                             const float one) {
+    const bfm_gen_sample &s = sh.sd;
+    const bfm_deform &d = s.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int s0 = d.size[0], s1 = d.size[1], s2 = d.size[2];
+    const int i = (s.x_count > 0 ? s.x_begin : 0) + blockIdx.y;
+    const int j0 = blockIdx.x * rpb, j1 = min(j0 + rpb, s1);
+    const float *__restrict__ bfsmall = s.bfsmall;
+    const int nf = FIELD == 1 ? d.fs[2] : 0, fw = nf * 3;
+    const int nb = bfsmall ? s.bs[2] : 0;
+    // ---- first zoom pass (axis 0) at this i: t1F[y][z*3+c], t1B[y][z]                 utils.py:239-240
+    if (FIELD == 1) {
+        const int lo = __ldg(d.ftab.lo[0] + i), hi = __ldg(d.ftab.hi[0] + i);
+        const float wl = __ldg(d.ftab.wl[0] + i), wh = __ldg(d.ftab.wh[0] + i);
+        const int n = d.fs[1] * fw;
+        const float *a = d.fsmall + lo * n, *b = d.fsmall + hi * n;
+        for (int q = tid; q < n; q += blockDim.x) t1F[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
+    }
+    if (nb) {
+        const int lo = __ldg(s.btab.lo[0] + i), hi = __ldg(s.btab.hi[0] + i);
+        const float wl = __ldg(s.btab.wl[0] + i), wh = __ldg(s.btab.wh[0] + i);
+        const int n = s.bs[1] * nb;
+        const float *a = bfsmall + lo * n, *b = bfsmall + hi * n;
+        for (int q = tid; q < n; q += blockDim.x) t1B[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
+    }
+    __syncthreads();
+    const bool photo = d.photo != 0;
+    // ---- second pass (axis 1) for kWR rows starting at jj into buffer `buf`           utils.py:241-243
+    auto ypass = [&](int jj, int buf) {
+        for (int r = warp; r < kWR; r += nwarps) {
+            const int j = min(jj + r, s1 - 1);
+            if (FIELD == 1) {
+                const int lo = __ldg(d.ftab.lo[1] + j) * fw, hi = __ldg(d.ftab.hi[1] + j) * fw;
+                const float wl = __ldg(d.ftab.wl[1] + j), wh = __ldg(d.ftab.wh[1] + j);
+                float *dst = &sh.f2[buf][r >> 1][0][r & 1];
+                for (int q = lane; q < fw + 3; q += 32) {             // node nf duplicates node nf - 1
+                    const int node = q / 3, ch = q - node * 3, src = min(node, nf - 1) * 3 + ch;
+                    const float v = lerp_rn(wl, t1F[lo + src], wh, t1F[hi + src]);
+                    dst[node * 8 + ch * 2] = (photo && ch == 1) ? 0.f : v;       // datasets.py:211-212
+                }
+            }
+            if (nb) {
+                const int lo = __ldg(s.btab.lo[1] + j) * nb, hi = __ldg(s.btab.hi[1] + j) * nb;
+                const float wl = __ldg(s.btab.wl[1] + j), wh = __ldg(s.btab.wh[1] + j);
+                float *dst = &sh.b2[buf][r >> 1][0][r & 1];
+                for (int q = lane; q <= nb; q += 32) {
+                    const int src = min(q, nb - 1);
+                    dst[q * 2] = lerp_rn(wl, t1B[lo + src], wh, t1B[hi + src]);
+                }
+            }
+        }
+    };
+    const BoxRegs box = load_box(s.bbox, d.src[1], d.src[2]);
+    const int origin = box.b0 * box.n1n2 + box.b1 * box.n2 + box.b2;
+    const float2 *__restrict__ syn2 = (const float2 *)s.syn;
+    const float gamma = c.gamma;
+    float *__restrict__ i_bf = s.i_bf;
+    float *__restrict__ bfl = nb ? s.bflog_out : nullptr;
+    float *__restrict__ araw = s.aux_raw[0];
+    float amin = INFINITY, amax = -INFINITY;
+    const float mx = (float)(d.src[0] - 1), my = (float)(d.src[1] - 1), mz = (float)(d.src[2] - 1);
+    const u64 ONE = pk2(one, one);
+    const float xc = __fsub_rn((float)i, c.ctr[0]);
+    const u64 XC = pk2(xc, xc);
+    const u64 NL0 = pk2(-box.l0, -box.l0), NL1 = pk2(-box.l1, -box.l1), NL2 = pk2(-box.l2, -box.l2);
+    const int plane_in = i * s1, plane_out = (s.flip ? s0 - 1 - i : i) * s1;
+
+    for (int k0 = 0; k0 < s2; k0 += blockDim.x) {
+        const int k = k0 + tid;
+        const bool kv = k < s2;
+        const int kk = kv ? k : s2 - 1;
+        // ---- everything that only depends on k
+        int zlo = 0, blo = 0;
+        u64 ZWL = 0, ZWH = 0, BWL = 0, BWH = 0;
+        if (FIELD == 1) {
+            zlo = __ldg(d.ftab.lo[2] + kk);
+            const float wl = __ldg(d.ftab.wl[2] + kk), wh = __ldg(d.ftab.wh[2] + kk);
+            ZWL = pk2(wl, wl); ZWH = pk2(wh, wh);
+        }
+        if (nb) {
+            blo = __ldg(s.btab.lo[2] + kk);
+            const float wl = __ldg(s.btab.wl[2] + kk), wh = __ldg(s.btab.wh[2] + kk);
+            BWL = pk2(wl, wl); BWH = pk2(wh, wh);
+        }
+        const float zc = __fsub_rn((float)kk, c.ctr[2]);
+        const u64 ZC = pk2(zc, zc);
+        int buf = 0;
+        ypass(j0, 0);
+        __syncthreads();
+        for (int jj = j0; jj < j1; jj += kWR) {
+            if (jj + kWR < j1) ypass(jj + kWR, buf ^ 1);
+#pragma unroll
+            for (int rp = 0; rp < kWR / 2; ++rp) {
+                const int j = jj + 2 * rp;
+                if (j >= j1) break;
+                // ---- coordinates of rows j and j + 1 as f32x2 pairs
+                u64 X1 = XC, Y1 = pk2(__fsub_rn((float)j, c.ctr[1]), __fsub_rn((float)(j + 1), c.ctr[1])), Z1 = ZC;
+                if (FIELD == 1) {                                    // third pass (axis 2), utils.py:244-246
+                    const float4 *fn = (const float4 *)&sh.f2[buf][rp][zlo][0];
+                    const float4 l01 = fn[0], h01 = fn[2];
+                    const float2 l2 = *(const float2 *)(fn + 1), h2 = *(const float2 *)(fn + 3);
+                    const u64 F0 = fma2(mul2(ZWH, pk2(h01.x, h01.y)), ONE, mul2(ZWL, pk2(l01.x, l01.y)));
+                    const u64 F1 = fma2(mul2(ZWH, pk2(h01.z, h01.w)), ONE, mul2(ZWL, pk2(l01.z, l01.w)));
+                    const u64 F2 = fma2(mul2(ZWH, f2u(h2)), ONE, mul2(ZWL, f2u(l2)));
+                    X1 = add2(X1, F0); Y1 = add2(Y1, F1); Z1 = add2(Z1, F2);
+                }
+                // ((A0*x + A1*y) + A2*z) + c, every product and sum separately rounded (datasets.py:276-278)
+                auto affine = [&](const float a0, const float a1, const float a2, const float cc) {
+                    const u64 m0 = mul2(pk2(a0, a0), X1), m1 = mul2(pk2(a1, a1), Y1), m2 = mul2(pk2(a2, a2), Z1);
+                    return add2(fma2(m2, ONE, fma2(m1, ONE, m0)), pk2(cc, cc));
+                };
+                const float2 px = upk2(affine(c.A[0], c.A[1], c.A[2], c.c2[0]));
+                const float2 py = upk2(affine(c.A[3], c.A[4], c.A[5], c.c2[1]));
+                const float2 pz = upk2(affine(c.A[6], c.A[7], c.A[8], c.c2[2]));
+                auto clampf = [](float v, float hi) { v = v < 0.f ? 0.f : v; return v > hi ? hi : v; };   // :279-284
+                const float2 rx = upk2(add2(pk2(clampf(px.x, mx), clampf(px.y, mx)), NL0));
+                const float2 ry = upk2(add2(pk2(clampf(py.x, my), clampf(py.y, my)), NL1));
+                const float2 rz = upk2(add2(pk2(clampf(pz.x, mz), clampf(pz.y, mz)), NL2));
+                // ---- trilinear taps relative to the crop (fast_3D_interp_torch, utils.py:140-192)
+                const float rxa[2] = {rx.x, rx.y}, rya[2] = {ry.x, ry.y}, rza[2] = {rz.x, rz.y};
+                int e00[2];
+                float ax[2], ay[2], az[2];
+                bool ok[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    ok[q] = (rxa[q] > 0.f) & (rya[q] > 0.f) & (rza[q] > 0.f) & (rxa[q] <= box.h0) & (rya[q] <= box.h1) &
+                            (rza[q] <= box.h2) & (j + q < j1);
+                    const int ix = __float2int_rd(rxa[q]), iy = __float2int_rd(rya[q]), iz = __float2int_rd(rza[q]);
+                    ax[q] = __fsub_rn(rxa[q], (float)ix); ay[q] = __fsub_rn(rya[q], (float)iy);
+                    az[q] = __fsub_rn(rza[q], (float)iz);
+                    e00[q] = ok[q] ? origin + ix * box.n1n2 + iy * box.n2 + iz : origin;
+                }
+                u64 tap[2][8];                          // {synthetic, target} at 000 001 100 101 010 011 110 111
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float2 *b00 = syn2 + e00[q], *b10 = b00 + box.n1n2, *b01 = b00 + box.n2, *b11 = b10 + box.n2;
+                    tap[q][0] = f2u(__ldg(b00)); tap[q][1] = f2u(__ldg(b00 + 1));
+                    tap[q][2] = f2u(__ldg(b10)); tap[q][3] = f2u(__ldg(b10 + 1));
+                    tap[q][4] = f2u(__ldg(b01)); tap[q][5] = f2u(__ldg(b01 + 1));
+                    tap[q][6] = f2u(__ldg(b11)); tap[q][7] = f2u(__ldg(b11 + 1));
+                }
+                // bias field rows of the pair                        utils.py:574-589
+                float2 bl = make_float2(0.f, 0.f);
+                if (nb) {
+                    const float2 *bn = (const float2 *)&sh.b2[buf][rp][blo][0];
+                    bl = upk2(fma2(mul2(BWH, f2u(bn[1])), ONE, mul2(BWL, f2u(bn[0]))));
+                }
+                const float bla[2] = {bl.x, bl.y};
+                const int pr0 = (plane_in + j) * s2 + kk, po0 = (plane_out + j) * s2 + kk;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const u64 *t = tap[q];
+                    const u64 AX = pk2(ax[q], ax[q]), AY = pk2(ay[q], ay[q]), AZ = pk2(az[q], az[q]);
+                    const u64 c00 = fma2(AX, sub2(t[2], t[0]), t[0]), c01 = fma2(AX, sub2(t[3], t[1]), t[1]);
+                    const u64 c10 = fma2(AX, sub2(t[6], t[4]), t[4]), c11 = fma2(AX, sub2(t[7], t[5]), t[5]);
+                    const u64 c0 = fma2(AY, sub2(c10, c00), c00), c1 = fma2(AY, sub2(c11, c01), c01);
+                    const float2 vv = upk2(fma2(AZ, sub2(c1, c0), c0));
+                    float v = ok[q] ? vv.x : 0.f;
+                    const float a = ok[q] ? vv.y : 0.f;
+                    v = fmaxf(v, 0.f);                                // datasets.py:411
+                    v = 300.f * fast_pow(v * (1.f / 300.f), gamma);   // utils.py:568-572
+                    if (nb) v *= ex2_approx(bla[q] * 1.4426950408889634f);
+                    if (kv && j + q < j1) {
+                        i_bf[pr0 + q * s2] = v;
+                        if (bfl) bfl[po0 + q * s2] = bla[q];
+                        araw[pr0 + q * s2] = a;                       // read_and_deform_image: raw warp + min/max
+                        amin = fminf(amin, a);
+                        amax = fmaxf(amax, a);
+                    }
+                }
+            }
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    {
+        const float lo = warp_min(amin), hi = warp_max(amax);
+        if (lane == 0) { sh.red[warp][0] = lo; sh.red[warp][1] = hi; }
+        __syncthreads();
+        if (tid < 2) {
+            float v = sh.red[0][tid];
+            for (int w = 1; w < nwarps; ++w) v = (tid & 1) ? fmaxf(v, sh.red[w][tid]) : fminf(v, sh.red[w][tid]);
+            if (tid & 1) atomicMax(s.aux_mm + tid, f2ord(v));
+            else atomicMin(s.aux_mm + tid, f2ord(v));
+        }
+    }
+}
+
+#ifndef WARP_PK_MINB
+#define WARP_PK_MINB 3
+#endif
+__global__ void __launch_bounds__(256, WARP_PK_MINB)
+k_gen_warp_pk(const bfm_gen_sample *__restrict__ S, const __grid_constant__ PkParams P, int rpb, int t1f_cap) {
+    extern __shared__ float smem[];
+    __shared__ PkShared sh;
+    const int b = P.base + blockIdx.z;
+    {
+        const bfm_gen_sample *sp = S + b;
+        if (!use_pairs(*sp)) return;
+        const int nx = sp->x_count > 0 ? sp->x_count : sp->d.size[0];
+        if ((int)blockIdx.y >= nx || (int)blockIdx.x * rpb >= sp->d.size[1]) return;
+    }
+    stage_desc(&sh.sd, S + b);
+    float *t1F = smem, *t1B = smem + t1f_cap;
+    if (sh.sd.d.fsmall) warp_rows_pk<1>(sh, t1F, t1B, rpb, P.s[blockIdx.z], P.one);
+    else warp_rows_pk<0>(sh, t1F, t1B, rpb, P.s[blockIdx.z], P.one);
 }
 
 
@@ -1198,6 +1465,7 @@ int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
     if (rc) return rc;
     int t1f = 0, t1b = 0, wf = 0, wb = 0, s0 = 0, s1 = 0, s2 = 0;
     bool kinds[BFM_MAX_AUX + 2] = {false, false, false, false, false};      // n_aux 0..3, then MIX
+    bool any_pk = false;                                                    // pair mode (k_gen_warp_pk)
     for (int b = 0; b < B; ++b) {
         const bfm_gen_sample &s = h[b];
         if (s.n_aux < 0 || s.n_aux > BFM_MAX_AUX || (s.mix[0] && s.n_aux))
@@ -1205,7 +1473,8 @@ int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
         for (int c = 0; c < s.n_aux; ++c)
             if (!s.aux_src[c] || !s.aux_raw[c] || !s.aux_out[c] || !s.aux_mm)
                 return fail(BFM_E_INVALID, "%s", "bfm_gen_warp: null real-image target buffer");
-        kinds[s.mix[0] ? BFM_MAX_AUX + 1 : s.n_aux] = true;
+        if (use_pairs(s)) any_pk = true;
+        else kinds[s.mix[0] ? BFM_MAX_AUX + 1 : s.n_aux] = true;
         if (s.d.fsmall && !s.d.F_full) {
             t1f = max(t1f, s.d.fs[1] * s.d.fs[2] * 3);
             wf = max(wf, s.d.fs[2] * 3);
@@ -1244,6 +1513,28 @@ int bfm_gen_warp(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
     BFM_LAUNCH_WARP(3, 3, false)
     BFM_LAUNCH_WARP(4, 0, true)
 #undef BFM_LAUNCH_WARP
+    if (any_pk) {
+        if (smem > 40 * 1024)
+            cudaFuncSetAttribute(k_gen_warp_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        for (int base = 0; base < B; base += kPkBatch) {
+            const int nb = min(kPkBatch, B - base);
+            PkParams P;
+            bool any = false;
+            for (int q = 0; q < nb; ++q) {
+                const bfm_gen_sample &sm = h[base + q];
+                any |= use_pairs(sm);
+                for (int a = 0; a < 9; ++a) P.s[q].A[a] = sm.d.A[a];
+                for (int a = 0; a < 3; ++a) { P.s[q].c2[a] = sm.d.c2[a]; P.s[q].ctr[a] = sm.d.ctr[a]; }
+                P.s[q].gamma = sm.gamma;
+            }
+            if (!any) continue;
+            P.one = 1.0f;
+            P.base = base;
+            k_gen_warp_pk<<<dim3(grid.x, grid.y, nb), threads, smem, st>>>(d, P, rpb, t1f);
+            rc = check_launch("bfm_gen_warp");
+            if (rc) return rc;
+        }
+    }
     return BFM_OK;
 }
 

@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 5
+#define BFM_ABI_VERSION 6
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -235,6 +235,13 @@ typedef struct bfm_gen_sample {
        before the gamma transform.  2 = CT input: the warped value is clamped to [0, 80] (datasets.py:318-319) and
        there is no bias field (bfsmall == NULL, Generator/utils.py:575-577). */
     int real_input;
+    /* Pair mode.  syn_pair_ok != 0: `syn` has room for TWICE the floats (2 * (source volume + tail padding), zeroed
+       once by the caller).  For samples with exactly one real-image target, no mixing, a synthetic input, src[2] % 4
+       == 0 and no full-resolution field, bfm_gen_gmm then writes {synthetic value, aux_src[0] value} PAIRS
+       (float2 per source voxel) and bfm_gen_warp gathers both volumes with one 64-bit load per trilinear tap
+       (k_gen_warp_pk: half the load requests of the two-volume gather, packed f32x2 arithmetic).  Results are
+       identical to the unpaired path. */
+    int syn_pair_ok;
 } bfm_gen_sample;
 
 /* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,
@@ -324,6 +331,7 @@ typedef struct bfm_plan_item {
 typedef struct bfm_plan_out {       /* per SAMPLE buffers (device), caller allocated */
     float *out, *bflog_out, *residual;
     float *syn, *i_bf, *tmp[2], *lowres;
+    int64_t syn_pair_ok;            /* see bfm_gen_sample.syn_pair_ok */
 } bfm_plan_out;
 
 typedef struct bfm_plan_info {      /* what the host needs to know about a planned ITEM */

@@ -154,6 +154,23 @@ def zoom_linear(X, factor):
 # ----------------------------------------------------------------------------------------------
 # geometry
 # ----------------------------------------------------------------------------------------------
+def bspline_resize(I, size):
+    """interpol.resize(I, shape=size, anchor='edge', interpolation=3, bound='dct2', prefilter=True)
+    (Generator/datasets.py:337-338; utils/interpol/resize.py:74-128, api.py:137-212): cubic prefilter along every
+    axis (dct2), then a cubic pull at arange(out) * (in / out) + 0.5 * (in / out - 1), float32 throughout."""
+    from oracle import interpol_oracle as io
+    x = I.numpy().astype(np.float32)
+    for axis in range(3):
+        x = io.spline_filter(x, 3, 3, axis)
+    lin = []
+    for n_in, n_out in zip(x.shape, size):
+        scale = n_in / n_out
+        lin.append((torch.arange(0., n_out, dtype=torch.float32) * scale + 0.5 * (scale - 1)).numpy())
+    grid = np.stack(np.meshgrid(*lin, indexing="ij"), axis=-1)[None].astype(np.float32)
+    out = io.pull(x[None, None], grid, [3, 3, 3], [3, 3, 3], 1)
+    return torch.from_numpy(np.ascontiguousarray(out[0, 0]))
+
+
 def affine_matrix(rot, sh, s):
     """SHx.SHy.SHz.Rx.Ry.Rz with rows scaled by s, float64 (Generator/utils.py:102-116)."""
     c, n = np.cos(rot), np.sin(rot)
@@ -653,7 +670,10 @@ class GeneratorOracle:
         for name in steps:
             I = table[name](I, aux, setups)
             stages[name] = I
-        I = zoom_linear(I, 1 / aux["factors"])
+        if getattr(self.g, "bspline_zooming", False):
+            I = bspline_resize(I, self.size)
+        else:
+            I = zoom_linear(I, 1 / aux["factors"])
         top = torch.max(I)
         out = I / top
         flip = setups["flip"]

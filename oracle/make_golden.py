@@ -33,10 +33,11 @@ def sub(a, stride):
 
 def summarise(name, t, stride, out):
     a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
-    if a.ndim == 4 and a.shape[0] == 56:           # one-hot -> label index (lossless)
-        assert np.all(a.sum(0) == 1)
-        a = a.argmax(0).astype(np.uint8)
+    if a.ndim == 4 and a.shape[0] == 56 and np.all((a == 0) | (a == 1)) and np.all(a.sum(0) == 1):
+        a = a.argmax(0).astype(np.uint8)           # hard one-hot -> label index (lossless)
         name = name + ".argmax"
+    elif a.ndim == 4 and a.shape[0] == 56:         # deform_one_hots: linearly warped (soft) one-hots
+        stride = 2 * stride
     out[name + ".sub"] = sub(a, stride)
     out[name + ".sum"] = np.float64(a.astype(np.float64).sum())
     out[name + ".max"] = np.float64(a.max())
@@ -76,6 +77,30 @@ CASES = {
                                            "generator.random_shape_prob": 1.0}, [], "default", 2),
     "g64_pathol_s12": (64, 64, "brain", 12, {"task.pathology": True, "generator.pathology_prob": 1.0,
                                              "generator.random_shape_prob": 1.0}, [], "default", 2),
+    # ---- round 2: branches that were built but unpinned
+    # 'surface' task: SVF scaling-and-squaring of the nonlinear field (datasets.py:214-223), F / Fneg full-resolution,
+    # full bbox scan, k_gen_warp FIELD == 2
+    "g64_svf_s31": (64, 96, "brain", 31, {"task.surface": True}, [], "default", 2),
+    "g64_svf_s41": (64, 96, "brain", 41, {"task.surface": True}, [], "default", 2),          # photo mode + flip
+    # one-hot segmentation warped linearly (utils.py:404-416)
+    "g64_onehot_s43": (64, 96, "brain", 43, {"task.segmentation": True, "generator.deform_one_hots": True}, [],
+                       "default", 2),
+    "g64_onehot_s41": (64, 96, "brain", 41, {"task.segmentation": True, "generator.deform_one_hots": True}, [],
+                       "default", 2),                                                          # photo mode + flip
+    # cubic B-spline zoom back to the grid (datasets.py:337-340, interpol.resize)
+    "g64_bspline_s43": (64, 96, "brain", 43, {"generator.bspline_zooming": True}, [], "default", 2),
+    "g64_bspline_s41": (64, 96, "brain", 41, {"generator.bspline_zooming": True}, [], "default", 2),
+    # random centre shift (datasets.py:195-200)
+    "g64_shift_s43": (64, 96, "brain", 43, {"generator.random_shift": True}, [], "default", 2),
+    # CT-like contrast groups (datasets.py:349, get_contrast)
+    "g64_ct_s35": (64, 96, "brain", 35, {"generator.ct_prob": 1.0}, [], "default", 2),
+    # pathology shape advected by the ShapeID PDE inside the chain (utils.py:514-522)
+    "g64_augpath_s47": (64, 64, "brain", 47, {"task.pathology": True, "generator.pathology_prob": 1.0,
+                                              "generator.random_shape_prob": 1.0,
+                                              "generator.augment_pathology": True}, [], "default", 2),
+    "g64_augpath_s48": (64, 64, "brain", 48, {"task.pathology": True, "generator.pathology_prob": 1.0,
+                                              "generator.random_shape_prob": 1.0,
+                                              "generator.augment_pathology": True}, [], "default", 2),
 }
 
 
@@ -146,6 +171,13 @@ def run_reference(name):
     args = cfg_for(size, over, option, ref=True)
     args.split_root = root
     ds = Generator.build_datasets(args, "cpu")["all"]
+    # keep the reference's deformation dict (F / Fneg of the 'surface' task are not part of the item)
+    inner = ds.generate_deformation
+
+    def keep(*a, **k):
+        ds.last_deform = inner(*a, **k)
+        return ds.last_deform
+    ds.generate_deformation = keep
     go.seed_all(seed)
     return ds[0], ds
 
@@ -207,6 +239,15 @@ def main(argv):
             else:
                 out[k] = v
         out["meta.bbox"] = np.array(orc.deform["lo"] + orc.deform["hi"])
+        rd = getattr(ds, "last_deform", None)
+        if rd is not None and rd.get("Fneg") is not None:       # integrated fields: reference values, oracle checked
+            for key in ("F", "Fneg"):
+                a, b = rd[key].numpy(), orc.deform[key].numpy()
+                assert np.array_equal(a, b), (name, key, float(np.abs(a - b).max()))
+                summarise("deform." + key, rd[key], stride, out)
+            g = [int(v) for v in rd["grid"][3:]]
+            assert g == [g[0], g[1], g[2], g[3], g[4], g[5]] and \
+                [g[0], g[1], g[2]] == list(orc.deform["lo"]) and [g[3], g[4], g[5]] == list(orc.deform["hi"]), (g, orc.deform["lo"])
         out["meta.factors"] = np.asarray(orc.aux["factors"])
         out["meta.flip"] = np.array(bool(orc.setups["flip"]))
         out["meta.photo"] = np.array(bool(orc.setups["photo_mode"]))
