@@ -68,7 +68,7 @@ class BaseGen(Dataset):
         if self.device.type != 'cuda':
             raise _lib.BfmError("device must be a CUDA device")
         self.rng = draws or HostDraws()
-        self.cache = bio.DeviceVolumeCache(self.device)
+        self.cache = bio.shared_cache(self.device)     # one cache per device, shared with the op-wise target readers
         self.arena = Arena(self.device)
         self.tables = device_tables(self.device)
         self._ws = {}                  # persistent device scratch of the fused chain (see _workspace)
@@ -77,7 +77,7 @@ class BaseGen(Dataset):
         self._info = {}                # t1 path -> modality table
         self._inputs = {}              # volume path -> (img, aff, res)
         self._c2 = {}                  # source shape -> centre (float32)
-        self._hemis = {}               # (segmentation path, registration path) -> left-hemisphere mask
+        self._hemis_key = ()           # (segmentation path, registration path) of the current left-hemisphere mask
         self.hemis_mask = None
         self.write_bflog = None        # None: follow the task list; True/False: force
         self.prepare_tasks()
@@ -315,13 +315,13 @@ class BaseGen(Dataset):
             self.hemis_mask = None
             return
         key = (self.modalities['segmentation'], self.modalities['registration'][0])
-        hit = self._hemis.get(key)
-        if hit is None:
+
+        def build():
             S = self.cache.get(key[0], 'i32')
             X = self.cache.get(key[1], 'f32')
-            hit = ((self.lut[S.long()] > 0) & (X < 0)).to(torch.uint8)
-            self._hemis[key] = hit
-        self.hemis_mask = hit
+            return ((self.lut[S.long()] > 0) & (X < 0)).to(torch.uint8)
+        self.hemis_mask = self.cache.derived('left_hemis_mask', key, build)     # dropped when a dependency is uploaded
+        self._hemis_key = key
 
     # ---- targets (datasets.py:593-631) -------------------------------------------------------------
     def read_and_deform_target(self, idx, exist_keys, task_name, input_mode, setups, deform_dict, linear_weights=None):
@@ -656,12 +656,10 @@ class BaseGen(Dataset):
         lab = self.cache.get(self.modalities['Gen'], 'gen')
         if self.hemis_mask is None:
             return lab
-        key = ('gen_masked', self.modalities['Gen'])          # G[hemis_mask == 0] = 0 (datasets.py:367-368)
-        hit = self._hemis.get(key)
-        if hit is None:
-            hit = torch.where(self.hemis_mask != 0, lab, torch.zeros((), dtype=lab.dtype, device=lab.device))
-            self._hemis[key] = hit.contiguous()
-        return self._hemis[key]
+        mask = self.hemis_mask                                # G[hemis_mask == 0] = 0 (datasets.py:367-368)
+        return self.cache.derived('gen_masked', (self.modalities['Gen'],) + tuple(self._hemis_key),
+                                  lambda: torch.where(mask != 0, lab, torch.zeros((), dtype=lab.dtype,
+                                                                                  device=lab.device)).contiguous())
 
     def _want_bflog(self, input_mode):
         if input_mode == 'CT':                          # no bias field on CT (utils.py:575-577, datasets.py:351)
@@ -912,6 +910,7 @@ class BaseGen(Dataset):
     def generate_batch(self, indices, timers=None):
         """Several items in one go: all host draws first (reference order, item by item), then ONE batched launch
         per stage of the fused chain.  Returns a list of __getitem__ tuples."""
+        self.cache.begin_batch()          # volumes looked up from here on stay alive until the launches are enqueued
         native = self._native_planner(indices)
         if native is not None:
             return native.run(indices, timers=timers)

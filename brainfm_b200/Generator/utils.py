@@ -300,14 +300,9 @@ def _plan_of(deform_dict):
     return dict.__getitem__(deform_dict, '_plan')
 
 
-_CACHES = {}
-
-
 def _cache(device):
-    key = str(torch.device(device))
-    if key not in _CACHES:
-        _CACHES[key] = bio.DeviceVolumeCache(torch.device(device))
-    return _CACHES[key]
+    """The device's one volume cache (shared with BaseGen: an uploaded / refreshed volume is seen by every reader)."""
+    return bio.shared_cache(device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -392,7 +387,14 @@ def read_and_deform_CT(exist_keys, task_name, file_name, setups, deform_dict, de
     Idef, _ = read_and_deform(file_name, torch.float, deform_dict, device, mask, scale=1000)
     if setups['flip']:
         Idef = _normalise_flip(Idef, True, minmax=False)
-    return {'CT': Idef[None]}
+    update_dict = {'CT': Idef[None]}
+    dm = file_name[:-4] + '.defacingmask.nii'
+    if bio.exists(dm):                                     # defacing mask (Generator/utils.py:353-359)
+        Idef_DM, _ = read_and_deform(dm, torch.float, deform_dict, device, mask)
+        Idef_DM = torch.clamp(Idef_DM, min=0.)
+        Idef_DM /= torch.max(Idef_DM)
+        update_dict.update({task_name + '_DM': Idef_DM[None]})    # the reference leaves the mask unflipped (:357-359)
+    return update_dict
 
 
 def read_and_deform_distance(exist_keys, task_name, file_names, setups, deform_dict, device, mask=None, cfg=None,

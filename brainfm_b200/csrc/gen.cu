@@ -737,8 +737,8 @@ struct PkParams {
 
 struct PkShared {
     bfm_gen_sample sd;
-    float f2[2][kWR / 2][kPkNodes][8];    // node-major: {c0 r0, c0 r1, c1 r0, c1 r1, c2 r0, c2 r1, -, -}
-    float b2[2][kWR / 2][kPkNodes][2];    // {r0, r1}
+    alignas(16) float f2[2][kWR / 2][kPkNodes][8];    // node-major: {c0 r0, c0 r1, c1 r0, c1 r1, c2 r0, c2 r1, -, -}
+    alignas(16) float b2[2][kWR / 2][kPkNodes][2];    // {r0, r1}
     float red[8][2];
 };
 

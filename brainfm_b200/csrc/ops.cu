@@ -433,6 +433,47 @@ __global__ void k_svf_step(const float *__restrict__ Fin, float *__restrict__ Fo
     }
 }
 
+// Cached 'f32' volume <- a volume in its stored dtype, converted on the device: dst = nan_to_num(src * slope + inter)
+// (nib get_fdata scaling + torch.nan_to_num, Generator/utils.py:304-305).  16 source elements per thread for the
+// narrow dtypes so that loads and stores are both 128-bit.
+template <typename T>
+__global__ void __launch_bounds__(256) k_ingest(float *__restrict__ dst, const T *__restrict__ src, int64_t n,
+                                                float slope, float inter) {
+    constexpr int V = 16 / sizeof(T);                       // elements per 128-bit load
+    const int64_t groups = n / V;
+    const bool aligned = (((uintptr_t)src & 15) == 0) && (((uintptr_t)dst & 15) == 0);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (aligned) {
+        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+            const uint4 raw = __ldg((const uint4 *)src + g);
+            const T *e = (const T *)&raw;
+            float v[V];
+#pragma unroll
+            for (int q = 0; q < V; ++q) v[q] = nan_to_num(__fadd_rn(__fmul_rn((float)e[q], slope), inter));
+            float4 *o = (float4 *)(dst + g * V);
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    const int64_t done = aligned ? groups * V : 0;
+    for (int64_t p = done + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+        dst[p] = nan_to_num(__fadd_rn(__fmul_rn((float)src[p], slope), inter));
+}
+
+// out[4g .. 4g+3] = philox_normal4(seed, stream, first_group + g): the N(0,1) source of the fused chain, exposed
+// so that its distribution can be tested directly (tests/test_noise_gpu.py).
+__global__ void __launch_bounds__(256) k_philox_normal(float *__restrict__ out, int64_t n, uint64_t seed,
+                                                       uint32_t stream, uint64_t first_group) {
+    const int64_t groups = (n + 3) / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const float4 e = philox_normal4(seed, stream, first_group + (uint64_t)g);
+        const float v[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * g + q < n) out[4 * g + q] = v[q];
+    }
+}
+
 static inline int grid_for(int64_t n, int block = 256) {
     int64_t g = (n + block - 1) / block;
     const int64_t cap = 148LL * 32;
@@ -456,6 +497,28 @@ using namespace bfm;
 extern "C" {
 
 int bfm_abi_version(void) { return BFM_ABI_VERSION; }
+
+int bfm_ingest_volume(float *dst, const void *src, int src_dtype, int64_t n, float slope, float inter, void *stream) {
+    BFM_REQUIRE(dst && src && n >= 0, "bfm_ingest_volume: null pointer");
+    if (n == 0) return BFM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (src_dtype) {
+        case 0: k_ingest<uint8_t><<<grid_for((n + 15) / 16), 256, 0, st>>>(dst, (const uint8_t *)src, n, slope, inter); break;
+        case 1: k_ingest<int16_t><<<grid_for((n + 7) / 8), 256, 0, st>>>(dst, (const int16_t *)src, n, slope, inter); break;
+        case 2: k_ingest<int32_t><<<grid_for((n + 3) / 4), 256, 0, st>>>(dst, (const int32_t *)src, n, slope, inter); break;
+        case 3: k_ingest<float><<<grid_for((n + 3) / 4), 256, 0, st>>>(dst, (const float *)src, n, slope, inter); break;
+        case 4: k_ingest<int8_t><<<grid_for((n + 15) / 16), 256, 0, st>>>(dst, (const int8_t *)src, n, slope, inter); break;
+        default: return fail(BFM_E_INVALID, "%s", "bfm_ingest_volume: src_dtype must be 0 (u8), 1 (i16), 2 (i32), 3 (f32) or 4 (i8)");
+    }
+    return check_launch("bfm_ingest_volume");
+}
+
+int bfm_philox_normal(float *out, int64_t n, uint64_t seed, uint32_t stream_id, uint64_t first_group, void *stream) {
+    BFM_REQUIRE(out && n >= 0, "bfm_philox_normal: null output");
+    if (n == 0) return BFM_OK;
+    k_philox_normal<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id, first_group);
+    return check_launch("bfm_philox_normal");
+}
 
 int bfm_upload_pinned(void *dst, const void *src_pinned, int64_t nbytes, void *stream) {
     BFM_REQUIRE(dst && src_pinned && nbytes >= 0, "bfm_upload_pinned: null pointer");

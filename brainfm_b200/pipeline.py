@@ -41,6 +41,7 @@ class HostPipeline:
         self._next = 0
         self._last_reader = {}           # (path, kind) -> event of the last batch that read the volume
         self._stages = {}                # batched-upload staging buffers on the device
+        self._last_done = None           # event of the most recent batch
 
     def _stage(self, kind, host):
         """Device staging buffer of a batched upload: a ring of two per (kind, shape), so that the DMA of step k+1 can
@@ -74,12 +75,15 @@ class HostPipeline:
         main = torch.cuda.current_stream(self.device)
         # 1. uploads on the copy-in stream (after the last reader of each destination volume)
         flat = []                                         # (path, kind) of every uploaded volume
+        direct = []                                       # ... of those copied straight into the cached tensor
         staged = []                                       # batched uploads: (paths, kind, staging buffer, slot)
         if uploads:
             with torch.cuda.stream(self.copy_in):
                 for path, kind, host in uploads:
                     if isinstance(path, (list, tuple)):
-                        # batched host buffer (len(paths), *volume shape): ONE host->device DMA into a staging buffer
+                        # batched host buffer (len(paths), *volume shape), in the volumes' STORED dtype (uint8 labels,
+                        # int16 / uint8 / float32 images -- widened to the cached float32 on the device by
+                        # bfm_ingest_volume, so an int16 T1 crosses PCIe as 2 bytes per voxel): ONE host->device DMA into a staging buffer
                         # on the copy stream (nothing else is queued there, so the copy engine never idles between
                         # steps); the device-to-device copies into the cached volumes follow on the compute stream.
                         # With one DMA per volume the engine idles 40-50 us between copies whenever the download
@@ -91,11 +95,14 @@ class HostPipeline:
                         staged.append((list(path), kind, stage, slot))
                         flat += [(p, kind) for p in path]
                     else:
-                        ev = self._last_reader.get((path, kind))
+                        # after the last batch that read this volume; a volume that was never uploaded before may have
+                        # been read by ANY earlier batch (it came from cache.get): wait for the latest one
+                        ev = self._last_reader.get((path, kind), self._last_done)
                         if ev is not None:
                             self.copy_in.wait_event(ev)
                         ds.cache.upload(path, kind, host)     # copies only: the copy stream never waits for an SM
                         flat.append((path, kind))
+                        direct.append((path, kind))
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.copy_in)
             main.wait_event(ev_in)
@@ -104,7 +111,7 @@ class HostPipeline:
                     ds.cache.upload(p, kind, part)
                 slot["free"] = torch.cuda.Event()
                 slot["free"].record(main)
-            for p, kind in flat:
+            for p, kind in direct:                        # (staged volumes were sanitised by bfm_ingest_volume)
                 ds.cache.sanitize(p, kind)                # nan_to_num on the compute stream
         # 2. generation on the caller's stream
         items = ds.generate_batch(list(indices))
@@ -112,6 +119,7 @@ class HostPipeline:
         ev_done.record(main)
         for key in flat:
             self._last_reader[key] = ev_done
+        self._last_done = ev_done
         # 3. download on the copy-out stream
         outs = [it[4][self.key] if not isinstance(it[4], list) else torch.cat([s[self.key] for s in it[4]], 0)
                 for it in items]

@@ -79,6 +79,20 @@ int bfm_band_axis(const float *in, float *out, const int *in_shape, int axis, in
  * uploads queued on the copy engine.  Addresses and nbytes: multiples of 16. */
 int bfm_upload_pinned(void *dst, const void *src_pinned, int64_t nbytes, void *stream);
 
+/* Label-map / image ingestion: dst (float32, n elements) = nan_to_num(src * slope + inter), src in its
+ * stored dtype -- 0 uint8, 1 int16, 2 int32, 3 float32, 4 int8 -- so that a volume crosses PCIe in its on-disk width
+ * and is widened on the device.  Replaces `nib.load().get_fdata()` scaling + `.astype(float)` + torch.nan_to_num
+ * (Generator/utils.py:279, 304-305) + the float32 host->device copy. */
+int bfm_ingest_volume(float *dst, const void *src, int src_dtype, int64_t n, float slope, float inter, void *stream);
+
+/* The volume-sized N(0,1) fields of the chain (`torch.randn` of Generator/datasets.py:371 and utils.py:635) come from
+ * an in-kernel counter-based generator: Philox4x32-10 keyed on the per-sample `seed`, counter = (group index,
+ * stream), Box-Muller on the four 32-bit outputs; element e of a field is component e % 4 of group e / 4.  Streams:
+ * 0 GMM noise (indexed by the absolute SOURCE voxel), 1 acquisition noise (absolute low-res voxel), 2 / 3 the small
+ * deformation / bias grids.  This entry point writes out[0..n) = that sequence starting at group first_group, so that
+ * the distribution the kernels draw from can be tested on its own. */
+int bfm_philox_normal(float *out, int64_t n, uint64_t seed, uint32_t stream_id, uint64_t first_group, void *stream);
+
 /* x = nan_to_num(x) in place (torch.nan_to_num, Generator/utils.py:305): applied once when a real-image volume
  * enters the device cache instead of at every crop read. */
 int bfm_sanitize_f32(float *x, int64_t n, void *stream);
