@@ -231,18 +231,352 @@ class RK4(_FixedGrid):
         return y + (k1 + 3 * k2 + 3 * k3 + k4) * (dt / 8)
 
 
-def _unbuilt(name):
-    class _Missing:
-        def __init__(self, *a, **k):
-            raise NotImplementedError("ODE method %r is not built yet (SURVEY.md 8f-4)" % name)
-    return _Missing
+# ---------------------------------------------------------------------------------------------------------------
+# Tsitouras 5(4) (tsit5.py).  Reproduced AS THE REFERENCE BEHAVES, not as the textbook method: its error estimate
+# (c_error, tsit5.py:19-27) rejects steps until dt ~ 1e-7 on ordinary problems (the reference needed 300 s for a
+# 2-element linear ODE on [0, 1]), and its dense output starts from k[0] = f0 instead of y0 (tsit5.py:45-50).
+# The (t0, dt, accepted) trace of the first steps is pinned on the reference's (tests/golden/solvers.npz).
+_TSIT_ALPHA = [0.161, 0.327, 0.9, 0.9800255409045097, 1., 1.]
+_TSIT_BETA = [
+    [0.161],
+    [-0.008480655492357, 0.3354806554923570],
+    [2.897153057105494, -6.359448489975075, 4.362295432869581],
+    [5.32586482843925895, -11.74888356406283, 7.495539342889836, -0.09249506636175525],
+    [5.86145544294642038, -12.92096931784711, 8.159367898576159, -0.071584973281401006, -0.02826905039406838],
+    [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774],
+]
+_TSIT_C_ERROR = [
+    0.09646076681806523 - 0.001780011052226, 0.01 - 0.000816434459657, 0.4798896504144996 - -0.007880878010262,
+    1.379008574103742 - 0.144711007173263, -3.290069515436081 - -0.582357165452555,
+    2.324710524099774 - 0.458082105929187, -1 / 66,
+]
+
+
+def _tsit5_interp_coeff(t0, dt, eval_t):
+    t = float((eval_t - t0) / dt)
+    b1 = -1.0530884977290216 * t * (t - 1.3299890189751412) * (t ** 2 - 1.4364028541716351 * t + 0.7139816917074209)
+    b2 = 0.1017 * t ** 2 * (t ** 2 - 2.1966568338249754 * t + 1.2949852507374631)
+    b3 = 2.490627285651252793 * t ** 2 * (t ** 2 - 2.38535645472061657 * t + 1.57803468208092486)
+    b4 = -16.54810288924490272 * (t - 1.21712927295533244) * (t - 0.61620406037800089) * t ** 2
+    b5 = 47.37952196281928122 * (t - 1.203071208372362603) * (t - 0.658047292653547382) * t ** 2
+    b6 = -34.87065786149660974 * (t - 1.2) * (t - 0.666666666666666667) * t ** 2
+    b7 = 2.5 * (t - 1) * (t - 0.6) * t ** 2
+    return [b1, b2, b3, b4, b5, b6, b7]
+
+
+class Tsit5Solver(Dopri5Solver):
+    """tsit5.py:60-139: the Dormand-Prince machinery with the Tsitouras tableau, the plain step-size controller (no
+    clamp, no forced accept) and the reference's dense output.  `max_num_steps` bounds the steps per output time
+    (AssertionError like the reference's)."""
+
+    def __init__(self, func, y0, rtol, atol, dt=None, options=None, max_num_steps=2 ** 31 - 1):
+        super(Tsit5Solver, self).__init__(func, y0, rtol, atol, dt, options)
+        self.max_num_steps = (options or {}).get('max_num_steps', max_num_steps) if isinstance(options, dict) \
+            else max_num_steps
+
+    def _rk_step(self, y0, f0, t0, dt):
+        dt_state = float(torch.tensor(dt, dtype=y0.dtype))
+        ks = [f0]
+        yi = y0
+        for alpha, beta in zip(_TSIT_ALPHA, _TSIT_BETA):
+            yi = _combine(y0, ks, _scaled(dt_state, beta, y0.dtype))
+            ks.append(self.f(t0 + alpha * dt_state, yi))
+        y1 = yi                                   # c_sol == the last beta row (+ 0 * k7)
+        err = _combine(None, ks, _scaled(dt_state, _TSIT_C_ERROR, y0.dtype))
+        n = y0.numel()
+        acc = torch.empty(1, dtype=torch.float64, device=y0.device)
+        _lib.check(_lib.lib().bfm_rk_error_sum(err.data_ptr(), y0.data_ptr(), y1.data_ptr(),
+                                               1 if y0.dtype == torch.float64 else 0, n, float(self.rtol),
+                                               float(self.atol), acc.data_ptr(), stream()))
+        return y1, ks, float(acc.item()) / n
+
+    def integrate(self, t):
+        t = [float(v) for v in t.to(torch.float64).cpu()]
+        assert all(b > a for a, b in zip(t[:-1], t[1:])), 't must be strictly increasing or decrasing'
+        y0 = self.y0
+        f0 = self.f(t[0], y0)                      # _select_initial_step evaluates f(t0, y0) itself (no f0 passed,
+        dt = self._initial_step(t[0], y0, f0)      # tsit5.py:76) and before_integrate evaluates it again (:81):
+        f0 = self.f(t[0], y0)                      # three RHS evaluations before the first step, like the reference
+        t0 = t1 = t[0]
+        ks = [y0] * 7                             # interp_coeff before any accepted step (tsit5.py:80-83)
+        solution = [y0]
+        for next_t in t[1:]:
+            n_steps = 0
+            while next_t > t1:
+                assert n_steps < self.max_num_steps, 'max_num_steps exceeded ({}>={})'.format(n_steps, self.max_num_steps)
+                assert t1 + dt > t1, 'underflow in dt {}'.format(dt)
+                y1, k_new, ratio = self._rk_step(y0, f0, t1, dt)
+                accept = ratio <= 1
+                self.trace.append((t1, dt, bool(accept), ratio))
+                t0 = t1                            # rk_state.t0 is the step's start even when it is rejected (:138)
+                if accept:
+                    t1 = t1 + dt
+                    y0, f0, ks = y1, k_new[-1], k_new
+                dt = self._optimal_step(dt, ratio)
+                n_steps += 1
+            coef = _tsit5_interp_coeff(t0, t1 - t0, next_t) if t1 != t0 else [0.0] * 7
+            T = np.float64 if y0.dtype == torch.float64 else np.float32
+            dtt = T(t1 - t0)
+            cf = [float(T(dtt * T(c))) for c in coef]
+            if y0.dtype == torch.float32:
+                solution.append(_combine(ks[0].to(y0.dtype), [k.float() for k in ks], cf))
+            else:
+                solution.append(ks[0].to(y0.dtype) + sum(c * k.to(y0.dtype) for c, k in zip(cf, ks)))
+        return torch.stack(solution)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Variable-coefficient Adams-Bashforth-Moulton (adams.py; Hairer, Norsett, Wanner III.5)
+_GAMMA_STAR = [1, -1 / 2, -1 / 12, -1 / 24, -19 / 720, -3 / 160, -863 / 60480, -275 / 24192, -33953 / 3628800,
+               -0.00789255, -0.00678585, -0.00592406, -0.00523669, -0.0046775, -0.00421495, -0.0038269]
+
+
+def _lincomb(y0, tensors, coefs):
+    """y0 + sum_j coef_j * tensor_j in the state dtype (y0 None: the bare sum): the RK combination kernel for float32
+    states, torch arithmetic for float64 ones (the kernel sums float32 partials)."""
+    if not tensors:
+        return y0
+    ref = y0 if y0 is not None else tensors[0]
+    if ref.dtype == torch.float32 and all(t.dtype == torch.float32 for t in tensors):
+        return _combine(y0, [t.contiguous() for t in tensors], [_f32(c) for c in coefs])
+    acc = None
+    for c, t in zip(coefs, tensors):
+        term = t.to(ref.dtype) * c
+        acc = term if acc is None else acc + term
+    return acc if y0 is None else y0 + acc
+
+
+def _error_ratio(err, y0, y1, rtol, atol):
+    """mean((err / (atol + rtol * max(|y0|, |y1|)))^2)  (misc.py:146-157) -- one reduction kernel, one 8-byte read."""
+    n = y0.numel()
+    acc = torch.empty(1, dtype=torch.float64, device=y0.device)
+    e32 = err.float().contiguous()
+    _lib.check(_lib.lib().bfm_rk_error_sum(e32.data_ptr(), y0.data_ptr(), y1.data_ptr(),
+                                           1 if y0.dtype == torch.float64 else 0, n, float(rtol), float(atol),
+                                           acc.data_ptr(), stream()))
+    return float(acc.item()) / n
+
+
+class VariableCoefficientAdamsBashforth(_Base):
+    """adams.py:59-170.  Orders 1..12, predictor-corrector with the implicit (modified divided difference) update,
+    order and step-size selection as in the reference.  `trace` rows: (t_n, dt, accepted, error ratio, order)."""
+    _MAX_ORDER = 12
+
+    def __init__(self, func, y0, rtol, atol, dt=None, options=None, implicit=True, max_order=12, safety=0.9,
+                 ifactor=10.0, dfactor=0.2):
+        super(VariableCoefficientAdamsBashforth, self).__init__(func, y0, rtol, atol, dt, options)
+        self.implicit = implicit
+        self.max_order = int(max(1, min(max_order, self._MAX_ORDER)))
+        self.safety, self.ifactor, self.dfactor = safety, ifactor, dfactor
+
+    def _initial_step2(self, t0, y0, f0):
+        """_select_initial_step(order=2, f0 given)  (misc.py:84-143)."""
+        rtol, atol = self.rtol, self.atol
+        scale = atol + torch.abs(y0) * rtol
+        d0, d1 = _rms(y0 / scale), _rms(f0.to(y0.dtype) / scale)
+        h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * (d0 / d1)
+        h0 = float(torch.tensor(h0, dtype=y0.dtype))
+        y1 = y0 + h0 * f0.to(y0.dtype)
+        f1 = self.f(t0 + h0, y1)
+        d2 = _rms((f1 - f0).to(y0.dtype) / scale) / h0
+        if d1 <= 1e-15 and d2 <= 1e-15:
+            h1 = max(1e-6, h0 * 1e-3)
+        else:
+            h1 = (0.01 / max(d1, d2)) ** (1. / 3.)
+        return min(100 * h0, h1)
+
+    @staticmethod
+    def _g_and_beta(prev_t, next_t, k):
+        """g[0..k] and the beta_j that turn implicit phi_j into explicit ones (adams.py:26-48), float64 scalars."""
+        curr_t = prev_t[0]
+        dt = next_t - prev_t[0]
+        g = [0.0] * (k + 1)
+        betas = [1.0]
+        beta = 1.0
+        g[0] = 1.0
+        c = [1.0 / q for q in range(1, k + 2)]
+        for j in range(1, k):
+            beta = (next_t - prev_t[j - 1]) / (curr_t - prev_t[j]) * beta
+            betas.append(beta)
+            if j == 1:
+                c = [a - b for a, b in zip(c[:-1], c[1:])]
+            else:
+                c = [a - b * dt / (next_t - prev_t[j - 1]) for a, b in zip(c[:-1], c[1:])]
+            g[j] = c[0]
+        c = [a - b * dt / (next_t - prev_t[k - 1]) for a, b in zip(c[:-1], c[1:])]
+        g[k] = c[0]
+        return g, betas
+
+    @staticmethod
+    def _implicit_phi(explicit_phi, f_n, k):
+        k = min(len(explicit_phi) + 1, k)
+        out = [f_n]
+        for j in range(1, k):
+            out.append(out[j - 1] - explicit_phi[j - 1])
+        return out
+
+    def _opt_step(self, last, ratio, order):
+        if ratio == 0:
+            return last * self.ifactor
+        dfactor = 1.0 if ratio < 1 else self.dfactor
+        factor = max(1 / self.ifactor, min((ratio ** 0.5) ** (1 / order) / self.safety, 1 / dfactor))
+        return last / factor
+
+    def integrate(self, t):
+        ts = [float(v) for v in t.to(torch.float64).cpu()]
+        assert all(b > a for a, b in zip(ts[:-1], ts[1:])), 't must be strictly increasing or decrasing'
+        import collections
+        y_n = self.y0
+        prev_t = collections.deque(maxlen=self.max_order + 1)
+        phi = collections.deque(maxlen=self.max_order)
+        f0 = self.f(ts[0], y_n)
+        prev_t.appendleft(ts[0])
+        phi.appendleft(f0)
+        phi = list(phi)
+        next_t = ts[0] + self._initial_step2(ts[0], y_n, f0)
+        order = 1
+        solution = [y_n]
+        T = np.float64 if y_n.dtype == torch.float64 else np.float32
+        for final_t in ts[1:]:
+            while final_t > prev_t[0]:
+                nt = min(next_t, final_t)
+                dt = nt - prev_t[0]
+                dt_c = float(T(dt))
+                g, betas = self._g_and_beta(list(prev_t), nt, order)
+                g = [float(T(v)) for v in g]
+                ephi = [phi[0]] + [phi[j] * float(T(betas[j])) for j in range(1, order)]
+                m = max(1, order - 1)
+                p_next = _lincomb(y_n, ephi[:m], [float(T(dt_c * g[j])) for j in range(m)])
+                next_f0 = self.f(nt, p_next)
+                iphi_p = self._implicit_phi(ephi, next_f0, order + 1)
+                y_next = _lincomb(p_next, [iphi_p[order - 1]], [float(T(T(dt_c * g[order - 1])))])
+                local_error = iphi_p[order] * float(T(dt_c * (g[order] - g[order - 1])))
+                error_k = _error_ratio(local_error, y_n, y_next, self.rtol, self.atol)
+                accept = error_k <= 1
+                self.trace.append((prev_t[0], dt, bool(accept), error_k, order))
+                if not accept:
+                    next_t = prev_t[0] + self._opt_step(dt, error_k, order)
+                    continue
+                next_f0 = self.f(nt, y_next)
+                iphi = self._implicit_phi(ephi, next_f0, order + 2)
+                next_order = order
+                if len(prev_t) <= 4 or order < 3:
+                    next_order = min(order + 1, 3, self.max_order)
+                else:
+                    e1 = _error_ratio(iphi_p[order - 1] * float(T(dt_c * (g[order - 1] - g[order - 2]))), y_n, y_next,
+                                      self.rtol, self.atol)
+                    e2 = _error_ratio(iphi_p[order - 2] * float(T(dt_c * (g[order - 2] - g[order - 3]))), y_n, y_next,
+                                      self.rtol, self.atol)
+                    if min(e1, e2) < error_k:      # `min(error_km1 + error_km2)`: the + concatenates two 1-tuples (adams.py:152)
+                        next_order = order - 1
+                    elif order < self.max_order:
+                        e3 = _error_ratio(iphi_p[order] * float(T(dt_c * _GAMMA_STAR[order])), y_n, y_next, self.rtol,
+                                          self.atol)
+                        if e3 < error_k:
+                            next_order = order + 1
+                dt_next = dt if next_order > order else self._opt_step(dt, error_k, order + 1)
+                prev_t.appendleft(nt)
+                # the reference continues from the PREDICTOR p_next, not from the corrected y_next (adams.py:169)
+                y_n, phi, order = p_next, iphi[:self.max_order], next_order
+                next_t = nt + dt_next
+            assert final_t == prev_t[0]
+            solution.append(y_n)
+        return torch.stack(solution)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fixed-grid Adams-Bashforth(-Moulton) (fixed_adams.py).  The reference's step_func calls `rk_common.rk4_alt_step_func`
+# through a name its module never binds (`import ShapeID.DiffEqs.rk_common`, fixed_adams.py:5,165) and therefore
+# raises NameError on the first step; this is the algorithm of that file with the name resolved (the golden vectors
+# come from the reference with exactly that one attribute supplied, oracle/make_golden_solvers.py).
+_BASHFORTH = {
+    1: ([11], 11), 2: ([3, -1], 2), 3: ([23, -16, 5], 12), 4: ([55, -59, 37, -9], 24),
+    5: ([1901, -2774, 2616, -1274, 251], 720), 6: ([4277, -7923, 9982, -7298, 2877, -475], 1440),
+    7: ([198721, -447288, 705549, -688256, 407139, -134472, 19087], 60480),
+    8: ([434241, -1152169, 2183877, -2664477, 2102243, -1041723, 295767, -36799], 120960),
+    9: ([14097247, -43125206, 95476786, -139855262, 137968480, -91172642, 38833486, -9664106, 1070017], 3628800),
+    10: ([30277247, -104995189, 265932680, -454661776, 538363838, -444772162, 252618224, -94307320, 20884811,
+          -2082753], 7257600),
+    11: ([2132509567, -8271795124, 23591063805, -46113029016, 63716378958, -63176201472, 44857168434, -22329634920,
+          7417904451, -1479574348, 134211265], 479001600),
+}
+_MOULTON = {
+    1: ([1], 11), 2: ([1, 1], 2), 3: ([5, 8, -1], 12), 4: ([9, 19, -5, 1], 24), 5: ([251, 646, -264, 106, -19], 720),
+    6: ([475, 1427, -798, 482, -173, 27], 1440), 7: ([19087, 65112, -46461, 37504, -20211, 6312, -863], 60480),
+    8: ([36799, 139849, -121797, 123133, -88547, 41499, -11351, 1375], 120960),
+    9: ([1070017, 4467094, -4604594, 5595358, -5033120, 3146338, -1291214, 312874, -33953], 3628800),
+    10: ([2082753, 9449717, -11271304, 16002320, -17283646, 13510082, -7394032, 2687864, -583435, 57281], 7257600),
+    11: ([134211265, 656185652, -890175549, 1446205080, -1823311566, 1710774528, -1170597042, 567450984, -184776195,
+          36284876, -3250433], 479001600),
+    12: ([262747265, 1374799219, -2092490673, 3828828885, -5519460582, 6043521486, -4963166514, 3007739418,
+          -1305971115, 384709327, -68928781, 5675265], 958003200),
+}
+
+
+class AdamsBashforthMoulton(_FixedGrid):
+    """fixed_adams.py:136-205: RK4 (3/8 rule) until three derivatives are known, then Adams-Bashforth of order up to
+    11 with an Adams-Moulton corrector iterated to convergence (at most max_iters times)."""
+    order = 4
+
+    def __init__(self, func, y0, rtol=1e-3, atol=1e-4, dt=None, options=None, implicit=True, max_iters=4, max_order=12):
+        super(AdamsBashforthMoulton, self).__init__(func, y0, rtol, atol, dt, options)
+        self.implicit, self.max_iters = implicit, max_iters
+        self.max_order = int(min(max_order, 12))
+        import collections
+        self.prev_f = collections.deque(maxlen=self.max_order - 1)
+        self.prev_t = None
+
+    def _update_history(self, t, f):
+        if self.prev_t is None or self.prev_t != t:
+            self.prev_f.appendleft(f)
+            self.prev_t = t
+
+    def _converged(self, a, b):
+        tol = self.atol + self.rtol * torch.max(torch.abs(a), torch.abs(b))
+        return bool((torch.abs(a - b) < tol).all())
+
+    def step(self, t, dt, y):
+        self._update_history(t, self.f(t, y))
+        order = min(len(self.prev_f), self.max_order - 1)
+        if order < 3:
+            k1 = self.prev_f[0]                                  # rk4_alt_step_func(func, t, dt, y, k1=prev_f[0])
+            k2 = self.f(t + dt / 3, y + dt * k1 / 3)
+            k3 = self.f(t + dt * 2 / 3, y + dt * (k1 / -3 + k2))
+            k4 = self.f(t + dt, y + dt * (k1 - k2 + k3))
+            return y + (k1 + 3 * k2 + 3 * k3 + k4) * (dt / 8)
+        coefs, div = _BASHFORTH[order]
+        fs = list(self.prev_f)[:order]
+        dy = _lincomb(None, fs, [(1 / div) * c for c in coefs]) * dt
+        if self.implicit:
+            mc, mdiv = _MOULTON[order + 1]
+            delta = _lincomb(None, fs, [(1 / mdiv) * c for c in mc[1:]]) * dt
+            converged = False
+            for _ in range(self.max_iters):
+                dy_old = dy
+                f = self.f(t + dt, y + dy.to(y.dtype))
+                dy = dt * (mc[0] / mdiv) * f + delta
+                converged = self._converged(dy_old, dy)
+                if converged:
+                    break
+            if not converged:
+                import sys
+                print('Warning: Functional iteration did not converge. Solution may be incorrect.', file=sys.stderr)
+                self.prev_f.pop()
+            self._update_history(t, f)
+        return y + dy.to(y.dtype)
+
+
+class AdamsBashforth(AdamsBashforthMoulton):
+    def __init__(self, func, y0, **kwargs):
+        kwargs.pop('implicit', None)
+        super(AdamsBashforth, self).__init__(func, y0, implicit=False, **kwargs)
 
 
 SOLVERS = {
-    'explicit_adams': _unbuilt('explicit_adams'),
-    'fixed_adams': _unbuilt('fixed_adams'),
-    'adams': _unbuilt('adams'),
-    'tsit5': _unbuilt('tsit5'),
+    'explicit_adams': AdamsBashforth,
+    'fixed_adams': AdamsBashforthMoulton,
+    'adams': VariableCoefficientAdamsBashforth,
+    'tsit5': Tsit5Solver,
     'dopri5': Dopri5Solver,
     'euler': Euler,
     'midpoint': Midpoint,

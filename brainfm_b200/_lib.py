@@ -128,6 +128,8 @@ _PROTOS = {
                              c_p, C.POINTER(c_p), c_p, c_p, c_i64, C.POINTER(c_i64)]),
     "bfm_interpol": (c_i, [c_i, c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_i, c_i, c_i,
                            c_i, c_i, c_i, c_i64, c_p]),
+    "bfm_interpol_grad_backward": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i),
+                                         c_i, c_i, c_i, c_i, c_i64, c_p]),
     "bfm_interpol_pull_fast": (c_i, [c_p, C.POINTER(c_i64), c_p, c_i64, c_p, c_i, C.POINTER(c_i), c_i, C.POINTER(c_i),
                                      c_i, c_i, c_i, c_i64, c_p]),
     "bfm_add_identity_grid": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),

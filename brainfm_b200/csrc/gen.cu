@@ -933,7 +933,7 @@ __device__ __forceinline__ void warp_rows_pk(PkShared &sh, float *t1F, float *t1
 }
 
 #ifndef WARP_PK_MINB
-#define WARP_PK_MINB 3
+#define WARP_PK_MINB 4
 #endif
 __global__ void __launch_bounds__(256, WARP_PK_MINB)
 k_gen_warp_pk(const bfm_gen_sample *__restrict__ S, const __grid_constant__ PkParams P, int rpb, int t1f_cap) {
@@ -1651,10 +1651,21 @@ int bfm_gen_run(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *s
     int rc;
     if ((rc = bfm_gen_plan(h, d, B, stream))) return rc;
     if ((rc = bfm_gen_bbox(h, d, B, stream))) return rc;
-    if ((rc = bfm_gen_gmm(h, d, B, stream))) return rc;
-    if ((rc = bfm_gen_warp(h, d, B, stream))) return rc;
-    if ((rc = bfm_gen_resample(h, d, B, stream))) return rc;
-    return bfm_gen_finish(h, d, B, stream);
+    // The volume-sized stages run over groups of samples (sample-major order) so that what one stage writes is
+    // still in the 126 MB L2 when the next one reads it (syn: 4-8 B/voxel of the crop, i_bf / raw targets / out:
+    // 4 B/voxel each).  BFM_GEN_GROUP overrides the group size (0 = the whole batch, stage-major).
+    static const int group_env = getenv("BFM_GEN_GROUP") ? atoi(getenv("BFM_GEN_GROUP")) : -1;
+    int G = group_env;
+    if (G < 0) G = B;               // default decided by measurement (profiles/): see DESIGN.md
+    if (G <= 0 || G > B) G = B;
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int n = B - b0 < G ? B - b0 : G;
+        if ((rc = bfm_gen_gmm(h + b0, d + b0, n, stream))) return rc;
+        if ((rc = bfm_gen_warp(h + b0, d + b0, n, stream))) return rc;
+        if ((rc = bfm_gen_resample(h + b0, d + b0, n, stream))) return rc;
+        if ((rc = bfm_gen_finish(h + b0, d + b0, n, stream))) return rc;
+    }
+    return BFM_OK;
 }
 
 }  // extern "C"

@@ -142,6 +142,35 @@ __device__ __forceinline__ T spline_grad(int order, T xs) {
     return g * sgn;
 }
 
+// Spline.fasthess (splines.py:149-195): second derivative of the weight wrt the distance (even in x)
+template <typename T>
+__device__ __forceinline__ T spline_hess(int order, T xs) {
+    if (order <= 1) return T(0);
+    const T x = xs < 0 ? -xs : xs;
+    switch (order) {
+        case 2: return x < T(0.5) ? T(-2) : T(1);
+        case 3: return x < T(1) ? T(3) * x - T(2) : T(2) - x;
+        case 4:
+            if (x < T(0.5)) return T(3) * x * x - T(1.25);
+            if (x < T(1.5)) return x * (T(-2) * x + T(5)) - T(2.5);
+            { T a = T(2) * x - T(5); return a * a / T(8); }
+        case 5:
+            if (x < T(1)) { T a = x * x; return -a * (x * (T(5.) / T(3.)) - T(3)) - T(1); }
+            if (x < T(2)) return x * (x * (x * (T(5.) / T(6.)) - T(9.) / T(2.)) + T(15.) / T(2.)) - T(7.) / T(2.);
+            return T(9.) / T(2.) - x * (x * (x / T(6) - T(3.) / T(2.)) + T(9.) / T(2.));
+        case 6:
+            if (x < T(0.5)) { T a = x * x; return -a * (a * (T(5.) / T(6.)) - T(7.) / T(4.)) - T(77.) / T(96.); }
+            if (x < T(1.5)) return x * (x * (x * (x * (T(5.) / T(8.)) - T(35.) / T(12.)) + T(63.) / T(16.)) - T(35.) / T(48.)) - T(91.) / T(128.);
+            if (x < T(2.5)) return -(x * (x * (x * (x / T(4) - T(7.) / T(3.)) + T(63.) / T(8.)) - T(133.) / T(12.)) + T(329.) / T(64.));
+            return x * (x * (x * (x / T(24) - T(7.) / T(12.)) + T(49.) / T(16.)) - T(343.) / T(48.)) + T(2401.) / T(384.);
+        default:
+            if (x < T(1)) { T a = x * x; return a * (a * (x * (T(7.) / T(24.)) - T(5.) / T(6.)) + T(4.) / T(3.)) - T(2.) / T(3.); }
+            if (x < T(2)) return -(x * (x * (x * (x * (x * (T(7.) / T(40.)) - T(3.) / T(2.)) + T(14.) / T(3.)) - T(6)) + T(7.) / T(3.)) + T(1.) / T(5.));
+            if (x < T(3)) return x * (x * (x * (x * (x * (T(7.) / T(120.)) - T(5.) / T(6.)) + T(14.) / T(3.)) - T(38.) / T(3.)) + T(49.) / T(3.)) - T(23.) / T(3.);
+            return -(x * (x * (x * (x * (x / T(120) - T(1.) / T(6.)) + T(4.) / T(3.)) - T(16.) / T(3.)) + T(32.) / T(3.)) - T(128.) / T(15.));
+    }
+}
+
 struct InterpolArgs {
     int ishape[3];
     int order[3];
@@ -154,11 +183,16 @@ struct InterpolArgs {
     int64_t P;        // points per batch element
 };
 
-enum { MODE_PULL = 0, MODE_PUSH = 1, MODE_GRAD = 2 };
+// MODE_PUSHGRAD / MODE_HESSDOT: the two halves of grid_grad's backward pass (pushpull.py:303-325):
+//   PUSHGRAD  inp = incoming gradient (B, C, P, 3) -> out (B, C, *ishape) += sum_d inp_d * d/dg_d(weights)    (nd.py:292-365)
+//   HESSDOT   inp = image, gout = incoming gradient (B, C, P, 3) -> out (B, P, 3):
+//             out_e = sum_c sum_d gout[c, d] * d2/(dg_d dg_e) pull(inp_c)                         (nd.py:368-465, contracted)
+enum { MODE_PULL = 0, MODE_PUSH = 1, MODE_GRAD = 2, MODE_PUSHGRAD = 3, MODE_HESSDOT = 4 };
 
 template <typename T, int MAXN, int MODE>
 __global__ void __launch_bounds__(128) k_interpol(const T *__restrict__ inp, const T *__restrict__ grid,
-                                                   T *__restrict__ out, const InterpolArgs a) {
+                                                   T *__restrict__ out, const InterpolArgs a,
+                                                   const T *__restrict__ gout = nullptr) {
     const int64_t total = (int64_t)a.B * a.P;
     const int64_t vol = (int64_t)a.ishape[0] * a.ishape[1] * a.ishape[2];
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
@@ -166,7 +200,7 @@ __global__ void __launch_bounds__(128) k_interpol(const T *__restrict__ inp, con
         const int64_t p = q - (int64_t)b * a.P;
         const T *g = grid + ((int64_t)(a.Bg == 1 ? 0 : b) * a.P + p) * 3;
         int idx[3][MAXN];
-        T w[3][MAXN], gw[3][MAXN];
+        T w[3][MAXN], gw[3][MAXN], hw[3][MAXN];
         bool inb = true;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -188,8 +222,9 @@ __global__ void __launch_bounds__(128) k_interpol(const T *__restrict__ inp, con
                     idx[d][k] = bound_index(a.bound[d], i0 + k, n);
                     const T dist = dist0 - T(k);
                     w[d][k] = (o == 0 ? T(1) : spline_weight<T>(o, dist)) * T(sg);
-                    if (MODE == MODE_GRAD)
+                    if (MODE == MODE_GRAD || MODE == MODE_PUSHGRAD || MODE == MODE_HESSDOT)
                         gw[d][k] = (a.iso == 2 ? (k == 0 ? T(-1) : T(1)) : spline_grad<T>(o, dist)) * T(sg);
+                    if (MODE == MODE_HESSDOT) hw[d][k] = a.iso == 2 ? T(0) : spline_hess<T>(o, dist) * T(sg);
                 }
             }
         }
@@ -215,6 +250,42 @@ __global__ void __launch_bounds__(128) k_interpol(const T *__restrict__ inp, con
                     o3[0] = a0 * m; o3[1] = a1 * m; o3[2] = a2 * m;
                 }
             }
+        } else if (MODE == MODE_PUSHGRAD) {
+            for (int c = 0; c < a.C; ++c) {
+                const T *g3 = inp + (((int64_t)(a.Bi == 1 ? 0 : b) * a.C + c) * a.P + p) * 3;
+                const T g0 = g3[0] * m, g1 = g3[1] * m, g2 = g3[2] * m;
+                T *dst = out + ((int64_t)b * a.C + c) * vol;
+                for (int kx = 0; kx <= a.order[0]; ++kx)
+                    for (int ky = 0; ky <= a.order[1]; ++ky)
+                        for (int kz = 0; kz <= a.order[2]; ++kz)
+                            atomicAdd(dst + ((int64_t)idx[0][kx] * a.ishape[1] + idx[1][ky]) * a.ishape[2] + idx[2][kz],
+                                      g0 * gw[0][kx] * w[1][ky] * w[2][kz] + g1 * w[0][kx] * gw[1][ky] * w[2][kz] +
+                                          g2 * w[0][kx] * w[1][ky] * gw[2][kz]);
+            }
+        } else if (MODE == MODE_HESSDOT) {
+            T o0 = 0, o1 = 0, o2 = 0;
+            for (int c = 0; c < a.C; ++c) {
+                const T *src = inp + ((int64_t)(a.Bi == 1 ? 0 : b) * a.C + c) * vol;
+                T h00 = 0, h11 = 0, h22 = 0, h01 = 0, h02 = 0, h12 = 0;
+                for (int kx = 0; kx <= a.order[0]; ++kx)
+                    for (int ky = 0; ky <= a.order[1]; ++ky)
+                        for (int kz = 0; kz <= a.order[2]; ++kz) {
+                            const T v = src[((int64_t)idx[0][kx] * a.ishape[1] + idx[1][ky]) * a.ishape[2] + idx[2][kz]];
+                            h00 += v * hw[0][kx] * w[1][ky] * w[2][kz];
+                            h11 += v * w[0][kx] * hw[1][ky] * w[2][kz];
+                            h22 += v * w[0][kx] * w[1][ky] * hw[2][kz];
+                            h01 += v * gw[0][kx] * gw[1][ky] * w[2][kz];
+                            h02 += v * gw[0][kx] * w[1][ky] * gw[2][kz];
+                            h12 += v * w[0][kx] * gw[1][ky] * gw[2][kz];
+                        }
+                const T *g3 = gout + (((int64_t)b * a.C + c) * a.P + p) * 3;
+                const T g0 = g3[0], g1 = g3[1], g2 = g3[2];
+                o0 += g0 * h00 + g1 * h01 + g2 * h02;
+                o1 += g0 * h01 + g1 * h11 + g2 * h12;
+                o2 += g0 * h02 + g1 * h12 + g2 * h22;
+            }
+            T *o3 = out + ((int64_t)b * a.P + p) * 3;
+            o3[0] = o0 * m; o3[1] = o1 * m; o3[2] = o2 * m;
         } else {  // push / count (inp == nullptr => ones)
             for (int c = 0; c < a.C; ++c) {
                 const T v0 = (inp ? inp[((int64_t)(a.Bi == 1 ? 0 : b) * a.C + c) * a.P + p] : T(1)) * m;
@@ -502,7 +573,8 @@ __global__ void __launch_bounds__(128) k_spline_filter_tile(float *__restrict__ 
 }
 
 template <typename T>
-static int launch_interpol(int mode, const void *inp, const void *grid, void *out, const InterpolArgs &a, cudaStream_t s) {
+static int launch_interpol(int mode, const void *inp, const void *grid, void *out, const InterpolArgs &a, cudaStream_t s,
+                           const void *gout = nullptr) {
     const int maxo = a.order[0] > a.order[1] ? (a.order[0] > a.order[2] ? a.order[0] : a.order[2])
                                              : (a.order[1] > a.order[2] ? a.order[1] : a.order[2]);
     const int64_t total = (int64_t)a.B * a.P;
@@ -515,6 +587,8 @@ static int launch_interpol(int mode, const void *inp, const void *grid, void *ou
     do {                                                                                                 \
         if (mode == MODE_PULL) k_interpol<T, MAXN, MODE_PULL><<<(unsigned)gsz, 128, 0, s>>>(ip, gp, op, a);    \
         else if (mode == MODE_PUSH) k_interpol<T, MAXN, MODE_PUSH><<<(unsigned)gsz, 128, 0, s>>>(ip, gp, op, a); \
+        else if (mode == MODE_PUSHGRAD) k_interpol<T, MAXN, MODE_PUSHGRAD><<<(unsigned)gsz, 128, 0, s>>>(ip, gp, op, a); \
+        else if (mode == MODE_HESSDOT) k_interpol<T, MAXN, MODE_HESSDOT><<<(unsigned)gsz, 128, 0, s>>>(ip, gp, op, a, (const T *)gout); \
         else k_interpol<T, MAXN, MODE_GRAD><<<(unsigned)gsz, 128, 0, s>>>(ip, gp, op, a);                      \
     } while (0)
     if (maxo <= 1) BFM_GO(2);
@@ -550,6 +624,33 @@ int bfm_interpol(int mode, int is_double, const void *inp, const void *grid, voi
     if (P == 0) return BFM_OK;
     return is_double ? launch_interpol<double>(mode, inp, grid, out, a, (cudaStream_t)stream)
                      : launch_interpol<float>(mode, inp, grid, out, a, (cudaStream_t)stream);
+}
+
+int bfm_interpol_grad_backward(int is_double, const void *gout, const void *inp, const void *grid, void *grad_inp,
+                               void *grad_grid, const int *ishape, const int *order, const int *bound, int extrapolate,
+                               int iso, int B, int C, int64_t P, void *stream) {
+    BFM_REQUIRE(gout && inp && grid && ishape && order && bound, "bfm_interpol_grad_backward: null pointer");
+    BFM_REQUIRE(B > 0 && C > 0 && P >= 0, "bfm_interpol_grad_backward: bad batch");
+    BFM_REQUIRE(iso >= 0 && iso <= 2 && extrapolate >= 0 && extrapolate <= 2, "bfm_interpol_grad_backward: bad option");
+    InterpolArgs a;
+    for (int d = 0; d < 3; ++d) {
+        if (ishape[d] <= 0) return fail(BFM_E_INVALID, "%s", "bfm_interpol_grad_backward: non-positive shape");
+        if (order[d] < 0 || order[d] > 7) return fail(BFM_E_INVALID, "%s", "bfm_interpol_grad_backward: order must be 0..7");
+        if (bound[d] < 0 || bound[d] > 6) return fail(BFM_E_INVALID, "%s", "bfm_interpol_grad_backward: bound must be 0..6");
+        a.ishape[d] = ishape[d]; a.order[d] = order[d]; a.bound[d] = bound[d];
+    }
+    a.extrapolate = extrapolate; a.iso = iso;
+    a.B = B; a.C = C; a.Bi = B; a.Bg = B; a.P = P;
+    if (P == 0) return BFM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = BFM_OK;
+    if (grad_inp)
+        rc = is_double ? launch_interpol<double>(MODE_PUSHGRAD, gout, grid, grad_inp, a, st)
+                       : launch_interpol<float>(MODE_PUSHGRAD, gout, grid, grad_inp, a, st);
+    if (rc == BFM_OK && grad_grid)
+        rc = is_double ? launch_interpol<double>(MODE_HESSDOT, inp, grid, grad_grid, a, st, gout)
+                       : launch_interpol<float>(MODE_HESSDOT, inp, grid, grad_grid, a, st, gout);
+    return rc;
 }
 
 int bfm_interpol_pull_fast(const float *inp, const int64_t *istride, const float *grid, int64_t grid_bstride,

@@ -213,6 +213,51 @@ class _Pull(torch.autograd.Function):
         return gi, gg, None, None, None
 
 
+class _Grad(torch.autograd.Function):
+    """grid_grad with its adjoints (utils/interpol/autograd.py:216-243, pushpull.py grid_grad_backward):
+    d/d input = push of the incoming gradient with the derivative weights (grid_pushgrad), d/d grid = the spline
+    Hessian of the input contracted with the incoming gradient (grid_hess)."""
+
+    @staticmethod
+    def forward(ctx, input, grid, order, bound, ext):
+        ctx.opt = (order, bound, ext)
+        ctx.save_for_backward(input, grid)
+        return _pull_raw(input, grid, order, bound, ext, mode=2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        input, grid = ctx.saved_tensors
+        order, bound, ext = ctx.opt
+        dim = grid.shape[-1]
+        B, Cn = input.shape[:2]
+        ishape = list(input.shape[2:])
+        oshape = list(grid.shape[1:-1])
+        P = int(math.prod(oshape))
+        dt = torch.promote_types(input.dtype, grid.dtype)
+        inp = input.to(dt).contiguous()
+        g = _grid3(grid.to(dt).reshape(B, P, dim))
+        go = grad.to(dt).reshape(B, Cn, P, dim)
+        if dim < 3:                                   # padded leading axes: zero incoming gradient there
+            g3 = go.new_zeros(B, Cn, P, 3)
+            g3[..., 3 - dim:] = go
+            go = g3
+        go = go.contiguous()
+        gi = torch.zeros_like(inp) if ctx.needs_input_grad[0] else None
+        gg = torch.empty((B, P, 3), dtype=dt, device=inp.device) if ctx.needs_input_grad[1] else None
+        pad = 3 - dim
+        iso = 1 if all(o == 0 for o in order) else (2 if all(o == 1 for o in order) else 0)
+        _lib.check(_lib.lib().bfm_interpol_grad_backward(
+            1 if dt == torch.float64 else 0, go.data_ptr(), inp.data_ptr(), g.data_ptr(),
+            None if gi is None else gi.data_ptr(), None if gg is None else gg.data_ptr(),
+            (C.c_int * 3)(*_pad3(ishape)), (C.c_int * 3)(*([0] * pad + order)), (C.c_int * 3)(*([1] * pad + bound)),
+            ext, iso, B, Cn, P, _stream()))
+        if gi is not None:
+            gi = gi.to(input.dtype)
+        if gg is not None:
+            gg = gg[..., 3 - dim:].reshape(B, *oshape, dim).to(grid.dtype)
+        return gi, gg, None, None, None
+
+
 class _Push(torch.autograd.Function):
     """grid_push (autograd.py:158-188): d/d input = pull of the incoming gradient, d/d grid = sum_c input_c *
     (spatial gradient of grad_c at grid)."""
@@ -301,15 +346,15 @@ def grid_grad(input, grid, interpolation='linear', bound='zero', extrapolate=Fal
     """Sample spatial gradients of an image (utils/interpol/api.py:290-332)."""
     _need(grid, 'grid')
     _need(input, 'input')
-    if _wants_grad(input, grid):
-        raise NotImplementedError("grid_grad is forward-only here (its backward needs spline Hessians); "
-                                  "detach the inputs or call it under torch.no_grad()")
     dim = grid.shape[-1]
     order, bnd, ext = _orders(interpolation, dim), _bounds(bound, dim), _extrap(extrapolate)
     grid, input, info = _preproc(grid, input)
     if prefilter:
         input = spline_coeff_nd(input, interpolation=interpolation, bound=bound, dim=dim)
-    out = _pull_raw(input, grid, order, bnd, ext, mode=2)
+    if _wants_grad(input, grid):
+        out = _Grad.apply(input, grid, order, bnd, ext)
+    else:
+        out = _pull_raw(input, grid, order, bnd, ext, mode=2)
     return _postproc(out, info, 'grad')
 
 

@@ -387,6 +387,16 @@ int bfm_interpol(int mode, int is_double, const void *inp, const void *grid, voi
                  const int *order, const int *bound, int extrapolate, int iso, int B, int C, int Bi, int Bg,
                  int64_t P, void *stream);
 
+/* Backward pass of grid_grad                                            utils/interpol/autograd.py:216-243,
+ *                                                                      pushpull.py:303-325, nd.py:292-465
+ * gout: incoming gradient (B, C, P, 3); inp (B, C, X, Y, Z); grid (B, P, 3) -- all with the full batch.
+ * grad_inp (optional, (B, C, X, Y, Z), PRE-ZEROED): push of gout with the first-derivative weights (grid_pushgrad).
+ * grad_grid (optional, (B, P, 3)): sum over channels and d of gout[..., d] * Hessian[..., d, :] (grid_hess contracted
+ * with gout), second-derivative weights Spline.fasthess (splines.py:149-195); zero Hessian diagonal for order <= 1. */
+int bfm_interpol_grad_backward(int is_double, const void *gout, const void *inp, const void *grid, void *grad_inp,
+                               void *grad_grid, const int *ishape, const int *order, const int *bound, int extrapolate,
+                               int iso, int B, int C, int64_t P, void *stream);
+
 /* grid_pull fast path: float32, the same spline order (1 = linear, 3 = cubic) on all three axes.
  * inp is addressed through element strides istride[5] = (batch, channel, x, y, z) -- a channels-last view (e.g. a
  * permuted displacement field) is read in place; a zero batch stride broadcasts.  grid (B or 1, P, 3) with batch

@@ -44,6 +44,18 @@ def test_gradcheck_pull(dim, bound, interpolation):
 
 @pytest.mark.parametrize("dim", [1, 2, 3])
 @pytest.mark.parametrize("interpolation,bound", order_bounds)
+def test_gradcheck_grad(dim, bound, interpolation):
+    """utils/interpol/tests/test_gradcheck_pushpull.py:62-74: the backward of grid_grad (push with derivative weights
+    + spline Hessians, bfm_interpol_grad_backward)."""
+    from brainfm_b200.interpol import grid_grad
+    vol, grid = make_data((shape1,) * dim, 300 * dim + 10 * interpolation + bound)
+    vol.requires_grad = True
+    grid.requires_grad = True
+    assert gradcheck(grid_grad, (vol, grid, interpolation, NAMES[bound], extrapolate), **kwargs)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("interpolation,bound", order_bounds)
 def test_gradcheck_push(dim, bound, interpolation):
     from brainfm_b200.interpol import grid_push
     shape = (shape1,) * dim

@@ -87,3 +87,112 @@ def test_default_dataloader_collation_like_the_reference_trainer():
         assert len(target['name']) == 2
         n += 1
     assert n == 2 and len(ds) == 4
+
+
+def test_device_pipeline_two_lanes_equals_one_stream():
+    """DevicePipeline (two batches in flight on their own streams and scratch) produces the batches generate_batch
+    produces one after the other: same planner stream, same kernels, no cross-talk between the lanes."""
+    from brainfm_b200.pipeline import DevicePipeline
+    ds, subs = _dataset()
+    idx = [0, 1, 2, 3]
+
+    def sequential():
+        return [torch.cat([it[4]['input'] for it in ds.generate_batch(idx)], 0).clone() for _ in range(4)]
+
+    def piped():
+        pipe = DevicePipeline(ds, depth=2)
+        tickets = [pipe.submit(idx) for _ in range(4)]
+        outs = [torch.cat([it[4]['input'] for it in t.wait()], 0).clone() for t in tickets]
+        t1 = [torch.cat([it[3]['T1'] for it in t.items], 0).clone() for t in tickets]
+        return outs, t1
+
+    ref = _run(ds, sequential)
+    got, t1 = _run(ds, piped)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    assert not torch.equal(got[0], got[1])
+    for t in t1:
+        assert torch.isfinite(t).all() and float(t.min()) == 0.0 and float(t.max()) == 1.0
+
+
+def test_cache_eviction_is_lru_and_spares_the_batch_in_flight():
+    from brainfm_b200 import io as bio
+    bio.clear_registry()
+    dev = torch.device("cuda", 0)
+    vols = {"/v/%d.nii" % k: np.full((16, 16, 16), k, np.float32) for k in range(6)}
+    for p, v in vols.items():
+        bio.register_volume(p, v)
+    one = 4 * (16 ** 3 + 16 * 16 + 16 + 1)
+    cache = bio.DeviceVolumeCache(dev, max_bytes=3 * one + 100)
+    cache.begin_batch()
+    a = [cache.get("/v/%d.nii" % k) for k in range(3)]
+    ptrs = [t.data_ptr() for t in a]
+    with pytest.raises(MemoryError):                       # a fourth volume in the SAME batch does not fit
+        cache.get("/v/3.nii")
+    assert cache.evictions == 0 and all(("/v/%d.nii" % k, "f32") in cache for k in range(3))
+    cache.begin_batch()                                    # previous batch: still protected (its launches may be pending)
+    with pytest.raises(MemoryError):
+        cache.get("/v/3.nii")
+    cache.begin_batch()
+    cache.get("/v/1.nii")                                  # touch 1: volume 0 is now the least recently used
+    cache.begin_batch()
+    cache.begin_batch()
+    t3 = cache.get("/v/3.nii")
+    assert cache.evictions == 1 and ("/v/0.nii", "f32") not in cache and ("/v/1.nii", "f32") in cache
+    assert float(t3.mean()) == 3.0 and cache.nbytes <= cache.max_bytes
+    # the evicted volume comes back from the registry when asked for again
+    cache.begin_batch(); cache.begin_batch()
+    assert float(cache.get("/v/0.nii").mean()) == 0.0 and cache.evictions == 2
+    assert [float(t.mean()) for t in a] == [0.0, 1.0, 2.0] and ptrs == [t.data_ptr() for t in a]   # callers' refs stay valid
+    bio.clear_registry()
+
+
+def test_upload_reaches_every_reader_and_drops_derived_tensors():
+    """One cache per device: a refreshed segmentation / image volume is what the op-wise target readers see."""
+    from oracle import make_golden as mg
+    from tests._harness import cuda_case, oracle_case
+    from brainfm_b200.Generator import utils as gu
+    name = "g64_full_s4"
+    _, orc = oracle_case(name)
+    got, ds, _ = cuda_case(name, orc.log)
+    assert gu._cache(ds.device) is ds.cache
+    seg_path = ds.modalities['segmentation']
+    before = got[3]['segmentation'].clone()
+    new_seg = torch.zeros(ds.cache.get(seg_path, 'i32').shape, dtype=torch.int32)          # all background
+    ds.cache.derived('probe', (seg_path,), lambda: torch.ones(4, device=ds.device))
+    ds.cache.upload(seg_path, 'i32', new_seg.pin_memory())
+    assert not any(seg_path in k[1] for k in ds.cache._derived)
+    ds.rng.pos = 0
+    got2 = ds[0]
+    torch.cuda.synchronize()
+    after = got2[3]['segmentation']
+    assert not torch.equal(before, after)
+    present = after.amax(dim=(1, 2, 3))                                          # a constant label map: one class
+    assert float(present.sum()) == 1.0 and float(after.sum(0).min()) == 1.0
+
+
+@pytest.mark.parametrize("dtype,code", [(np.uint8, 0), (np.int16, 1), (np.int32, 2), (np.float32, 3), (np.int8, 4)])
+def test_ingest_volume_dtypes(dtype, code):
+    import ctypes as C
+    from brainfm_b200 import _lib
+    rng = np.random.RandomState(code)
+    n = 160 * 157 + 3                                       # not a multiple of the vector width
+    if dtype == np.float32:
+        a = rng.randn(n).astype(np.float32) * 100
+        a[::97] = np.nan
+        a[5::131] = np.inf
+        a[7::131] = -np.inf
+    else:
+        info = np.iinfo(dtype)
+        a = rng.randint(info.min, int(info.max) + 1, size=n, dtype=np.int64).astype(dtype)
+    src = torch.from_numpy(a).cuda()
+    dst = torch.empty(n, dtype=torch.float32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for slope, inter in ((1.0, 0.0), (0.5, -3.0)):
+        _lib.check(_lib.lib().bfm_ingest_volume(dst.data_ptr(), src.data_ptr(), code, n, slope, inter, st))
+        want = torch.nan_to_num(torch.from_numpy(a.astype(np.float32)) * np.float32(slope) + np.float32(inter))
+        assert torch.equal(dst.cpu(), want)
+    # unaligned views take the scalar path
+    _lib.check(_lib.lib().bfm_ingest_volume(dst.data_ptr() + 4, src.data_ptr() + a.itemsize, code, n - 1, 1.0, 0.0, st))
+    assert torch.equal(dst[1:].cpu(), torch.nan_to_num(torch.from_numpy(a[1:].astype(np.float32))))
