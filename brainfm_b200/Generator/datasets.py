@@ -474,7 +474,7 @@ class BaseGen(Dataset):
         res_all = torch.empty((n_res, 1, *size), dtype=torch.float32, device=dev) if n_res else None
         aux_all = torch.empty((n_aux, 1, *size), dtype=torch.float32, device=dev) if n_aux else None
         # persistent scratch: syn is zero-initialised once and afterwards only ever holds finite values
-        src_pad = max(int(np.prod(j['plan'].src)) + j['plan'].src[1] * j['plan'].src[2] + j['plan'].src[2] + 1
+        src_pad = max(int(np.prod(j['plan'].src)) + j['plan'].src[1] * j['plan'].src[2] + j['plan'].src[2] + 9
                       for j in jobs)
         src_pad = 2 * ((src_pad + 3) // 4 * 4)         # room for float2 {synthetic, T1} pairs (syn_pair_ok)
         syn_ws = self._workspace('syn', B * src_pad, zero=True)

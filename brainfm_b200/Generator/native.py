@@ -186,7 +186,7 @@ class NativePlanner:
             for c, (key, vol) in enumerate(aux):
                 it.aux_src[c] = vol.data_ptr()
             n_aux_total += len(aux)
-            src_pad = max(src_pad, src[0] * src[1] * src[2] + src[1] * src[2] + src[2] + 1)
+            src_pad = max(src_pad, src[0] * src[1] * src[2] + src[1] * src[2] + src[2] + 9)
             metas.append((idx, dataset_name, t1_path, age, dict(mods), aux, src))
         src_pad = (src_pad + 3) // 4 * 4
         # ---- outputs (fresh) and persistent scratch

@@ -12,8 +12,10 @@ an exchange step, both point-to-point between neighbouring ranks (parallel.excha
   2. the zoom back to the training grid needs the 1-2 low-res planes next to the slab.
 
 The global maximum of I / max(I) is one scalar all-reduce.  Per voxel the arithmetic is that of the op-level
-path (resample_resolution -> add_noise -> myzoom_torch), so a volume generated on W ranks is bit-identical to
-the same volume generated in slab mode on one rank.
+path (resample_resolution -> add_noise -> myzoom_torch) and both volume-sized noise fields are counter-based (GMM
+noise keyed on the absolute source voxel, acquisition noise on the absolute low-res voxel, bfm_add_noise_at), so a
+volume generated on W ranks is bit-identical to the same volume generated in slab mode on one rank -- with injected
+draws or without (tests/test_gen_parity_gpu.py, tests/_slab_worker.py).
 """
 import ctypes as C
 
@@ -105,14 +107,16 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     for ax in (1, 2):
         st_a, w_a, T_a = band_host(size[ax], new[ax], stds[ax])
         x = _band_axis(x, ax, new[ax], st_a, w_a, T_a, arena)
-    # ---- noise (add_noise, utils.py:633-638): injected draws are sliced, otherwise a per-rank stream
+    # ---- noise (add_noise, utils.py:633-638): injected draws are sliced; otherwise the chain's counter-based stream 1,
+    # keyed on the ABSOLUTE low-res voxel -- the assembled volume does not depend on the number of ranks, and equals
+    # what the fused chain (generate_batch) draws for the same seed
     if p['eps_noise'] is not None:
         eps = p['eps_noise'][ob:oe].to(x.device)
+        low = torch.clamp(x + float(p['noise_std']) * eps, min=0)
     else:
-        gen = torch.Generator(device=x.device)
-        gen.manual_seed((int(p['seed']) ^ (0x9E3779B9 * (rank + 1))) & 0x7FFFFFFFFFFFFFFF)
-        eps = torch.randn(x.shape, dtype=torch.float32, device=x.device, generator=gen)
-    low = torch.clamp(x + float(p['noise_std']) * eps, min=0)
+        low = x.contiguous()
+        _lib.check(L.bfm_add_noise_at(low.data_ptr(), low.numel(), float(p['noise_std']), int(p['seed']), 1,
+                                      ob * new[1] * new[2], _stream()))
 
     # ---- back to the training grid: low-res planes lo[c0] .. hi[c1-1] (1-2 from the neighbours)
     up = 1 / (np.array(new) / np.array(size))

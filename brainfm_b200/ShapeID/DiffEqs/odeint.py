@@ -306,6 +306,7 @@ class Tsit5Solver(Dopri5Solver):
                 assert n_steps < self.max_num_steps, 'max_num_steps exceeded ({}>={})'.format(n_steps, self.max_num_steps)
                 assert t1 + dt > t1, 'underflow in dt {}'.format(dt)
                 y1, k_new, ratio = self._rk_step(y0, f0, t1, dt)
+                assert ratio == ratio, 'non-finite values in state `y`'
                 accept = ratio <= 1
                 self.trace.append((t1, dt, bool(accept), ratio))
                 t0 = t1                            # rk_state.t0 is the step's start even when it is rejected (:138)
@@ -452,6 +453,8 @@ class VariableCoefficientAdamsBashforth(_Base):
                 y_next = _lincomb(p_next, [iphi_p[order - 1]], [float(T(T(dt_c * g[order - 1])))])
                 local_error = iphi_p[order] * float(T(dt_c * (g[order] - g[order - 1])))
                 error_k = _error_ratio(local_error, y_n, y_next, self.rtol, self.atol)
+                assert error_k == error_k, 'non-finite values in state `y`'
+                assert prev_t[0] + dt > prev_t[0], 'underflow in dt {}'.format(dt)
                 accept = error_k <= 1
                 self.trace.append((prev_t[0], dt, bool(accept), error_k, order))
                 if not accept:

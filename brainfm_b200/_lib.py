@@ -109,6 +109,7 @@ _PROTOS = {
     "bfm_upload_pinned": (c_i, [c_p, c_p, c_i64, c_p]),
     "bfm_sanitize_f32": (c_i, [c_p, c_i64, c_p]),
     "bfm_ingest_volume": (c_i, [c_p, c_p, c_i, c_i64, c_f, c_f, c_p]),
+    "bfm_add_noise_at": (c_i, [c_p, c_i64, c_f, c_u64, C.c_uint32, c_i64, c_p]),
     "bfm_philox_normal": (c_i, [c_p, c_i64, c_u64, C.c_uint32, c_u64, c_p]),
     "bfm_band_build": (c_i, [c_i, c_i, C.c_double, c_i, c_p, c_p, c_p]),
     "bfm_minmax": (c_i, [c_p, c_i64, c_p, c_p]),

@@ -474,6 +474,27 @@ __global__ void __launch_bounds__(256) k_philox_normal(float *__restrict__ out, 
     }
 }
 
+// x[i] = max(0, x[i] + noise_std * eps[first + i]), eps = the chain's stream-`stream` normal sequence of `seed`
+// (element e = component e & 3 of Philox group e >> 2): add_noise (Generator/utils.py:633-638) for a PART of a volume
+// whose first element has the absolute index `first` -- a slab of a volume cut across GPUs draws exactly the numbers
+// the whole volume would.
+__global__ void __launch_bounds__(256) k_add_noise_at(float *__restrict__ x, int64_t n, float noise_std, uint64_t seed,
+                                                      uint32_t stream, int64_t first) {
+    const int64_t g0 = first >> 2, g1 = (first + n - 1) >> 2;
+    for (int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= g1; g += (int64_t)gridDim.x * blockDim.x) {
+        const float4 e = philox_normal4(seed, stream, (uint64_t)g);
+        const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t i = 4 * g + c - first;
+            if (i >= 0 && i < n) {
+                const float v = __fadd_rn(x[i], __fmul_rn(noise_std, ev[c]));
+                x[i] = v < 0.f ? 0.f : v;
+            }
+        }
+    }
+}
+
 static inline int grid_for(int64_t n, int block = 256) {
     int64_t g = (n + block - 1) / block;
     const int64_t cap = 148LL * 32;
@@ -511,6 +532,15 @@ int bfm_ingest_volume(float *dst, const void *src, int src_dtype, int64_t n, flo
         default: return fail(BFM_E_INVALID, "%s", "bfm_ingest_volume: src_dtype must be 0 (u8), 1 (i16), 2 (i32), 3 (f32) or 4 (i8)");
     }
     return check_launch("bfm_ingest_volume");
+}
+
+int bfm_add_noise_at(float *x, int64_t n, float noise_std, uint64_t seed, uint32_t stream_id, int64_t first_element,
+                     void *stream) {
+    BFM_REQUIRE(x && n >= 0 && first_element >= 0, "bfm_add_noise_at: bad argument");
+    if (n == 0) return BFM_OK;
+    k_add_noise_at<<<grid_for((n + 3) / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x, n, noise_std, seed, stream_id,
+                                                                                  first_element);
+    return check_launch("bfm_add_noise_at");
 }
 
 int bfm_philox_normal(float *out, int64_t n, uint64_t seed, uint32_t stream_id, uint64_t first_group, void *stream) {

@@ -68,6 +68,14 @@ class DevicePipeline:
         self.device = ds.device
         self.lanes = [dict(stream=torch.cuda.Stream(device=self.device), ws={}) for _ in range(max(1, int(depth)))]
         self._k = 0
+        # the plan arena is a ring whose slot k is reused only after batch k - len(ring) has finished on the GPU: with
+        # the default 3 slots the host could not plan batch k before batch k - 3 is done, which leaves a lane idle
+        # while batch k is being planned (measured: 0.93 instead of 0.72 ms per step).  2 * depth + 2 slots keep every
+        # lane one batch ahead.
+        want = 2 * len(self.lanes) + 2
+        if len(ds.arena.slots) < want:
+            from .plan import Arena
+            ds.arena = Arena(ds.device, capacity=ds.arena.capacity, slots=want)
 
     def submit(self, indices, timers=None):
         ds = self.ds

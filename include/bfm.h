@@ -93,6 +93,12 @@ int bfm_ingest_volume(float *dst, const void *src, int src_dtype, int64_t n, flo
  * the distribution the kernels draw from can be tested on its own. */
 int bfm_philox_normal(float *out, int64_t n, uint64_t seed, uint32_t stream_id, uint64_t first_group, void *stream);
 
+/* add_noise (Generator/utils.py:633-638) on a PART of a volume: x[i] = max(0, x[i] + noise_std * eps[first_element + i])
+ * with eps the stream-`stream_id` sequence of bfm_philox_normal.  Slab mode (one volume cut across GPUs) passes the
+ * absolute low-res index of its first voxel, so the assembled volume does not depend on the decomposition. */
+int bfm_add_noise_at(float *x, int64_t n, float noise_std, uint64_t seed, uint32_t stream_id, int64_t first_element,
+                     void *stream);
+
 /* x = nan_to_num(x) in place (torch.nan_to_num, Generator/utils.py:305): applied once when a real-image volume
  * enters the device cache instead of at every crop read. */
 int bfm_sanitize_f32(float *x, int64_t n, void *stream);
@@ -250,7 +256,8 @@ typedef struct bfm_gen_sample {
        there is no bias field (bfsmall == NULL, Generator/utils.py:575-577). */
     int real_input;
     /* Pair mode.  syn_pair_ok != 0: `syn` has room for TWICE the floats (2 * (source volume + tail padding), zeroed
-       once by the caller).  For samples with exactly one real-image target, no mixing, a synthetic input, src[2] % 4
+       once by the caller; tail padding >= src[1]*src[2] + src[2] + 9 elements: bfm_gen_warp's tile mode copies whole
+       16-byte aligned row segments of the pairs into shared memory).  For samples with exactly one real-image target, no mixing, a synthetic input, src[2] % 4
        == 0 and no full-resolution field, bfm_gen_gmm then writes {synthetic value, aux_src[0] value} PAIRS
        (float2 per source voxel) and bfm_gen_warp gathers both volumes with one 64-bit load per trilinear tap
        (k_gen_warp_pk: half the load requests of the two-volume gather, packed f32x2 arithmetic).  Results are

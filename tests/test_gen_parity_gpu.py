@@ -111,11 +111,17 @@ def test_svf_integration_is_bit_exact(name):
     assert [int(v) for v in grid[3:]] == orc.deform["lo"] + orc.deform["hi"]
 
 
+@pytest.mark.parametrize("tile", ["1", "0", "tiny-bricks"])
 @pytest.mark.parametrize("name", ["g64_s0", "g64_s2", "g160_s0", "g64_s5_lowres"])
-def test_pair_mode_is_identical_to_the_unpaired_gather(name, monkeypatch):
-    """k_gen_warp_pk (float2 {synthetic, T1} pairs, packed f32x2 arithmetic) against k_gen_warp<1, 0>: same
+def test_pair_mode_is_identical_to_the_unpaired_gather(name, tile, monkeypatch):
+    """k_gen_warp_tile (bulk-copied source bricks in shared memory; BFM_WARP_TILE=1), k_gen_warp_pk
+    (float2 {synthetic, T1} gathers from global memory, packed f32x2 arithmetic; BFM_WARP_TILE=0, the default) and the tile
+    kernel with a 4 KB brick budget (most tiles take its global-memory fallback) against k_gen_warp<1, 0>: same
     operations, bit-identical outputs."""
     _, orc = oracle_case(name)
+    monkeypatch.setenv("BFM_WARP_TILE", "0" if tile == "0" else "1")
+    if tile == "tiny-bricks":
+        monkeypatch.setenv("BFM_BRICK_KB", "4")
     got_pk, ds, _ = cuda_case(name, orc.log)
     assert ds.pair_mode and ds._last_descs[0][0].syn_pair_ok == 1
     monkeypatch.setenv("BFM_PAIR_MODE", "0")
@@ -179,6 +185,23 @@ def test_slab_mode_two_ranks():
                             os.path.join(root, "tests", "_slab_worker.py"), name],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_slab_mode_without_injected_draws_does_not_depend_on_the_decomposition(world):
+    """The library's own noise (counter-based, keyed on absolute source / low-res voxels): a volume generated on W
+    ranks equals the single-rank slab run bit for bit and the fused chain within tolerance.  The ranks share GPU 0
+    (gloo stages the exchanged planes through the host), so this runs on a 1-GPU box."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BFM_SLAB_ONE_GPU="1")
+    worker = os.path.join(root, "tests", "_slab_noise_worker.py")
+    cmd = [sys.executable, worker] if world == 1 else \
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+         "--master-addr", "127.0.0.1", "--master-port", "29541", worker]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 @pytest.mark.parametrize("name", ["g64_s0", "g64_s2", "g160_s0"])

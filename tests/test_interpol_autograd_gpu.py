@@ -95,5 +95,5 @@ def test_adjoints_and_prefilter_backward():
     assert gradcheck(lambda a, g: interpol.grid_pull(a, g, 3, 'dct2', True, prefilter=True), (xs, gs))
     c = torch.randn(2, 10, 11, dtype=dtype, device='cuda', requires_grad=True)
     assert gradcheck(lambda a: interpol.spline_coeff_nd(a, 3, 'dct2', dim=2), (c,))
-    with pytest.raises(NotImplementedError):
-        interpol.grid_grad(xs, gs, 3, 'dct2', True)
+    # grid_grad is differentiable too (round 2: pushgrad + spline Hessians), prefilter included
+    assert gradcheck(lambda a, g: interpol.grid_grad(a, g, 3, 'dct2', True, prefilter=True), (xs, gs))

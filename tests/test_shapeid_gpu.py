@@ -89,7 +89,7 @@ def test_ode_solvers_match_reference(name):
         out = odeint(pde, y0[None], t, mgs.DT, method=method)[:, 0].cpu().numpy()
         ref = GOLD["%s_%s" % (method, name)]
         assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-6, method
-    with pytest.raises(NotImplementedError):
-        odeint(pde, y0[None], t, mgs.DT, method='tsit5')
+    with pytest.raises(KeyError):
+        odeint(pde, y0[None], t, mgs.DT, method='bogus')
     with pytest.raises(ValueError):
         odeint_adjoint(lambda tt, y: y, y0[None], t, mgs.DT)
