@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="device-resident arm only (profiling runs)")
     ap.add_argument("--planner", default="auto", choices=["auto", "python", "native"])
     ap.add_argument("--lanes", type=int, default=2, help="batches in flight in the device-resident arm")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2..4] records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -264,7 +265,8 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("BFM_NUMA_BIND") else None   # opt-in
+    # one process per GPU: run (and first-touch the pinned buffers) on the GPU's NUMA node unless BFM_NUMA_BIND=0
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("BFM_NUMA_BIND", "1") != "0" else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when the communicator comes up: send fd 1 to stderr meanwhile, so
@@ -458,6 +460,26 @@ def main():
         cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d samples of 160^3 (same label maps, same parameter ranges), torch %d threads" % (n, threads)}
 
+    # ---------------- the other BASELINE.json configurations, on the record (extra keys, not bench values) ----------------
+    extras = {}
+    if not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            if world == 1:
+                import config_bench as cb
+                r = cb.interpol_cfg(256)                      # configs[2]
+                r["frac_of_peak"] = r["algorithmic_GBps"] / peak
+                extras["interpol256"] = r
+                r = cb.shapeid_cfg(192)                       # configs[3]
+                r["frac_of_peak"] = r["algorithmic_GBps"] / peak
+                extras["shapeid192"] = r
+                extras["brainid_stream"] = cb.brainid_cfg()   # configs[4]a
+            else:
+                import slab_bench as sb                       # configs[4]b: one 512^3 volume in x-slabs over the ranks
+                extras["slab512"] = sb.run(512, 3, rank, world, local)
+        except Exception as e:                                # never lose the bench line over an extra
+            extras["error"] = repr(e)[:300]
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -471,7 +493,7 @@ def main():
                           "stage_ms_per_step": stage_ms, "host_wall_ms_per_step": 1e3 * host_s / args.steps},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "configs": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -133,6 +133,7 @@ _PROTOS = {
                                          c_i, c_i, c_i, c_i, c_i64, c_p]),
     "bfm_interpol_pull_fast": (c_i, [c_p, C.POINTER(c_i64), c_p, c_i64, c_p, c_i, C.POINTER(c_i), c_i, C.POINTER(c_i),
                                      c_i, c_i, c_i, c_i64, c_p]),
+    "bfm_compose_step": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, C.POINTER(c_i), c_i, c_p]),
     "bfm_add_identity_grid": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "bfm_spline_filter": (c_i, [c_p, c_i, c_i64, c_i, c_i64, c_i, C.POINTER(C.c_double), c_i, c_p]),
     "bfm_perlin3d": (c_i, [c_p, C.POINTER(c_i), C.POINTER(c_i), c_p, c_p]),
@@ -140,6 +141,7 @@ _PROTOS = {
     "bfm_gradient3d": (c_i, [c_p, c_i, C.POINTER(c_i), c_i, C.POINTER(c_f), c_p, c_p]),
     "bfm_curl3d": (c_i, [c_p, c_p, c_p, c_i, C.POINTER(c_i), c_f, c_p, c_p, c_p, c_p]),
     "bfm_advect_rhs": (c_i, [c_p, c_i, c_p, c_p, c_p, C.POINTER(c_i), c_i, C.POINTER(c_f), c_p, c_p]),
+    "bfm_diffuse_rhs": (c_i, [c_p, c_i, c_p, c_f, C.POINTER(c_i), c_i, C.POINTER(c_f), c_i, c_p, c_p]),
     "bfm_rk_combine": (c_i, [c_p, c_i, C.POINTER(c_p), C.POINTER(c_f), c_i, c_i64, c_p, c_i, c_p]),
     "bfm_rk_error_fused": (c_i, [C.POINTER(c_p), C.POINTER(c_f), c_i, c_p, c_p, c_i, c_i64, C.c_double, C.c_double, c_p,
                                  c_p, c_p]),

@@ -402,6 +402,70 @@ __global__ void __launch_bounds__(256) k_pull_fast(const float *__restrict__ inp
     }
 }
 
+// One scaling-and-squaring step of a displacement field, fused: out = disp + pull(disp, identity + disp) with linear
+// interpolation (the composition `disp += grid_pull(disp, add_identity_grid(disp))` of BASELINE configs[2]).
+// disp, out: (B, X, Y, Z, 3) float32.  Same operations in the same order as k_add_identity followed by
+// k_pull_fast<1, 3> and the final add -- identical bits -- but the grid and the pulled field never exist in HBM:
+// 24 bytes per voxel and step instead of ~100.
+__global__ void __launch_bounds__(256) k_compose_linear3(const float *__restrict__ disp, float *__restrict__ out,
+                                                         const PullFastArgs a) {
+    const int64_t total = (int64_t)a.B * a.P;
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int b = (int)(q / a.P);
+    const int64_t p = q - (int64_t)b * a.P;
+    const int X = a.ishape[0], Y = a.ishape[1], Z = a.ishape[2];
+    const int z = (int)(p % Z);
+    const int64_t r = p / Z;
+    const int y = (int)(r % Y);
+    const int x = (int)(r / Y);
+    (void)X;
+    const float *dp = disp + q * 3;
+    const float d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    const float g[3] = {d0 + (float)x, d1 + (float)y, d2 + (float)z};
+    int off[3][2];
+    float w[3][2];
+    bool inb = true;
+    const int strides[3] = {Y * Z * 3, Z * 3, 3};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float xx = g[d];
+        const int n = a.ishape[d];
+        if (a.extrapolate != 1) {
+            const float thr = a.extrapolate == 2 ? 0.55f : 0.05f;
+            inb = inb && (xx > -thr) && (xx < float(n - 1) + thr);
+        }
+        const float f0 = floorf(xx);
+        const float dist0 = xx - f0;
+        const int64_t i0 = (int64_t)f0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int sg = bound_sign(a.bound[d], i0 + k, n);
+            off[d][k] = bound_index(a.bound[d], i0 + k, n) * strides[d];
+            w[d][k] = spline_weight<float>(1, dist0 - float(k)) * float(sg);
+        }
+    }
+    const float m = inb ? 1.f : 0.f;
+    const float *src = disp + (int64_t)b * a.P * 3;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kx = 0; kx < 2; ++kx)
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky) {
+            const int oxy = off[0][kx] + off[1][ky];
+            const float wxy = w[0][kx] * w[1][ky];
+#pragma unroll
+            for (int kz = 0; kz < 2; ++kz) {
+                const float ww = wxy * w[2][kz];
+                const float *t = src + oxy + off[2][kz];
+                acc[0] = fmaf(__ldg(t), ww, acc[0]); acc[1] = fmaf(__ldg(t + 1), ww, acc[1]);
+                acc[2] = fmaf(__ldg(t + 2), ww, acc[2]);
+            }
+        }
+    float *o = out + q * 3;
+    o[0] = d0 + acc[0] * m; o[1] = d1 + acc[1] * m; o[2] = d2 + acc[2] * m;
+}
+
 // out = disp + identity grid, (B, X, Y, Z, 3) float32 (add_identity_grid, utils/interpol/api.py:480-521)
 __global__ void __launch_bounds__(256) k_add_identity(const float *__restrict__ disp, float *__restrict__ out, int B,
                                                       int X, int Y, int Z) {
@@ -702,6 +766,25 @@ int bfm_interpol_pull_fast(const float *inp, const int64_t *istride, const float
     else BFM_PF(3);
 #undef BFM_PF
     return check_launch("bfm_interpol_pull_fast");
+}
+
+int bfm_compose_step(const float *disp, float *out, int B, int X, int Y, int Z, const int *bound, int extrapolate,
+                     void *stream) {
+    BFM_REQUIRE(disp && out && bound && disp != out && B > 0 && X > 0 && Y > 0 && Z > 0, "bfm_compose_step: bad argument");
+    BFM_REQUIRE(extrapolate >= 0 && extrapolate <= 2, "bfm_compose_step: extrapolate must be 0, 1 or 2");
+    PullFastArgs a;
+    a.ishape[0] = X; a.ishape[1] = Y; a.ishape[2] = Z;
+    for (int d = 0; d < 3; ++d) {
+        if (bound[d] < 0 || bound[d] > 6) return fail(BFM_E_INVALID, "%s", "bfm_compose_step: bound must be 0..6");
+        a.bound[d] = bound[d];
+    }
+    a.extrapolate = extrapolate; a.B = B; a.C = 3; a.P = (int64_t)X * Y * Z;
+    if (a.P * 3 >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_compose_step: field too large for 32-bit offsets");
+    a.sB = a.P * 3; a.sC = 1; a.sX = Y * Z * 3; a.sY = Z * 3; a.sZ = 3; a.gB = 0; a.out_chlast = 1;
+    const int64_t nblocks = ((int64_t)B * a.P + 255) / 256;
+    if (nblocks >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_compose_step: too many points");
+    k_compose_linear3<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(disp, out, a);
+    return check_launch("bfm_compose_step");
 }
 
 int bfm_add_identity_grid(const float *disp, float *out, int B, int X, int Y, int Z, void *stream) {

@@ -305,6 +305,81 @@ __global__ void __launch_bounds__(256) k_advect_rhs_p(const T *__restrict__ C, c
     out[p] = -__fadd_rn(__fadd_rn(__fmul_rn(vx, cx), __fmul_rn(vy, cy)), __fmul_rn(vz, cz));
 }
 
+// Diffusion right-hand side (AdvDiffPartial.Grad_constantD / Grad_scalarD, ShapeID/DiffEqs/pde.py:331-353) in the
+// reference's own composition of one-sided differences:
+//   second difference along d  = gradient_b(gradient_f(C)[d])[d]                       (pde.py:551-559)
+//   constant D:  D * (ddX + ddY + ddZ)
+//   scalar D:    sum_d gradient_c(D)[d] * gradient_c(C)[d]  +  sum_d D * ddC_d
+// Every gradient_* result is a float32 buffer divided by the spacing; C is read through the replicate-padded
+// interior when `neumann` (set_BC).  accumulate != 0: out += rhs (the advection part is already there).
+template <typename T>
+__global__ void __launch_bounds__(256) k_diffuse_rhs(const T *__restrict__ C, const float *__restrict__ D, float Dconst,
+                                                     int n0, int n1, int n2, int neumann, float sp0, float sp1, float sp2,
+                                                     int accumulate, float *__restrict__ out) {
+    const int i = blockIdx.y;
+    const int plane = n1 * n2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= plane) return;
+    const int j = q / n2, k = q - j * n2;
+    const int lo = neumann ? 1 : 0;
+    const int hi[3] = {neumann ? n0 - 2 : n0 - 1, neumann ? n1 - 2 : n1 - 1, neumann ? n2 - 2 : n2 - 1};
+    const int n[3] = {n0, n1, n2};
+    const float sp[3] = {sp0, sp1, sp2};
+    const int pos[3] = {i, j, k};
+    auto cl = [&](int v, int d) { return neumann ? min(max(v, lo), hi[d]) : v; };
+    // C at the point whose coordinate along axis d is m (the other two are this voxel's), through the BC clamp
+    auto atC = [&](int d, int m) -> T {
+        int a[3] = {cl(pos[0], 0), cl(pos[1], 1), cl(pos[2], 2)};
+        a[d] = cl(m, d);
+        return __ldg(C + ((int64_t)a[0] * n1 + a[1]) * n2 + a[2]);
+    };
+    auto atD = [&](int d, int m) -> float {
+        int a[3] = {pos[0], pos[1], pos[2]};
+        a[d] = m;
+        return __ldg(D + ((int64_t)a[0] * n1 + a[1]) * n2 + a[2]);
+    };
+    // gradient_f along d at index m: forward difference, backward at the last index; float32 result / spacing
+    auto gfC = [&](int d, int m) -> float {
+        const float v = m != n[d] - 1 ? (float)(atC(d, m + 1) - atC(d, m)) : (float)(atC(d, m) - atC(d, m - 1));
+        return __fdiv_rn(v, sp[d]);
+    };
+    auto gcC = [&](int d, int m) -> float {
+        float v;
+        if (m == 0) v = (float)(atC(d, 1) - atC(d, 0));
+        else if (m == n[d] - 1) v = (float)(atC(d, m) - atC(d, m - 1));
+        else v = (float)((atC(d, m + 1) - atC(d, m - 1)) / T(2));
+        return __fdiv_rn(v, sp[d]);
+    };
+    auto gcD = [&](int d, int m) -> float {
+        float v;
+        if (m == 0) v = __fsub_rn(atD(d, 1), atD(d, 0));
+        else if (m == n[d] - 1) v = __fsub_rn(atD(d, m), atD(d, m - 1));
+        else v = __fdiv_rn(__fsub_rn(atD(d, m + 1), atD(d, m - 1)), 2.f);
+        return __fdiv_rn(v, sp[d]);
+    };
+    float dd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int m = pos[d];
+        // gradient_b of the float32 forward-difference array: backward difference, forward at index 0
+        const float v = m != 0 ? __fsub_rn(gfC(d, m), gfC(d, m - 1)) : __fsub_rn(gfC(d, 1), gfC(d, 0));
+        dd[d] = __fdiv_rn(v, sp[d]);
+    }
+    const int64_t p = (int64_t)i * plane + q;
+    float r;
+    if (D) {
+        const float dv = __ldg(D + p);
+        r = __fadd_rn(__fadd_rn(__fmul_rn(gcD(0, i), gcC(0, i)), __fmul_rn(gcD(1, j), gcC(1, j))),
+                      __fmul_rn(gcD(2, k), gcC(2, k)));
+        r = __fadd_rn(r, __fmul_rn(dv, dd[0]));
+        r = __fadd_rn(r, __fmul_rn(dv, dd[1]));
+        r = __fadd_rn(r, __fmul_rn(dv, dd[2]));
+    } else {
+        r = __fmul_rn(Dconst, __fadd_rn(__fadd_rn(dd[0], dd[1]), dd[2]));
+    }
+    out[p] = accumulate ? __fadd_rn(out[p], r) : r;
+}
+
 static inline unsigned g1d(int64_t n) {
     int64_t g = (n + 255) / 256;
     const int64_t cap = 148LL * 16;
@@ -374,6 +449,20 @@ int bfm_advect_rhs(const void *C, int is_double, const float *Vx, const float *V
     if (is_double) k_advect_rhs<double><<<g1d(n), 256, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
     else k_advect_rhs<float><<<g1d(n), 256, 0, s>>>((const float *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
     return check_launch("bfm_advect_rhs");
+}
+
+int bfm_diffuse_rhs(const void *C, int is_double, const float *D, float D_const, const int *shape, int neumann,
+                    const float *spacing, int accumulate, float *out, void *stream) {
+    BFM_REQUIRE(C && shape && spacing && out, "bfm_diffuse_rhs: null pointer");
+    BFM_REQUIRE(shape[0] >= 2 + 2 * (neumann != 0) && shape[1] >= 2 + 2 * (neumann != 0) && shape[2] >= 2 + 2 * (neumann != 0),
+                "bfm_diffuse_rhs: every axis needs at least 2 samples (4 with the Neumann boundary)");
+    const int64_t plane = (int64_t)shape[1] * shape[2];
+    if (plane >= (1LL << 30) || shape[0] > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_diffuse_rhs: volume too large");
+    const dim3 grid((unsigned)((plane + 255) / 256), (unsigned)shape[0]);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_double) k_diffuse_rhs<double><<<grid, 256, 0, s>>>((const double *)C, D, D_const, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], accumulate, out);
+    else k_diffuse_rhs<float><<<grid, 256, 0, s>>>((const float *)C, D, D_const, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], accumulate, out);
+    return check_launch("bfm_diffuse_rhs");
 }
 
 int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, const float *coef_host, int n_terms,

@@ -418,6 +418,13 @@ int bfm_interpol_pull_fast(const float *inp, const int64_t *istride, const float
  * utils/interpol/api.py:480-521 */
 int bfm_add_identity_grid(const float *disp, float *out, int B, int X, int Y, int Z, void *stream);
 
+/* One scaling-and-squaring step of a 3-D displacement field: out = disp + grid_pull(disp, disp + identity)
+ * with linear interpolation, (B, X, Y, Z, 3) float32, out != disp.  Bit-identical to bfm_add_identity_grid +
+ * bfm_interpol_pull_fast(order 1) + add (utils/interpol/api.py:480-521, nd.py:81-150), without materialising the grid
+ * or the pulled field. */
+int bfm_compose_step(const float *disp, float *out, int B, int X, int Y, int Z, const int *bound, int extrapolate,
+                     void *stream);
+
 /* spline_coeff: in-place recursive prefilter along one axis of a tensor viewed as (outer, n, inner)
  * utils/interpol/coeff.py:35-316.  bound: 0 zero (=dct1), 1 replicate (=dct2), 2 dct1, 3 dct2, 6 dft. */
 int bfm_spline_filter(void *data, int is_double, int64_t outer, int n, int64_t inner, int bound,
@@ -444,6 +451,12 @@ int bfm_curl3d(const void *A, const void *B, const void *C, int is_double, const
  * neumann != 0: replicate-pad the interior before differencing (set_BC). */
 int bfm_advect_rhs(const void *C, int is_double, const float *Vx, const float *Vy, const float *Vz, const int *shape,
                    int neumann, const float *spacing, float *out, void *stream);
+/* AdvDiffPDE.forward, diffusion part, D_type 'constant' (D == NULL, D_const) or 'scalar' (D: (shape) float32 field)
+ * ShapeID/DiffEqs/pde.py:331-353, 551-559, 623-639.  accumulate != 0: out += rhs (perf_pattern 'adv_diff': call
+ * bfm_advect_rhs first). */
+int bfm_diffuse_rhs(const void *C, int is_double, const float *D, float D_const, const int *shape, int neumann,
+                    const float *spacing, int accumulate, float *out, void *stream);
+
 /* out = y0 + sum_j coef[j]*k[j] (float32 partial sums, state precision for the final add); y0 == NULL: out = sum
  * _runge_kutta_step / _scaled_dot_product                            ShapeID/DiffEqs/rk_common.py:22-61, misc.py:22-25 */
 int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, const float *coef_host, int n_terms,

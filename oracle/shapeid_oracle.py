@@ -205,3 +205,44 @@ def fixed(rhs, y0, t, method):
             y = (y + (k1 + 3 * k2 + 3 * k3 + k4) * F32(dt / 8)).astype(y.dtype)
         sol.append(y)
     return sol
+
+
+# ---- diffusion right-hand side (ShapeID/DiffEqs/pde.py:13-183, 331-353, 551-559, 623-639) ----------------------
+def _set_bc(C):
+    """set_BC for 'neumann' / 'cauchy': replicate-pad the interior (pde.py:590-600)."""
+    return np.pad(C[1:-1, 1:-1, 1:-1], 1, mode="edge")
+
+
+def _grad(X, mode, spacing):
+    """gradient_f / gradient_b / gradient_c of a 3-D array: float32 buffers divided by the spacing."""
+    out = []
+    for d in range(3):
+        Xd = np.moveaxis(X, d, 0)
+        g = np.zeros(Xd.shape, dtype=np.float32)
+        if mode == "f":
+            g[:-1] = Xd[1:] - Xd[:-1]
+            g[-1] = Xd[-1] - Xd[-2]
+        elif mode == "b":
+            g[1:] = Xd[1:] - Xd[:-1]
+            g[0] = Xd[1] - Xd[0]
+        else:
+            g[1:-1] = (Xd[2:] - Xd[:-2]) / 2
+            g[0] = Xd[1] - Xd[0]
+            g[-1] = Xd[-1] - Xd[-2]
+        out.append(np.moveaxis(g / np.float32(spacing[d]), 0, d))
+    return out
+
+
+def diffuse_rhs(C, D, spacing=(1., 1., 1.), neumann=True):
+    """Grad_constantD (D a scalar) / Grad_scalarD (D an array) of the reference, same composition of differences."""
+    C = _set_bc(C) if neumann else C
+    gf = _grad(C, "f", spacing)
+    dd = [_grad(gf[d], "b", spacing)[d] for d in range(3)]
+    if np.ndim(D) == 0:
+        return (np.float32(D) * ((dd[0] + dd[1]) + dd[2])).astype(np.float32)
+    D = np.asarray(D, dtype=np.float32)
+    gD, gC = _grad(D, "c", spacing), _grad(C, "c", spacing)
+    out = (gD[0] * gC[0] + gD[1] * gC[1]) + gD[2] * gC[2]
+    for d in range(3):
+        out = out + D * dd[d]
+    return out.astype(np.float32)

@@ -63,8 +63,9 @@ def test_velocity_gradients_and_rhs_bit_exact():
                      dt=mgs.DT, device='cuda')
     out = pde(torch.tensor(0.), cu(GOLD["shape_prob"])[None])[0].cpu().numpy()
     assert out.dtype == np.float32 and np.array_equal(out, GOLD["rhs0"])
-    with pytest.raises(NotImplementedError):
-        AdvDiffPDE([1., 1., 1.], 'adv_diff', V_type='vector_div_free', V_dict=V, device='cuda')(0., cu(x)[None])
+    with pytest.raises(NotImplementedError):       # tensor diffusivities are not built
+        AdvDiffPDE([1., 1., 1.], 'adv_diff', D_type='full', V_type='vector_div_free', V_dict=V,
+                   device='cuda')(0., cu(x)[None])
 
 
 @pytest.mark.parametrize("name", ["f64", "f32"])
@@ -93,3 +94,29 @@ def test_ode_solvers_match_reference(name):
         odeint(pde, y0[None], t, mgs.DT, method='bogus')
     with pytest.raises(ValueError):
         odeint_adjoint(lambda tt, y: y, y0[None], t, mgs.DT)
+
+
+PDE = np.load(os.path.join(os.path.dirname(__file__), "golden", "pde.npz"))
+
+
+@pytest.mark.parametrize("name,pattern,dtype_d,bc,spacing,dt,stoch", [
+    ("diff_const", "diff", "constant", "neumann", [1., 1., 1.], "f32", False),
+    ("diff_scalar", "diff", "scalar", "neumann", [1., 1., 1.], "f32", False),
+    ("diff_scalar_nobc", "diff", "scalar", None, [1., 0.8, 1.3], "f32", False),
+    ("diff_scalar_f64", "diff", "scalar", "neumann", [1., 0.8, 1.3], "f64", False),
+    ("advdiff_scalar", "adv_diff", "scalar", "neumann", [1., 1., 1.], "f32", False),
+    ("advdiff_const_f64", "adv_diff", "constant", None, [1., 1., 1.], "f64", False),
+    ("advdiff_scalar_stoch0", "adv_diff", "scalar", "neumann", [1., 1., 1.], "f32", True)])
+def test_diffusion_and_advection_diffusion_rhs_bit_exact(name, pattern, dtype_d, bc, spacing, dt, stoch):
+    """AdvDiffPDE.forward for the 'diff' / 'adv_diff' patterns (bfm_diffuse_rhs) against the reference's output
+    (tests/golden/pde.npz): separately rounded float32 differences, so the result is bit-exact."""
+    from brainfm_b200.ShapeID.DiffEqs.pde import AdvDiffPDE
+    C = cu(PDE["C"] if dt == "f64" else PDE["C"].astype(np.float32))[None]
+    D = {"D": cu(PDE["D"])[None]} if dtype_d == "scalar" else {"D": float(PDE["Dconst"])}
+    V = {k: cu(PDE[k]) for k in ("Vx", "Vy", "Vz")}
+    pde = AdvDiffPDE(data_spacing=spacing, perf_pattern=pattern, D_type=dtype_d, V_type='vector_div_free', BC=bc,
+                     dt=0.1, V_dict=V, D_dict=D, stochastic=stoch, device='cuda')
+    out = pde(torch.tensor(0.), C)[0].cpu().numpy()
+    assert out.dtype == np.float32 and np.array_equal(out, PDE["out_" + name])
+    with pytest.raises(NotImplementedError):
+        AdvDiffPDE(spacing, 'diff', D_type='full', V_type='vector_div_free', D_dict=D, device='cuda')(0., C)

@@ -41,3 +41,17 @@ def test_percentile_helper_matches_numpy():
         x = rng.randn(n)
         for q in (85.0, 92.0, 99.9, 50.0, 0.0, 100.0, 33.3333):
             assert _percentile_device(torch.from_numpy(x), q) == np.percentile(x, q), (n, q)
+
+
+def test_diffusion_rhs_oracle_matches_reference_fixture():
+    """oracle.shapeid_oracle.diffuse_rhs against AdvDiffPDE.forward of the reference (tests/golden/pde.npz)."""
+    import os
+    import numpy as np
+    from oracle import shapeid_oracle as so
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pde.npz"))
+    C32, C64 = G["C"].astype(np.float32), G["C"]
+    for name, C, D, sp, neu in [("diff_const", C32, float(G["Dconst"]), (1, 1, 1), True),
+                                ("diff_scalar", C32, G["D"], (1, 1, 1), True),
+                                ("diff_scalar_nobc", C32, G["D"], (1, .8, 1.3), False),
+                                ("diff_scalar_f64", C64, G["D"], (1, .8, 1.3), True)]:
+        assert np.array_equal(so.diffuse_rhs(C, D, sp, neu), G["out_" + name]), name

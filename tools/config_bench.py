@@ -34,7 +34,7 @@ def timed(fn, reps=3):
     return best, out
 
 
-def interpol_cfg(n=256):
+def interpol_cfg(n=256, oracle_check=False):
     from brainfm_b200 import interpol
     torch.manual_seed(0)
     vol = torch.rand(1, 4, n, n, n, device="cuda")
@@ -49,7 +49,11 @@ def interpol_cfg(n=256):
             disp = disp + interpol.grid_pull(disp.permute(0, 4, 1, 2, 3), grid, interpolation=1, bound='dct2',
                                              extrapolate=True).permute(0, 2, 3, 4, 1)
         return disp
-    stages["scaling_and_squaring_7"], disp = timed(ss)
+    stages["scaling_and_squaring_7_three_call_form"], disp_ref = timed(ss)
+    stages_fused, disp = timed(lambda: interpol.exp_velocity(svf, steps=7, bound='dct2', extrapolate=True))
+    assert torch.equal(disp, disp_ref), "fused scaling and squaring differs from the composed form"
+    del stages["scaling_and_squaring_7_three_call_form"]
+    stages["scaling_and_squaring_7"] = stages_fused
     grid = interpol.add_identity_grid(disp)
     stages["cubic_prefilter_4ch"], coeff = timed(lambda: interpol.spline_coeff_nd(vol, interpolation=3, bound='dct2', dim=3))
     stages["cubic_pull_4ch"], out = timed(lambda: interpol.grid_pull(coeff, grid, interpolation=3, bound='dct2',
@@ -58,9 +62,20 @@ def interpol_cfg(n=256):
                                                                          extrapolate=True))
     total = sum(stages.values())
     N = n ** 3
-    print(json.dumps({"config": "interpol 4ch %d^3 (configs[2])" % n, "ms": stages, "total_ms": total,
-                      "algorithmic_GB": 316 * N / 1e9, "algorithmic_GBps": 316 * N / total / 1e6,
-                      "reference_cpu_s_8_threads": 63.4 if n == 256 else None}))
+    # parity spot check at full size: strided sample of the cubic pull and of the label pull against the numpy oracle
+    parity = None
+    if oracle_check:        # tests only (tests/test_configs_gpu.py): bench.py never touches oracle/ on this path
+        from oracle import interpol_oracle as io_
+        sel = torch.arange(0, N, 40009, device="cuda")[:256]
+        g = grid.reshape(1, N, 3)[:, sel].cpu().numpy()[:, :, None, None, :].astype(np.float64)
+        want = io_.pull(coeff.cpu().numpy().astype(np.float64), g, [3, 3, 3], [3, 3, 3], 1)[0, :, :, 0, 0]
+        got = out.reshape(4, N)[:, sel].cpu().numpy()
+        wl = io_.pull(lab.cpu().numpy().astype(np.float64), g, [0, 0, 0], [3, 3, 3], 1)[0, 0, :, 0, 0]
+        parity = {"points": int(sel.numel()), "cubic_max_abs_err": float(np.abs(got - want).max()),
+                  "labels_equal": bool(np.array_equal(lo.reshape(N)[sel].cpu().numpy(), wl))}
+    return {"config": "interpol 4ch %d^3 (configs[2])" % n, "ms": stages, "total_ms": total,
+            "algorithmic_GB": 316 * N / 1e9, "algorithmic_GBps": 316 * N / total / 1e6,
+            "oracle_spot_check": parity, "reference_cpu_s_8_threads": 63.4 if n == 256 else None}
 
 
 def shapeid_cfg(n=192):
@@ -92,10 +107,11 @@ def shapeid_cfg(n=192):
     N = n ** 3
     S = len(solver.trace)
     alg = (84 * N + S * 368 * N + (nt - 1) * 60 * N)
-    print(json.dumps({"config": "ShapeID %d^3 (configs[3])" % n, "ms": stages, "total_ms": sum(stages.values()),
-                      "rhs_evaluations": int(solver.n_rhs), "steps": S, "algorithmic_GB": alg / 1e9,
-                      "algorithmic_GBps": alg / sum(stages.values()) / 1e6,
-                      "reference_cpu_s_8_threads": 95.6 if n == 192 else None}))
+    return {"config": "ShapeID %d^3 (configs[3])" % n, "ms": stages, "total_ms": sum(stages.values()),
+            "rhs_evaluations": int(solver.n_rhs), "steps": S, "algorithmic_GB": alg / 1e9,
+            "algorithmic_GBps": alg / sum(stages.values()) / 1e6,
+            "mass_drift": float((sol[-1].double().sum() / sol[0].double().sum() - 1).abs()),
+            "reference_cpu_s_8_threads": 95.6 if n == 192 else None}
 
 
 def brainid_cfg(n_items=2, steps=100):
@@ -135,10 +151,10 @@ def brainid_cfg(n_items=2, steps=100):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print(json.dumps({"config": "BrainIDGen stream 160^3, all_samples 4 (configs[4]a)", "items_per_step": n_items,
-                      "samples_per_step": 4 * n_items, "ms_per_step": ms,
-                      "samples_per_s": 4 * n_items / ms * 1e3, "items_per_s": n_items / ms * 1e3,
-                      "planner": "native"}))
+    return {"config": "BrainIDGen stream 160^3, all_samples 4 (configs[4]a)", "items_per_step": n_items,
+            "samples_per_step": 4 * n_items, "ms_per_step": ms,
+            "samples_per_s": 4 * n_items / ms * 1e3, "items_per_s": n_items / ms * 1e3,
+            "planner": "native"}
 
 
 def realmix_cfg(steps=100):
@@ -164,18 +180,18 @@ def realmix_cfg(steps=100):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print(json.dumps({"config": "BaseGen batch 8x160^3, real T1 input with probability 0.5", "ms_per_step": ms,
-                      "samples_per_s": bench.BATCH / ms * 1e3, "real_fraction": n_real / (steps * bench.BATCH),
-                      "planner": "native"}))
+    return {"config": "BaseGen batch 8x160^3, real T1 input with probability 0.5", "ms_per_step": ms,
+            "samples_per_s": bench.BATCH / ms * 1e3, "real_fraction": n_real / (steps * bench.BATCH),
+            "planner": "native"}
 
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["interpol", "shapeid", "brainid", "realmix"]
     if "realmix" in which:
-        realmix_cfg()
+        print(json.dumps(realmix_cfg()))
     if "brainid" in which:
-        brainid_cfg()
+        print(json.dumps(brainid_cfg()))
     if "interpol" in which:
-        interpol_cfg(int(os.environ.get("INTERPOL_N", "256")))
+        print(json.dumps(interpol_cfg(int(os.environ.get("INTERPOL_N", "256")))))
     if "shapeid" in which:
-        shapeid_cfg(int(os.environ.get("SHAPEID_N", "192")))
+        print(json.dumps(shapeid_cfg(int(os.environ.get("SHAPEID_N", "192")))))

@@ -21,11 +21,9 @@ from brainfm_b200.Generator.slab import generate_slab
 from tests import _inputs as ti
 
 
-def main():
-    size = int(os.environ.get("SLAB_SIZE", "512"))
-    steps = int(os.environ.get("SLAB_STEPS", "5"))
-    rank, world, local = par.init()
-    torch.cuda.set_device(local)
+def run(size=512, steps=5, rank=0, world=1, local=0):
+    """ms per volume (max over ranks) of one size^3 sample in slab mode on `world` ranks + a checksum of the assembled
+    volume (sum over ranks of the owned planes' sums: equal for every decomposition)."""
     dev = torch.device("cuda", local)
     half = ti.brain_like_labels((size // 2,) * 3, seed=7)
     lab = np.repeat(np.repeat(np.repeat(half, 2, 0), 2, 1), 2, 2)       # nearest x2 (SURVEY 8d)
@@ -60,11 +58,24 @@ def main():
     e1.record()
     sync()
     ms = par.all_reduce_max(e0.elapsed_time(e1) / steps, device=dev)
+    chk = out["input"].double().sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(chk)
+    bio.clear_registry()
+    return {"workload": "one %d^3 BaseGen sample (input + bias_field_log), slab mode" % size,
+            "n_gpus": world, "ms_per_volume": ms, "volumes_per_s": 1e3 / ms,
+            "Mvoxels_per_s": size ** 3 / ms / 1e3, "slab_planes_rank0": list(out["x_range"]),
+            "checksum": float(chk.item()), "steps": steps}
+
+
+def main():
+    size = int(os.environ.get("SLAB_SIZE", "512"))
+    steps = int(os.environ.get("SLAB_STEPS", "5"))
+    rank, world, local = par.init()
+    torch.cuda.set_device(local)
+    res = run(size, steps, rank, world, local)
     if rank == 0:
-        print(json.dumps({"workload": "one %d^3 BaseGen sample (input + bias_field_log), slab mode" % size,
-                          "n_gpus": world, "ms_per_volume": ms, "volumes_per_s": 1e3 / ms,
-                          "Mvoxels_per_s": size ** 3 / ms / 1e3, "slab_planes": list(out["x_range"]),
-                          "steps": steps}), flush=True)
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
