@@ -862,11 +862,7 @@ class BaseGen(Dataset):
                 self._native = NativePlanner(self)
             else:
                 self._native.refresh()
-            for idx in indices:
-                _, input_prob, t1_path, _ = self.idx_to_path(int(idx))
-                if not self._native.item_ok(input_prob, self.get_info(t1_path)):
-                    ok = False
-                    break
+            ok = self._native.batch_ok(indices)
         if not ok and self.planner == 'native':
             raise NotImplementedError("this configuration needs the Python planner (planner='python' or 'auto')")
         return self._native if ok else None

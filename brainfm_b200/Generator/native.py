@@ -38,6 +38,8 @@ class NativePlanner:
         self.cfg = self._build_cfg()
         self._fp = self.fingerprint()
         self.last = None
+        self._prep = {}
+        self._other_targets = None
 
     _KEYS = ('photo_prob', 'pathology_prob', 'random_shape_prob', 'flip_prob', 'max_rotation', 'max_shear',
              'max_scaling', 'nonlin_scale_min', 'nonlin_scale_max', 'nonlin_std_max', 'ct_prob', 'low_res_only',
@@ -145,6 +147,67 @@ class NativePlanner:
         self._keep += [dirs, ident]
         return cfg
 
+    # ---- per-batch preparation, cached ------------------------------------------------------------------
+    def _prepare(self, indices, use_cache=True):
+        """PlanItem array + per-item metadata of a batch of dataset indices.  Everything in here depends only on the
+        indices and on WHICH tensors the device cache holds, so it is built once per index tuple and reused until the
+        cache's membership changes (`DeviceVolumeCache.version`: a new volume, an eviction, a clear); uploads and
+        refreshes overwrite cached volumes in place and keep it valid.  On a hit the volumes are only touched (LRU
+        order + eviction epoch).  Saves ~0.15 ms of ctypes stores and dictionary look-ups per batch of 8."""
+        ds = self.ds
+        key = tuple(int(i) for i in indices)
+        ent = self._prep.get(key)
+        cache = ds.cache
+        if use_cache and ent is not None and ent['version'] == cache.version:
+            cache.touch(ent['keys'])
+            return ent
+        B = len(key)
+        items = (_lib.PlanItem * B)()
+        metas, keys = [], []
+        n_aux_total, src_pad = 0, 0
+        for n, idx in enumerate(key):
+            dataset_name, input_prob, t1_path, age = ds.idx_to_path(idx)
+            mods = ds.get_info(t1_path)
+            lab = cache.get(mods['Gen'], 'gen')
+            keys.append((mods['Gen'], 'gen'))
+            it = items[n]
+            it.labels = lab.data_ptr()
+            it.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
+            src = [int(v) for v in lab.shape[:3]]
+            it.src[:] = src
+            for q, m in enumerate(('T1', 'T2', 'FLAIR', 'CT')):
+                it.input_prob[q] = float(input_prob.get(m, 0))
+            for q, m in enumerate(('T1', 'T2', 'FLAIR')):
+                if m in mods and input_prob.get(m, 0) > 0:
+                    it.real_vol[q] = cache.get(mods[m], 'f32').data_ptr()
+                    keys.append((mods[m], 'f32'))
+            if 'CT' in mods and input_prob.get('CT', 0) > 0:
+                it.ct_vol = cache.get(mods['CT'], 'f32').data_ptr()
+                keys.append((mods['CT'], 'f32'))
+            aux = ds._fused_aux_volumes(mods, src)
+            it.n_aux = len(aux)
+            for c, (k_, vol) in enumerate(aux):
+                it.aux_src[c] = vol.data_ptr()
+                keys.append((mods[k_], 'f32'))
+            n_aux_total += len(aux)
+            src_pad = max(src_pad, src[0] * src[1] * src[2] + src[1] * src[2] + src[2] + 9)
+            metas.append((idx, dataset_name, t1_path, age, dict(mods), aux, src))
+        ent = dict(items=items, metas=metas, n_aux_total=n_aux_total, src_pad=src_pad, keys=keys,
+                   version=cache.version, ok=None)
+        if use_cache:
+            if len(self._prep) > 256:
+                self._prep.clear()
+            self._prep[key] = ent
+        return ent
+
+    def batch_ok(self, indices):
+        """item_ok for every index of the batch (cached with the batch's preparation)."""
+        ds = self.ds
+        ent = self._prepare(indices)
+        if ent['ok'] is None:
+            ent['ok'] = all(self.item_ok(ds.idx_to_path(m[0])[1], m[4]) for m in ent['metas'])
+        return ent['ok']
+
     # ---- one batch ---------------------------------------------------------------------------------------
     def run(self, indices, timers=None):
         ds, L = self.ds, _lib.lib()
@@ -159,35 +222,9 @@ class NativePlanner:
         ds.hemis_mask = None
         want_bflog = ds._want_bflog('synth')
         want_res = 'super_resolution' in ds.tasks
-        # ---- items: volumes from the device cache
-        items = (_lib.PlanItem * B)()
-        metas = []
-        n_aux_total, src_pad = 0, 0
-        for n, idx in enumerate(indices):
-            if torch.is_tensor(idx):
-                idx = idx.tolist()
-            dataset_name, input_prob, t1_path, age = ds.idx_to_path(idx)
-            mods = ds.get_info(t1_path)
-            lab = ds.cache.get(mods['Gen'], 'gen')
-            it = items[n]
-            it.labels = lab.data_ptr()
-            it.label_is_u8 = 1 if lab.dtype == torch.uint8 else 0
-            src = [int(v) for v in lab.shape[:3]]
-            it.src[:] = src
-            for q, m in enumerate(('T1', 'T2', 'FLAIR', 'CT')):
-                it.input_prob[q] = float(input_prob.get(m, 0))
-            for q, m in enumerate(('T1', 'T2', 'FLAIR')):
-                if m in mods and input_prob.get(m, 0) > 0:
-                    it.real_vol[q] = ds.cache.get(mods[m], 'f32').data_ptr()
-            if 'CT' in mods and input_prob.get('CT', 0) > 0:
-                it.ct_vol = ds.cache.get(mods['CT'], 'f32').data_ptr()
-            aux = ds._fused_aux_volumes(mods, src)
-            it.n_aux = len(aux)
-            for c, (key, vol) in enumerate(aux):
-                it.aux_src[c] = vol.data_ptr()
-            n_aux_total += len(aux)
-            src_pad = max(src_pad, src[0] * src[1] * src[2] + src[1] * src[2] + src[2] + 9)
-            metas.append((idx, dataset_name, t1_path, age, dict(mods), aux, src))
+        # ---- items: volumes from the device cache (prepared once per index tuple, see _prepare)
+        prep = self._prepare(indices, use_cache=not replay)     # replayed draws park eps pointers in the items
+        items, metas, n_aux_total, src_pad = prep['items'], prep['metas'], prep['n_aux_total'], prep['src_pad']
         src_pad = (src_pad + 3) // 4 * 4
         # ---- outputs (fresh) and persistent scratch
         out = torch.empty((total, 1, *size), dtype=torch.float32, device=dev)
@@ -269,18 +306,25 @@ class NativePlanner:
         arena.committed = arena.used
         # ---- per-item context (targets that do not ride on the fused gather need a DeformPlan)
         h, d_dev = C.addressof(descs), descs_dev.value
+        other_targets = self._other_targets
+        if other_targets is None:
+            other_targets = self._other_targets = any(t in K.processing_funcs and t not in ('T1', 'T2', 'FLAIR')
+                                                      for t in ds.tasks)
+        need_plans = other_targets or any(len(m[5]) < sum(1 for k in ('T1', 'T2', 'FLAIR') if k in m[4]) for m in metas)
+
+        def setups_of(inf):
+            return {'resolution': np.array(inf.resolution[:]), 'thickness': np.array(inf.thickness[:]),
+                    'photo_mode': bool(inf.photo_mode), 'pathol_mode': False, 'pathol_random_shape': False,
+                    'spac': inf.spac if inf.photo_mode else None, 'flip': bool(inf.flip), 'hemis': 'both'}
+
         ctxs = []
-        other_targets = any(t in K.processing_funcs and t not in ('T1', 'T2', 'FLAIR') for t in ds.tasks)
         for n, (idx, dataset_name, t1_path, age, mods, aux, src) in enumerate(metas):
             inf = info[n]
-            setups = {'resolution': np.array(inf.resolution[:]), 'thickness': np.array(inf.thickness[:]),
-                      'photo_mode': bool(inf.photo_mode), 'pathol_mode': False, 'pathol_random_shape': False,
-                      'spac': inf.spac if inf.photo_mode else None, 'flip': bool(inf.flip), 'hemis': 'both'}
+            # the set-up dictionary is only read by the op-wise target readers (and kept as ds.last_setups)
+            setups = setups_of(inf) if (need_plans or n == B - 1) else None
             ctxs.append(dict(idx=idx, dataset_name=dataset_name, case_name=_case_name(t1_path),
-                             input_mode=('synth', 'T1', 'T2', 'FLAIR', 'CT')[inf.input_mode],
+                             input_mode=_INPUT_MODES[inf.input_mode],
                              age=age, setups=setups, modalities=mods, aux=aux, src=src, n=n))
-        need_plans = other_targets or any(len(c['aux']) < sum(1 for k in ('T1', 'T2', 'FLAIR') if k in c['modalities'])
-                                          for c in ctxs)
 
         def stage(name, fn):
             if timers is not None:
@@ -400,6 +444,9 @@ class NativePlanner:
             bb = arena.view(d.bbox - base, 8, torch.int32, slot=last['arena_slot'])[:6].tolist()
             rows.append((bb, list(last['info'][q // ns].new_size[q % ns])))
         return rows
+
+
+_INPUT_MODES = ('synth', 'T1', 'T2', 'FLAIR', 'CT')
 
 
 def _case_name(t1_path):

@@ -76,6 +76,7 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     descs[0].x_begin, descs[0].x_count = c0, c1 - c0
     d_dev = arena.put_struct_array(descs)
     arena.commit()
+    ds._last_descs = (descs, d_dev, 1)
     h, st = C.addressof(descs), _stream()
     _lib.check(L.bfm_gen_bbox(h, d_dev, 1, st))
     job['plan'].have_bbox = True
@@ -140,7 +141,12 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     # ---- I / max(I) with the global maximum (datasets.py:342-343), then the flip
     mx = out.max().reshape(1) if out.numel() else torch.zeros(1, device=low.device)
     if world > 1:
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        if dist.get_backend(group) == "gloo":              # ranks sharing one GPU (tests): reduce on the host
+            h_mx = mx.cpu()
+            dist.all_reduce(h_mx, op=dist.ReduceOp.MAX, group=group)
+            mx = h_mx.to(mx.device)
+        else:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     # one pass: I / max and the flip of the slab's planes (bfm_shift_scale_flip: true division like the reference)
     if out.numel():
         fin = torch.empty_like(out)

@@ -6,7 +6,7 @@ from .. import _lib
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def need_cuda(t, what):

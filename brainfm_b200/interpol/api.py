@@ -21,7 +21,7 @@ _ORDERS = {'nearest': 0, 'linear': 1, 'quadratic': 2, 'cubic': 3, 'fourth': 4, '
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _as_list(x, n):

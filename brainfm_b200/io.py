@@ -136,6 +136,7 @@ class DeviceVolumeCache:
         self._bytes = 0
         self._epoch = 0
         self.evictions = 0
+        self.version = 0                 # bumped whenever the SET of cached tensors changes (insert / evict / clear)
 
     @staticmethod
     def _pad(shape):
@@ -174,6 +175,7 @@ class DeviceVolumeCache:
             self._bytes -= self._d.pop(victim)[1]
             self._drop_derived_of(victim[0])
             self.evictions += 1
+            self.version += 1
 
     def get(self, path, kind="f32"):
         key = (path, kind)
@@ -210,12 +212,22 @@ class DeviceVolumeCache:
             raise ValueError(kind)
         self._d[key] = [t, nbytes, self._epoch]
         self._bytes += nbytes
+        self.version += 1
         return t
+
+    def touch(self, keys):
+        """Mark cached volumes as used by the current batch (what `get` does on a hit) without returning them."""
+        d, epoch = self._d, self._epoch
+        for key in keys:
+            ent = d[key]
+            ent[2] = epoch
+            d.move_to_end(key)
 
     def clear(self):
         self._d.clear()
         self._derived.clear()
         self._bytes = 0
+        self.version += 1
 
     def derived(self, name, deps, build):
         """A tensor computed from cached volumes (`deps`: the paths it depends on), built once by `build()`."""
@@ -241,7 +253,7 @@ class DeviceVolumeCache:
             code = _INGEST_DTYPES.get(host_tensor.dtype)
             if code is not None and host_tensor.is_contiguous() and host_tensor.numel() == t.numel():
                 _lib.check(_lib.lib().bfm_ingest_volume(t.data_ptr(), host_tensor.data_ptr(), code, t.numel(), 1.0, 0.0,
-                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                                        C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))))
                 return t
         t.copy_(host_tensor, non_blocking=True)
         return t
@@ -254,7 +266,7 @@ class DeviceVolumeCache:
             return
         t = self.get(path, kind)
         _lib.check(_lib.lib().bfm_sanitize_f32(t.data_ptr(), t.numel(),
-                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                               C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))))
 
     def refresh(self, path, kind, host_tensor):
         """upload() + sanitize() on the current stream."""

@@ -95,6 +95,10 @@ def exchange_planes(local, owned, needed, rank=None, world=None, group=None):
     nb, ne = needed[rank]
     if local.shape[0] != oe - ob:
         raise ValueError("local tensor has %d planes, rank owns %d" % (local.shape[0], oe - ob))
+    if world > 1 and local.is_cuda and dist.get_backend(group) == "gloo":
+        # gloo moves host memory only (several ranks sharing one GPU in the tests): stage the planes through the host
+        host = exchange_planes(local.cpu(), owned, needed, rank, world, group)
+        return host.to(local.device)
     out = torch.empty((max(ne - nb, 0), *local.shape[1:]), dtype=local.dtype, device=local.device)
     # own planes
     a, b = max(ob, nb), min(oe, ne)

@@ -186,7 +186,8 @@ class Arena:
         if self.used > self.committed:
             a = self.committed // _ALIGN * _ALIGN
             b = min((self.used + _ALIGN - 1) // _ALIGN * _ALIGN, self.capacity)
-            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            st = C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index if self.device.index is not None
+                                                               else torch._C._cuda_getDevice()))
             _lib.check(_lib.lib().bfm_upload_pinned(s["dev"].data_ptr() + a, s["host"].data_ptr() + a, b - a, st))
             self.committed = self.used
 
