@@ -693,15 +693,24 @@ class BaseGen(Dataset):
     def _generate_sample_opwise(self, setups, deform_dict, res, target, has_pathol=False):
         """Op-by-op path through the registries (custom or reordered augmentation steps, pathology encoding)."""
         rng = self.rng
+        L, st = _lib.lib(), _stream()
         mus, sigmas = self.get_contrast(setups['photo_mode'])
         xx2, yy2, zz2, x1, y1, z1, x2, y2, z2 = deform_dict['grid']
-        G = self._labels()[x1:x2, y1:y2, z1:z2].float()
-        G[G == 77] = 2
-        Gr = torch.round(G).long()
+        # GMM image over the bbox crop (datasets.py:364-372): one kernel reading the cached label volume in place
+        lab = self._labels()
+        src = (C.c_int * 3)(*[int(v) for v in lab.shape[:3]])
+        box = (C.c_int * 6)(int(x1), int(y1), int(z1), int(x2), int(y2), int(z2))
+        crop = (int(x2 - x1), int(y2 - y1), int(z2 - z1))
+        lab_u8 = 1 if lab.dtype == torch.uint8 else 0
+        if not lab_u8 and lab.dtype != torch.float32:
+            lab = lab.float()
         eps = rng.field_randn("gmm.eps")
-        eps = torch.randn(Gr.shape, dtype=torch.float, device=self.device) if eps is None else eps.to(self.device)
-        SYN = mus.to(self.device)[Gr] + sigmas.to(self.device)[Gr] * eps
-        SYN[SYN < 0] = 0
+        eps = None if eps is None else eps.to(self.device, torch.float32).contiguous()
+        tab = torch.stack([mus.float(), sigmas.float()]).to(self.device)          # (2, 256), one upload
+        SYN = torch.empty(crop, dtype=torch.float32, device=self.device)
+        _lib.check(L.bfm_gmm_crop(lab.data_ptr(), lab_u8, src, box, tab[0].data_ptr(), tab[1].data_ptr(),
+                                  0 if eps is None else eps.data_ptr(), int(rng.seed64()) if eps is None else 0,
+                                  SYN.data_ptr(), st))
         SYN = fast_3D_interp_torch(SYN.contiguous(), xx2, yy2, zz2)
         if rng.rand("mix.u") < self.gen_args.mix_synth_prob:
             v = rng.torch_rand("mix.v", 4)
@@ -716,15 +725,27 @@ class BaseGen(Dataset):
         if has_pathol:
             # datasets.py:390-406, quirks included: the masks have the crop's shape, so this branch (like the
             # reference's) only works when the crop covers the whole output shape; SYN_cerebral is warped twice
-            SYN_cerebral = SYN.clone()
-            SYN_cerebral[Gr == 0] = 0
-            SYN_cerebral = fast_3D_interp_torch(SYN_cerebral.contiguous(), xx2, yy2, zz2)[None]
-            wm_mask = (Gr == 2) | (Gr == 41)
-            wm_mean = (SYN * wm_mask).sum() / wm_mask.sum()
-            gm_mask = (Gr != 0) & (Gr != 2) & (Gr != 41)
-            gm_mean = (SYN * gm_mask).sum() / gm_mask.sum()
-            target['pathology'][SYN_cerebral == 0] = 0
-            target['pathology_prob'][SYN_cerebral == 0] = 0
+            if tuple(SYN.shape) != crop:
+                raise RuntimeError("pathology encoding needs the bbox crop to cover the output shape "
+                                   "(the reference's masks have the crop's shape, datasets.py:391-400)")
+            SYN = SYN.contiguous()
+            SYN_cerebral = torch.empty_like(SYN)
+            sums = torch.empty(4, dtype=torch.float64, device=self.device)
+            _lib.check(L.bfm_pathol_cerebral(SYN.data_ptr(), lab.data_ptr(), lab_u8, src, box, SYN_cerebral.data_ptr(),
+                                             sums.data_ptr(), st))
+            SYN_cerebral = fast_3D_interp_torch(SYN_cerebral, xx2, yy2, zz2).contiguous()
+            for key in ('pathology', 'pathology_prob'):
+                t = target[key]
+                if not t.is_contiguous():
+                    t = target[key] = t.contiguous()
+                if t.numel() != SYN_cerebral.numel() or t.dtype not in (torch.float32, torch.float64):
+                    t[SYN_cerebral[None] == 0] = 0                      # unusual shapes / dtypes: tensor expression
+                else:
+                    _lib.check(L.bfm_zero_where_zero(t.data_ptr(), int(t.dtype == torch.float64),
+                                                     SYN_cerebral.data_ptr(), t.numel(), st))
+            wm_sum, wm_n, gm_sum, gm_n = sums.tolist()                  # host sync (the reference's bool(gm > wm))
+            wm_mean = wm_sum / wm_n if wm_n else float('nan')
+            gm_mean = gm_sum / gm_n if gm_n else float('nan')
             pathol_direction = self.get_pathology_direction('synth', bool(gm_mean > wm_mean))
         else:
             pathol_direction = None
@@ -779,12 +800,31 @@ class BaseGen(Dataset):
         if pathol_direction is None:       # True: T2/FLAIR-resembled, False: T1-resembled
             pathol_direction = rng.choice("pathol.dir", [True, False])
         P, Pprob = torch.squeeze(P), torch.squeeze(Pprob)
-        I_mu = (I * P).sum() / P.sum()
-        p_mask = torch.round(P).long()
+        fast = (I.dtype == torch.float32 and P.dtype == Pprob.dtype and P.dtype in (torch.float32, torch.float64)
+                and P.shape == I.shape and Pprob.shape == I.shape)
+        if fast:
+            L, st = _lib.lib(), _stream()
+            I = I if I.is_contiguous() else I.contiguous()
+            P, Pprob = P.contiguous(), Pprob.contiguous()
+            dbl = int(P.dtype == torch.float64)
+            sums = torch.empty(2, dtype=torch.float64, device=self.device)
+            _lib.check(L.bfm_masked_mean(I.data_ptr(), P.data_ptr(), dbl, I.numel(), sums.data_ptr(), st))
+            I_mu = (sums[0] / sums[1]).to(P.dtype if dbl else torch.float32)           # 0-dim, like the reference's
+        else:
+            I_mu = (I * P).sum() / P.sum()
         pth_mus = 3 * I_mu / 4 + I_mu / 4 * rng.torch_rand("pathol.mus", 10000).to(self.device)
         pth_mus = pth_mus if pathol_direction else -pth_mus
         pth_sigmas = I_mu / 4 * rng.torch_rand("pathol.sigmas", 10000).to(self.device)
-        eps = rng.field_randn("pathol.eps", tuple(p_mask.shape))
+        eps = rng.field_randn("pathol.eps", tuple(P.shape))
+        if fast and pth_mus.dtype == torch.float32:
+            eps = None if eps is None else eps.to(self.device, torch.float32).contiguous()
+            pth_mus, pth_sigmas = pth_mus.contiguous(), pth_sigmas.contiguous()
+            _lib.check(L.bfm_encode_pathology(I.data_ptr(), P.data_ptr(), Pprob.data_ptr(), dbl, pth_mus.data_ptr(),
+                                              pth_sigmas.data_ptr(), pth_mus.numel(),
+                                              0 if eps is None else eps.data_ptr(),
+                                              int(rng.seed64()) if eps is None else 0, I.numel(), st))
+            return I
+        p_mask = torch.round(P).long()
         eps = torch.randn(p_mask.shape, dtype=torch.float, device=self.device) if eps is None else eps.to(self.device)
         I += Pprob * (pth_mus[p_mask] + pth_sigmas[p_mask] * eps)
         I[I < 0] = 0

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BFM_LIB") or os.path.join(_HERE, "libbfm.so")
 
 BFM_OK, BFM_E_INVALID, BFM_E_UNSUPPORTED, BFM_E_CUDA = 0, -1, -2, -3
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_f = C.c_float
 c_i = C.c_int
@@ -142,6 +142,11 @@ _PROTOS = {
     "bfm_curl3d": (c_i, [c_p, c_p, c_p, c_i, C.POINTER(c_i), c_f, c_p, c_p, c_p, c_p]),
     "bfm_advect_rhs": (c_i, [c_p, c_i, c_p, c_p, c_p, C.POINTER(c_i), c_i, C.POINTER(c_f), c_p, c_p]),
     "bfm_diffuse_rhs": (c_i, [c_p, c_i, c_p, c_f, C.POINTER(c_i), c_i, C.POINTER(c_f), c_i, c_p, c_p]),
+    "bfm_gmm_crop": (c_i, [c_p, c_i, C.POINTER(c_i), C.POINTER(c_i), c_p, c_p, c_p, c_u64, c_p, c_p]),
+    "bfm_pathol_cerebral": (c_i, [c_p, c_p, c_i, C.POINTER(c_i), C.POINTER(c_i), c_p, c_p, c_p]),
+    "bfm_zero_where_zero": (c_i, [c_p, c_i, c_p, c_i64, c_p]),
+    "bfm_masked_mean": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p]),
+    "bfm_encode_pathology": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_u64, c_i64, c_p]),
     "bfm_rk_combine": (c_i, [c_p, c_i, C.POINTER(c_p), C.POINTER(c_f), c_i, c_i64, c_p, c_i, c_p]),
     "bfm_rk_error_fused": (c_i, [C.POINTER(c_p), C.POINTER(c_f), c_i, c_p, c_p, c_i, c_i64, C.c_double, C.c_double, c_p,
                                  c_p, c_p]),

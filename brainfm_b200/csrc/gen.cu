@@ -1529,25 +1529,34 @@ __global__ void __launch_bounds__(256) k_gen_identity(const bfm_gen_sample *__re
 // row (kWR rows per barrier, double buffered), so a voxel costs one 2-tap lerp from shared memory.  The kernel
 // stores the UNNORMALISED value at its final (flipped) position and reduces the global maximum;
 // k_gen_normalize then applies I / max(I) (datasets.py:342-343) and finishes the real-image targets.
-constexpr int kUR = 16;           // output rows per block
+#ifndef UPS_ROWS
+#define UPS_ROWS 32
+#endif
+#ifndef UPS_MINB
+#define UPS_MINB 8
+#endif
+constexpr int kUR = UPS_ROWS;     // output rows per block
+constexpr int kFinishGroup = 0;   // samples per upsample -> normalise group (0 = whole batch); see bfm_gen_finish
 
-__global__ void __launch_bounds__(256) k_gen_upsample(const bfm_gen_sample *__restrict__ S, int lz_cap, int ny_cap) {
+// myzoom_torch(lowres, 1/factors): three sequential 2-tap passes (axis 0, 1, 2), each `wl*a + wh*b` separately rounded.
+// Block = (x plane i, kUR output rows), thread = k.  The first pass (axis 0) of the low-res rows under the block's
+// output rows is evaluated once per block into shared memory (t1[y'][z']); a voxel then evaluates the second pass at
+// its two z taps and the third pass itself: 4 shared loads + 9 flops, no barrier in the row loop.  (v1 shared the
+// second pass through double-buffered row buffers: the y pass + its barriers cost more instructions per voxel than
+// the duplicated lerps -- 62 -> ~30 warp instructions per 32 voxels, profiles/r2_ncu_rest_summary.csv.)
+__global__ void __launch_bounds__(160, UPS_MINB) k_gen_upsample(const bfm_gen_sample *__restrict__ S, int lz_cap, int ny_cap) {
     extern __shared__ float smem[];
-    __shared__ bfm_gen_sample sd;
     __shared__ float red[8];
-    {
-        const bfm_gen_sample *sp = S + blockIdx.z;
-        if ((int)blockIdx.y >= sp->d.size[0] || (int)blockIdx.x * kUR >= sp->d.size[1]) return;
-    }
-    stage_desc(&sd, S + blockIdx.z);
-    const bfm_gen_sample &s = sd;
+    __shared__ int ylo_s[kUR], yhi_s[kUR];
+    __shared__ float ywl_s[kUR], ywh_s[kUR];
+    const bfm_gen_sample &s = S[blockIdx.z];
+    const int s0 = s.d.size[0], s1 = s.d.size[1], s2 = s.d.size[2];
+    if ((int)blockIdx.y >= s0 || (int)blockIdx.x * kUR >= s1) return;
     if (is_identity_sample(s)) return;                  // k_gen_identity (resample stage) already wrote `out`
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const int s0 = s.d.size[0], s1 = s.d.size[1], s2 = s.d.size[2];
     const int ly = s.new_size[1], lz = s.new_size[2];
     const int i = blockIdx.y, j0 = blockIdx.x * kUR, j1 = min(j0 + kUR, s1);
     float *t1 = smem;                                   // [ny][lz]   first pass at this i
-    float *t2 = smem + ny_cap * lz_cap;                 // [2][kWR][lz_cap]
     const bfm_zoom_tab &u = s.utab;
     // low-res rows needed by output rows j0..j1-1 (the tables are monotone in j)
     const int y0 = __ldg(u.lo[1] + j0), y1 = __ldg(u.hi[1] + j1 - 1);
@@ -1557,45 +1566,39 @@ __global__ void __launch_bounds__(256) k_gen_upsample(const bfm_gen_sample *__re
         const float wl = __ldg(u.wl[0] + i), wh = __ldg(u.wh[0] + i);
         const float *a = s.lowres + ((size_t)lo * ly + y0) * lz, *b = s.lowres + ((size_t)hi * ly + y0) * lz;
         const int n = ny * lz;                          // rows y0..y1 are contiguous in the low-res volume
-        for (int q = tid; q < n; q += blockDim.x) t1[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
+        if ((lz & 3) == 0) {                            // 128-bit loads: both row blocks start on a multiple of lz
+            const float4 *a4 = (const float4 *)a, *b4 = (const float4 *)b;
+            float4 *t4 = (float4 *)t1;
+            for (int q = tid; q < (n >> 2); q += blockDim.x) {
+                const float4 x = __ldg(a4 + q), y = __ldg(b4 + q);
+                t4[q] = make_float4(lerp_rn(wl, x.x, wh, y.x), lerp_rn(wl, x.y, wh, y.y), lerp_rn(wl, x.z, wh, y.z),
+                                    lerp_rn(wl, x.w, wh, y.w));
+            }
+        } else {
+            for (int q = tid; q < n; q += blockDim.x) t1[q] = lerp_rn(wl, __ldg(a + q), wh, __ldg(b + q));
+        }
+    }
+    if (tid < j1 - j0) {
+        const int j = j0 + tid;
+        ylo_s[tid] = (__ldg(u.lo[1] + j) - y0) * lz; yhi_s[tid] = (__ldg(u.hi[1] + j) - y0) * lz;
+        ywl_s[tid] = __ldg(u.wl[1] + j); ywh_s[tid] = __ldg(u.wh[1] + j);
     }
     __syncthreads();
-    auto ypass = [&](int jj, int buf) {
-        for (int r = warp; r < kWR; r += nwarps) {
-            const int j = min(jj + r, s1 - 1);
-            const float *a = t1 + (__ldg(u.lo[1] + j) - y0) * lz, *b = t1 + (__ldg(u.hi[1] + j) - y0) * lz;
-            const float wl = __ldg(u.wl[1] + j), wh = __ldg(u.wh[1] + j);
-            float *row = t2 + (buf * kWR + r) * lz_cap;
-            for (int q = lane; q < lz; q += 32) row[q] = lerp_rn(wl, a[q], wh, b[q]);
-        }
-    };
     float *__restrict__ outp = s.out;
     const int plane_out = (s.flip ? s0 - 1 - i : i) * s1;
     float hi = 0.f;
-    for (int k0 = 0; k0 < s2; k0 += blockDim.x) {
-        const int k = k0 + tid;
-        const bool kv = k < s2;
-        const int kk = kv ? k : s2 - 1;
-        const int zlo = __ldg(u.lo[2] + kk), zhi = __ldg(u.hi[2] + kk);
-        const float zwl = __ldg(u.wl[2] + kk), zwh = __ldg(u.wh[2] + kk);
-        int buf = 0;
-        ypass(j0, 0);
-        __syncthreads();
-        for (int jj = j0; jj < j1; jj += kWR) {
-            if (jj + kWR < j1) ypass(jj + kWR, buf ^ 1);
-            const float *rows = t2 + buf * kWR * lz_cap;
-#pragma unroll
-            for (int r = 0; r < kWR; ++r) {
-                const int j = jj + r;
-                if (j >= j1) break;
-                const float v = lerp_rn(zwl, rows[r * lz_cap + zlo], zwh, rows[r * lz_cap + zhi]);
-                if (kv) {
-                    outp[(plane_out + j) * s2 + k] = v;
-                    hi = fmaxf(hi, v);
-                }
-            }
-            __syncthreads();
-            buf ^= 1;
+    for (int k = tid; k < s2; k += blockDim.x) {
+        const int zlo = __ldg(u.lo[2] + k), zhi = __ldg(u.hi[2] + k);
+        const float zwl = __ldg(u.wl[2] + k), zwh = __ldg(u.wh[2] + k);
+        float *__restrict__ o = outp + (size_t)(plane_out + j0) * s2 + k;
+#pragma unroll 4
+        for (int r = 0; r < j1 - j0; ++r) {
+            const float *a = t1 + ylo_s[r], *b = t1 + yhi_s[r];
+            const float wl = ywl_s[r], wh = ywh_s[r];
+            const float vl = lerp_rn(wl, a[zlo], wh, b[zlo]), vh = lerp_rn(wl, a[zhi], wh, b[zhi]);
+            const float v = lerp_rn(zwl, vl, zwh, vh);
+            o[(size_t)r * s2] = v;
+            hi = fmaxf(hi, v);
         }
     }
     hi = warp_max(hi);
@@ -1740,7 +1743,12 @@ int bfm_gen_gmm(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *s
     if (plane_groups > 0) {
         if (max_n0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_gmm: grid too large");
         // blockIdx.y walks the x planes of the crop (<= src[0]); a few row tiles per plane when the batch is small
-        const int tiles = (int)min((int64_t)8, max((int64_t)1, (int64_t)(4 * 148) / ((int64_t)max_n0 * B)));
+        // and enough blocks for ~2 waves of 148 SMs x 8 resident blocks: with one block per plane a batch of 8 x 160
+        // planes is 1.08 waves (a nearly empty second wave).  Measured per sample: 1 tile 13.8 us, 2: 12.6, 4: 13.1,
+        // 8: 14.4 (the 512-entry table is staged per block).
+        static const int tiles_env = getenv("BFM_GMM_TILES") ? atoi(getenv("BFM_GMM_TILES")) : 0;
+        const int64_t want = (2LL * 148 * 8 + (int64_t)max_n0 * B - 1) / ((int64_t)max_n0 * B);
+        const int tiles = tiles_env > 0 ? tiles_env : (int)min((int64_t)8, max((int64_t)1, want));
         k_gen_gmm_planes<<<dim3(tiles, max_n0, B), 256, 0, (cudaStream_t)stream>>>(d);
         rc = check_launch("bfm_gen_gmm");
         if (rc) return rc;
@@ -1994,25 +2002,34 @@ int bfm_gen_finish(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void
         s0 = max(s0, s.d.size[0]); s1 = max(s1, s.d.size[1]); s2 = max(s2, s.d.size[2]);
         if (((int64_t)s.d.size[1] * s.d.size[2]) & 3) scalar = true; else vec = true;
     }
-    const size_t smem = ((size_t)ny * lz + 2 * kWR * lz) * sizeof(float);
+    const size_t smem = (size_t)ny * lz * sizeof(float);
     if (smem > 200 * 1024) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: low-res rows too long for shared memory");
     if (s0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: grid too large");
     if (smem > 40 * 1024)
         cudaFuncSetAttribute(k_gen_upsample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = (cudaStream_t)stream;
-    const int threads = min(256, (s2 + 31) / 32 * 32);
-    k_gen_upsample<<<dim3((s1 + kUR - 1) / kUR, s0, B), threads, smem, st>>>(d, lz, ny);
-    rc = check_launch("bfm_gen_finish");
-    if (rc) return rc;
+    const int threads = min(160, (s2 + 31) / 32 * 32);
     const int64_t plane = (int64_t)s1 * s2;
-    if (vec) {
-        k_gen_normalize<4><<<dim3((unsigned)((plane / 4 + 255) / 256), s0, B), 256, 0, st>>>(d);
+    // Groups of samples: the unnormalised volumes k_gen_upsample writes (4 B/voxel) are still in the 126 MB L2 when
+    // k_gen_normalize reads them back if a group stays well below L2 size.  BFM_FINISH_GROUP overrides (0 = whole batch).
+    static const int group_env = getenv("BFM_FINISH_GROUP") ? atoi(getenv("BFM_FINISH_GROUP")) : -1;
+    int G = group_env < 0 ? kFinishGroup : group_env;
+    if (G <= 0 || G > B) G = B;
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int n = B - b0 < G ? B - b0 : G;
+        k_gen_upsample<<<dim3((s1 + kUR - 1) / kUR, s0, n), threads, smem, st>>>(d + b0, lz, ny);
         rc = check_launch("bfm_gen_finish");
         if (rc) return rc;
-    }
-    if (scalar) {
-        k_gen_normalize<1><<<dim3((unsigned)((plane + 255) / 256), s0, B), 256, 0, st>>>(d);
-        rc = check_launch("bfm_gen_finish");
+        if (vec) {
+            k_gen_normalize<4><<<dim3((unsigned)((plane / 4 + 255) / 256), s0, n), 256, 0, st>>>(d + b0);
+            rc = check_launch("bfm_gen_finish");
+            if (rc) return rc;
+        }
+        if (scalar) {
+            k_gen_normalize<1><<<dim3((unsigned)((plane + 255) / 256), s0, n), 256, 0, st>>>(d + b0);
+            rc = check_launch("bfm_gen_finish");
+            if (rc) return rc;
+        }
     }
     return rc;
 }

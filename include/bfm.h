@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 6
+#define BFM_ABI_VERSION 7
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -471,6 +471,25 @@ int bfm_rk_error_sum(const float *err, const void *y0, const void *y1, int is_do
 int bfm_rk_error_fused(const float *const *k_host, const float *coef_host, int n_terms, const void *y0, const void *y1,
                        int is_double, int64_t n, double rtol, double atol, float *err_scratch, double *result_dev,
                        void *stream);
+
+/* ---- pathology branch of generate_sample / augment_sample (op-level) ------------------------------------------- */
+/* SYN = clamp(mus[round(G)] + sigmas[round(G)] * eps, 0) over the crop bbox = {x1,y1,z1,x2,y2,z2} of the label volume
+ * (label 77 -> 2); eps: (crop) float32 draws or NULL (counter-based field keyed on the absolute source voxel).
+ * Generator/datasets.py:364-372 */
+int bfm_gmm_crop(const void *labels, int label_is_u8, const int *src, const int *bbox, const float *mu,
+                 const float *sigma, const float *eps, uint64_t seed, float *out, void *stream);
+/* cerebral = SYN * (Gr != 0); sums_dev[0..3] = sum(SYN | white matter), #white, sum(SYN | grey), #grey
+ * Generator/datasets.py:391-398 */
+int bfm_pathol_cerebral(const float *syn, const void *labels, int label_is_u8, const int *src, const int *bbox,
+                        float *cerebral, double *sums_dev, void *stream);
+/* p[c == 0] = 0 (p float32 or float64)                                Generator/datasets.py:399-400 */
+int bfm_zero_where_zero(void *p, int p_is_double, const float *c, int64_t n, void *stream);
+/* sums_dev[0] = sum(I * P), sums_dev[1] = sum(P)                       Generator/datasets.py:500 */
+int bfm_masked_mean(const float *I, const void *P, int p_is_double, int64_t n, double *sums_dev, void *stream);
+/* I += Pprob * (mus[round(P)] + sigmas[round(P)] * eps); I[I < 0] = 0 with the reference's dtype promotions (float64
+ * P / Pprob: product and sum in float64, one rounding to float32)      Generator/datasets.py:509-513 */
+int bfm_encode_pathology(float *I, const void *P, const void *Pprob, int p_is_double, const float *mus,
+                         const float *sigmas, int n_tab, const float *eps, uint64_t seed, int64_t n, void *stream);
 
 #ifdef __cplusplus
 }
