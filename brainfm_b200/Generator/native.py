@@ -209,7 +209,11 @@ class NativePlanner:
         return ent['ok']
 
     # ---- one batch ---------------------------------------------------------------------------------------
-    def run(self, indices, timers=None):
+    def run(self, indices, timers=None, patch=None, plan_only=False):
+        """Plan the batch in the library and run the fused chain.
+        patch(descs, info): optional hook called after planning and BEFORE the descriptors travel to the device (slab
+        mode sets x_begin / x_count there, which depend on the planned flip).  plan_only: stop after the upload and
+        return the plan (descs, device address, info, output tensors) without launching any stage."""
         ds, L = self.ds, _lib.lib()
         size, N, ns = self.size, self.N, self.n_samples
         B = len(indices)
@@ -301,9 +305,19 @@ class NativePlanner:
         self.counter += B
         arena.used = used.value
         st = _stream()
+        if patch is not None:
+            patch(descs, info)
+            C.memmove(slot["host"].data_ptr() + (descs_dev.value - slot["dev"].data_ptr()), C.addressof(descs),
+                      C.sizeof(descs))
         nbytes = (upload.value + 15) // 16 * 16
         _lib.check(L.bfm_upload_pinned(slot["dev"].data_ptr() + start, slot["host"].data_ptr() + start, nbytes, st))
         arena.committed = arena.used
+        if plan_only:
+            self.last = dict(descs=descs, descs_dev=descs_dev.value, info=info, total=total,
+                             keep=(out, bfl, res, aux_all, keep), arena_slot=arena.cur)
+            ds._last_descs = (descs, descs_dev.value, total)
+            return dict(descs=descs, d_dev=descs_dev.value, info=info, out=out, bfl=bfl, res=res, aux=aux_all,
+                        arena=arena, metas=metas)
         # ---- per-item context (targets that do not ride on the fused gather need a DeformPlan)
         h, d_dev = C.addressof(descs), descs_dev.value
         other_targets = self._other_targets

@@ -44,6 +44,158 @@ def _band_axis(x, axis, n_out, start, w, T, arena):
     return y
 
 
+_HOST_TABS = {}
+
+
+def _band_ranges_host(n_in, n_out):
+    """floor of the low-res sample positions along one axis (the band's first tap is floor - ceil(3 sigma)); cached."""
+    key = ('band', int(n_in), int(n_out))
+    hit = _HOST_TABS.get(key)
+    if hit is None:
+        lo = np.floor(resample_coords_host(n_in, n_out)[0]).astype(np.int64)
+        hit = _HOST_TABS[key] = (lo, np.clip(lo, 0, n_in - 1))
+    return hit
+
+
+def _zoom_ranges_host(n_in, n_out):
+    """lo / hi source planes of the zoom back along one axis (host copy of the device table); cached."""
+    key = ('zoom', int(n_in), int(n_out))
+    hit = _HOST_TABS.get(key)
+    if hit is None:
+        t = zoom_tables_host(n_in, 1 / (n_in / n_out), n_out)
+        hit = _HOST_TABS[key] = (t[0].astype(np.int64), t[1].astype(np.int64))
+    return hit
+
+
+def _mx_all_reduce(mx, world, group):
+    if world > 1:
+        if dist.get_backend(group) == "gloo":              # ranks sharing one GPU (tests): reduce on the host
+            h_mx = mx.cpu()
+            dist.all_reduce(h_mx, op=dist.ReduceOp.MAX, group=group)
+            mx = h_mx.to(mx.device)
+        else:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return mx
+
+
+def _generate_slab_native(ds, native, idx, rank, world, group):
+    """Slab mode on the library planner: ONE bfm_plan_batch call plans the volume (a few microseconds, against ~1 ms
+    for the Python planner), the band tables are built on the device by bfm_gen_plan, the zoom tables come from the
+    device-resident cache, and the banded passes run in the fused chain's order (ascending factor, identity axes
+    skipped) with the fused chain's tables -- so the assembled volume equals what generate_batch produces for the same
+    planner state, up to the order-independent parts.  The x pass and the zoom back address the exchanged plane
+    buffers through a base pointer biased by the first plane they hold, so the whole-volume tables are used as they
+    are (no per-slab copies of tables)."""
+    L = _lib.lib()
+    s0, s1, s2 = [int(v) for v in ds.size]
+    state = {}
+
+    def patch(descs, info):
+        flip = bool(descs[0].flip)
+        # planes of the (unflipped) grid this rank computes; with a flip the slabs are mirrored so that the planes
+        # a rank computes are the ones it owns in the flipped output
+        owned = [list(par.slab_bounds(s0, (world - 1 - r) if flip else r, world)) for r in range(world)]
+        c0, c1 = owned[rank]
+        if c1 <= c0:
+            raise ValueError("slab mode: rank %d owns no plane (%d planes over %d ranks)" % (rank, s0, world))
+        descs[0].x_begin, descs[0].x_count = c0, c1 - c0
+        state.update(flip=flip, owned=owned)
+
+    plan = native.run([idx], patch=patch, plan_only=True)
+    descs, d_dev = plan['descs'], plan['d_dev']
+    s = descs[0]
+    if s.real_input or s.mix[0]:
+        raise NotImplementedError("slab mode covers synthetic inputs without mixing")
+    flip, owned = state['flip'], state['owned']
+    c0, c1 = owned[rank]
+    h, st = C.addressof(descs), _stream()
+    for fn in (L.bfm_gen_plan, L.bfm_gen_bbox, L.bfm_gen_gmm, L.bfm_gen_warp):
+        _lib.check(fn(h, d_dev, 1, st))
+    N = s0 * s1 * s2
+    dev = plan['out'].device
+    cur = ds._ws['i_bf'][:N].view(s0, s1, s2)[c0:c1]
+    dims = [s0, s1, s2]
+    new = [int(v) for v in s.new_size[:]]
+    identity = s.n_band == 1 and s.band[0].T == 1 and s.band[0].build == 0
+    low_owned = [list(o) for o in owned]
+    if identity:
+        cur = cur.clone()                      # the noise is added in place; i_bf is persistent scratch
+    else:
+        for q in range(s.n_band):
+            b = s.band[q]
+            a, T, n_out = int(b.axis), int(b.T), int(b.n_out)
+            if a == 0:
+                # ---- x pass: ceil(3 sigma) + 1 planes from each neighbour
+                lo, centre = _band_ranges_host(s0, n_out)
+                start = lo - (T - 2) // 2
+                low_owned, needed = [], []
+                for r in range(world):
+                    b_, e_ = owned[r]
+                    o = np.nonzero((centre >= b_) & (centre < e_))[0]
+                    low_owned.append([int(o[0]), int(o[-1]) + 1] if o.size else [0, 0])
+                    ob, oe = low_owned[-1]
+                    if oe > ob:
+                        needed.append([int(max(0, start[ob:oe].min())), int(min(s0, start[ob:oe].max() + T))])
+                    else:
+                        needed.append([owned[r][0], owned[r][0]])
+                ext = par.exchange_planes(cur, owned, needed, rank, world, group)
+                ob, oe = low_owned[rank]
+                y = torch.empty((max(oe - ob, 0), dims[1], dims[2]), dtype=torch.float32, device=dev)
+                if y.numel():
+                    plane_bytes = 4 * dims[1] * dims[2]
+                    _lib.check(L.bfm_band_axis(ext.data_ptr() - needed[rank][0] * plane_bytes, y.data_ptr(),
+                                               (C.c_int * 3)(s0, dims[1], dims[2]), 0, oe - ob, b.start + 4 * ob,
+                                               b.w + 4 * ob * T, T, -1.0, None, 0, st))
+            else:
+                shape = [cur.shape[0], dims[1], dims[2]]
+                oshape = list(shape)
+                oshape[a] = n_out
+                y = torch.empty(oshape, dtype=torch.float32, device=dev)
+                if y.numel():
+                    _lib.check(L.bfm_band_axis(cur.data_ptr(), y.data_ptr(), (C.c_int * 3)(*shape), a, n_out, b.start,
+                                               b.w, T, -1.0, None, 0, st))
+            cur = y
+            dims[a] = n_out
+    ob, oe = low_owned[rank]
+    low = cur
+    # ---- strict `> 0` masks of the identity axes, then the noise (counter-based stream 1 keyed on the ABSOLUTE low-res
+    # voxel: the assembled volume does not depend on the number of ranks)
+    if low.numel():
+        if s.zero_first[0] and ob == 0:
+            low[0].zero_()
+        if s.zero_first[1]:
+            low[:, 0].zero_()
+        if s.zero_first[2]:
+            low[:, :, 0].zero_()
+        _lib.check(L.bfm_add_noise_at(low.data_ptr(), low.numel(), float(s.noise_std), int(s.seed), 1,
+                                      ob * dims[1] * dims[2], st))
+    if identity:
+        out = low
+    else:
+        # ---- back to the training grid: low-res planes lo[c0] .. hi[c1-1] (1-2 from the neighbours)
+        zlo, zhi = _zoom_ranges_host(new[0], s0)
+        need_low = [[int(zlo[o[0]]), int(zhi[o[1] - 1]) + 1] if o[1] > o[0] else [0, 0] for o in owned]
+        lext = par.exchange_planes(low, low_owned, need_low, rank, world, group)
+        nb = need_low[rank][0]
+        out = torch.empty((c1 - c0, s1, s2), dtype=torch.float32, device=dev)
+        u = s.utab
+        args = [lext.data_ptr() - nb * 4 * new[1] * new[2], new[0], new[1], new[2], 1,
+                u.lo[0] + 4 * c0, u.hi[0] + 4 * c0, u.wl[0] + 4 * c0, u.wh[0] + 4 * c0, c1 - c0,
+                u.lo[1], u.hi[1], u.wl[1], u.wh[1], s1, u.lo[2], u.hi[2], u.wl[2], u.wh[2], s2]
+        _lib.check(L.bfm_zoom_linear(*args, out.data_ptr(), st))
+    # ---- I / max(I) with the global maximum (datasets.py:342-343), then the flip
+    mx = _mx_all_reduce(out.max().reshape(1), world, group)
+    fin = torch.empty_like(out)
+    _lib.check(L.bfm_shift_scale_flip(out.data_ptr(), fin.data_ptr(), c1 - c0, s1 * s2, None, mx.data_ptr(), 1.0,
+                                      1 if flip else 0, st))
+    x0, x1 = (s0 - c1, s0 - c0) if flip else (c0, c1)
+    sample = {'input': fin[None], 'x_range': (x0, x1)}
+    if plan['bfl'] is not None and s.bflog_out:
+        sample['bias_field_log'] = plan['bfl'][0][:, x0:x1]
+    plan['arena'].mark_done()
+    return sample
+
+
 def generate_slab(ds, idx, rank=None, world=None, group=None):
     """This rank's x-slab of sample `idx` of dataset `ds` (BaseGen): {'input': (1, nx, s1, s2),
     'bias_field_log': (1, nx, s1, s2) or absent, 'x_range': (x0, x1)} with x0:x1 the owned planes of the final
@@ -52,6 +204,10 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
+    ds.cache.begin_batch()
+    native = ds._native_planner([idx]) if not getattr(ds.rng, 'replay', False) else None
+    if native is not None and native.n_samples == 1:
+        return _generate_slab_native(ds, native, idx, rank, world, group)
     L = _lib.lib()
     size = [int(v) for v in ds.size]
     s0, s1, s2 = size
@@ -139,14 +295,7 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
             args += [addr[4 * d], addr[4 * d + 1], addr[4 * d + 2], addr[4 * d + 3], int(n_out)]
         _lib.check(L.bfm_zoom_linear(*args, out.data_ptr(), _stream()))
     # ---- I / max(I) with the global maximum (datasets.py:342-343), then the flip
-    mx = out.max().reshape(1) if out.numel() else torch.zeros(1, device=low.device)
-    if world > 1:
-        if dist.get_backend(group) == "gloo":              # ranks sharing one GPU (tests): reduce on the host
-            h_mx = mx.cpu()
-            dist.all_reduce(h_mx, op=dist.ReduceOp.MAX, group=group)
-            mx = h_mx.to(mx.device)
-        else:
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    mx = _mx_all_reduce(out.max().reshape(1) if out.numel() else torch.zeros(1, device=low.device), world, group)
     # one pass: I / max and the flip of the slab's planes (bfm_shift_scale_flip: true division like the reference)
     if out.numel():
         fin = torch.empty_like(out)

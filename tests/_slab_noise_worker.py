@@ -29,7 +29,7 @@ def dataset(dev):
     old = bench.SIZE
     bench.SIZE = SIZE
     try:
-        ds = bench.build_dataset(bench.make_inputs(1), dev, planner="python")
+        ds = bench.build_dataset(bench.make_inputs(1), dev, planner=os.environ.get("BFM_SLAB_PLANNER", "python"))
     finally:
         bench.SIZE = old
     return ds
@@ -38,6 +38,8 @@ def dataset(dev):
 def seeded(fn, seed, ds=None):
     if ds is not None:                       # the Philox key of a sample = splitmix64(one numpy draw, call counter):
         ds.rng._seed_base, ds.rng._seed_count = None, 0        # restart it so that equal seeds give equal keys
+        if getattr(ds, "_native", None) is not None:             # library planner: (seed, item counter) likewise
+            ds._native.seed, ds._native.counter = None, 0
     np.random.seed(seed)
     torch.manual_seed(seed)
     import random
@@ -55,6 +57,8 @@ def main():
         ds = dataset(dev)
         mine = seeded(lambda: generate_slab(ds, 0, rank, world), seed, ds)
         assert ds._last_descs[0][0].eps_noise is None and ds._last_descs[0][0].eps_gmm is None
+        if os.environ.get("BFM_SLAB_PLANNER") == "native":
+            assert ds._native is not None and ds._last_descs[0][0].gen_small != 0      # planned by the library
         solo = seeded(lambda: generate_slab(ds, 0, 0, 1), seed, ds)
         fused = seeded(lambda: ds.generate_batch([0])[0][4]['input'], seed, ds)
         torch.cuda.synchronize()

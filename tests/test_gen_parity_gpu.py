@@ -187,15 +187,16 @@ def test_slab_mode_two_ranks():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("planner", ["python", "native"])
 @pytest.mark.parametrize("world", [1, 3])
-def test_slab_mode_without_injected_draws_does_not_depend_on_the_decomposition(world):
+def test_slab_mode_without_injected_draws_does_not_depend_on_the_decomposition(world, planner):
     """The library's own noise (counter-based, keyed on absolute source / low-res voxels): a volume generated on W
     ranks equals the single-rank slab run bit for bit and the fused chain within tolerance.  The ranks share GPU 0
     (gloo stages the exchanged planes through the host), so this runs on a 1-GPU box."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, BFM_SLAB_ONE_GPU="1")
+    env = dict(os.environ, BFM_SLAB_ONE_GPU="1", BFM_SLAB_PLANNER=planner)
     worker = os.path.join(root, "tests", "_slab_noise_worker.py")
     cmd = [sys.executable, worker] if world == 1 else \
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
