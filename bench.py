@@ -97,14 +97,62 @@ class ClockSampler:
     def start(self):
         if os.environ.get("BFM_CLOCK_MS") == "0":       # development switch: no sampler at all
             return
+        self.period = float(os.environ.get("BFM_CLOCK_MS", "20")) * 1e-3
+        self._stop = False
+        # in-process NVML (three queries per sample) when pynvml is importable; an `nvidia-smi -lms` child otherwise.
+        # The child re-queries a dozen fields per line through the driver and was measured to cost the two-stream
+        # device-resident arm ~5-8 % at a 20 ms period.
+        try:
+            if os.environ.get("BFM_CLOCK_SMI") == "1":
+                raise RuntimeError("nvidia-smi forced")
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+            self.proc = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BFM_CLOCK_MS", "20")], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BFM_CLOCK_MS", "20")],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self):
+        n = self.nvml
+        bits = [("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self._stop:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                r = int(get_reasons(self.handle))
+                row = [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits]
+                self.rows.append((time.perf_counter(), row))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -117,6 +165,9 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
+            return
+        if self.proc == "nvml":
+            self._stop = True
             return
         self.proc.terminate()
         try:
@@ -138,6 +189,7 @@ class ClockSampler:
         timed = self._stats([r for r in self.rows if t0 <= r[0] <= t1])
         load = self._stats([r for r in self.rows if load0 <= r[0] <= load1])
         out = dict(timed if timed["samples"] else load)
+        out["sampler"] = "nvml (in-process)" if self.proc == "nvml" else "nvidia-smi -lms"
         out["window"] = "timed region" if timed["samples"] else "whole run under load (timed region < sampling interval)"
         out["timed_region_samples"] = timed["samples"]
         out["under_load"] = load

@@ -99,7 +99,12 @@ def _generate_slab_native(ds, native, idx, rank, world, group):
         if c1 <= c0:
             raise ValueError("slab mode: rank %d owns no plane (%d planes over %d ranks)" % (rank, s0, world))
         descs[0].x_begin, descs[0].x_count = c0, c1 - c0
-        state.update(flip=flip, owned=owned)
+        # the GMM stage only synthesises the source planes this slab gathers from (bfm_gen_bbox reduces the range)
+        xr = None
+        if world > 1:
+            xr = torch.empty(2, dtype=torch.int32, device=ds.device)
+            descs[0].gmm_xr = xr.data_ptr()
+        state.update(flip=flip, owned=owned, xr=xr)
 
     plan = native.run([idx], patch=patch, plan_only=True)
     descs, d_dev = plan['descs'], plan['d_dev']
@@ -230,6 +235,9 @@ def generate_slab(ds, idx, rank=None, world=None, group=None):
     owned = [list(par.slab_bounds(s0, (world - 1 - r) if flip else r, world)) for r in range(world)]
     c0, c1 = owned[rank]
     descs[0].x_begin, descs[0].x_count = c0, c1 - c0
+    if world > 1:
+        xr = torch.empty(2, dtype=torch.int32, device=ds.device)      # source planes this slab gathers from (GMM range)
+        descs[0].gmm_xr = xr.data_ptr()
     d_dev = arena.put_struct_array(descs)
     arena.commit()
     ds._last_descs = (descs, d_dev, 1)

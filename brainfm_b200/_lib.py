@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BFM_LIB") or os.path.join(_HERE, "libbfm.so")
 
 BFM_OK, BFM_E_INVALID, BFM_E_UNSUPPORTED, BFM_E_CUDA = 0, -1, -2, -3
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_f = C.c_float
 c_i = C.c_int
@@ -46,7 +46,8 @@ class GenSample(C.Structure):
                 ("utab", ZoomTab), ("maxval", c_p), ("out", c_p), ("residual", c_p),
                 ("n_aux", c_i), ("aux_src", c_p * MAX_AUX), ("aux_raw", c_p * MAX_AUX), ("aux_out", c_p * MAX_AUX),
                 ("aux_mm", c_p), ("x_begin", c_i), ("x_count", c_i),
-                ("gen_small", c_i), ("fs_std", c_f), ("bf_std", c_f), ("real_input", c_i), ("syn_pair_ok", c_i)]
+                ("gen_small", c_i), ("fs_std", c_f), ("bf_std", c_f), ("real_input", c_i), ("syn_pair_ok", c_i),
+                ("gmm_xr", c_p)]
 
 
 # ---- native host planner (bfm_plan_batch) ----------------------------------------------------------------

@@ -272,6 +272,56 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_bbox_full(const bfm_gen_
     block_minmax_atomic(lo, hi, sd.bbox);
 }
 
+// Slab mode: source x range of the owned output planes [x_begin, x_begin + x_count) -> gmm_xr (see bfm.h).
+// init: {+inf bits, 0}; scan: persistent blocks over the slab's rows; finish: floor(min), 1 + ceil(max).
+__global__ void k_gen_slab_xr_init(const bfm_gen_sample *__restrict__ S) {
+    const bfm_gen_sample &s = S[blockIdx.x];
+    if (s.gmm_xr && s.x_count > 0 && threadIdx.x < 2) s.gmm_xr[threadIdx.x] = threadIdx.x ? 0 : 0x7f7fffff;
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) k_gen_slab_xr(const bfm_gen_sample *__restrict__ S, int fstride) {
+    extern __shared__ float smem[];
+    __shared__ bfm_gen_sample sd;
+    __shared__ float red[32][2];
+    {
+        const bfm_gen_sample &s0 = S[blockIdx.y];
+        if (!s0.gmm_xr || s0.x_count <= 0) return;
+    }
+    stage_desc(&sd, S + blockIdx.y);
+    const bfm_deform &d = sd.d;
+    const DefRegs g = load_def(d);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float *smF = smem + warp * kRowsPerWarp * fstride;
+    const int first = sd.x_begin * g.s1, n_rows = (sd.x_begin + sd.x_count) * g.s1;
+    float lo = INFINITY, hi = 0.f;
+    for (int chunk = blockIdx.x; first + chunk * kRowWarps * kRowsPerWarp < n_rows; chunk += gridDim.x) {
+        const int row0 = first + (chunk * kRowWarps + warp) * kRowsPerWarp;
+        if (row0 < n_rows) {
+            deform_rows<kRowsPerWarp>(d, g, smF, row0, n_rows, lane, [](int) {},
+                                      [&](int, int, int, int, int, float px, float, float) {
+                                          lo = fminf(lo, px); hi = fmaxf(hi, px);
+                                      });
+        }
+        __syncwarp();
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    if (lane == 0) { red[warp][0] = lo; red[warp][1] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float v = red[0][threadIdx.x];
+        for (int w = 1; w < nw; ++w) v = threadIdx.x ? fmaxf(v, red[w][1]) : fminf(v, red[w][0]);
+        if (threadIdx.x) atomicMax(sd.gmm_xr + 1, __float_as_int(v));      // coordinates >= 0: bit order == float order
+        else atomicMin(sd.gmm_xr, __float_as_int(v));
+    }
+}
+
+__global__ void k_gen_slab_xr_finish(const bfm_gen_sample *__restrict__ S) {
+    const bfm_gen_sample &s = S[blockIdx.x];
+    if (!s.gmm_xr || s.x_count <= 0) return;
+    if (threadIdx.x == 0) s.gmm_xr[0] = (int)floorf(__int_as_float(s.gmm_xr[0]));
+    else if (threadIdx.x == 1) s.gmm_xr[1] = 1 + (int)ceilf(__int_as_float(s.gmm_xr[1]));
+}
+
 __global__ void k_gen_bbox_finish(const bfm_gen_sample *__restrict__ S) {
     if (bbox_follower(S, blockIdx.x)) return;
     int *bb = S[blockIdx.x].bbox;
@@ -302,6 +352,7 @@ __global__ void __launch_bounds__(256) k_gen_gmm_planes(const bfm_gen_sample *__
     const int b0 = bb[0], b1 = bb[1], b2 = bb[2], e0 = bb[3], e1 = bb[4], e2 = bb[5];
     const int x = b0 + blockIdx.y;
     if (x >= e0 || x >= n0) return;
+    if (sp->gmm_xr && sp->x_count > 0 && (x < sp->gmm_xr[0] || x >= sp->gmm_xr[1])) return;   // slab mode: reachable planes
     // rows of this tile
     const int rows = e1 - b1, per = (rows + gridDim.x - 1) / gridDim.x;
     const int ya = b1 + blockIdx.x * per, yb = min(ya + per, e1);
@@ -380,6 +431,7 @@ __global__ void __launch_bounds__(256) k_gen_gmm(const bfm_gen_sample *__restric
     {   // whole block outside the crop slab along x?  (blocks cover contiguous flat ranges)
         const int xa = blk0 / (n1 * n2), xb = min(blk0 + (int)blockDim.x * 4 - 1, total - 1) / (n1 * n2);
         if (xb < s.bbox[0] || xa >= s.bbox[3]) return;
+        if (s.gmm_xr && s.x_count > 0 && (xb < s.gmm_xr[0] || xa >= s.gmm_xr[1])) return;      // slab mode
     }
     for (int q = threadIdx.x; q < 512; q += blockDim.x) lut[q] = q < 256 ? __ldg(s.mu + q) : __ldg(s.sigma + q - 256);
     __syncthreads();
@@ -1720,6 +1772,14 @@ int bfm_gen_bbox(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
     k_gen_bbox_full<<<dim3(full_blocks, B), kRowWarps * 32, smem, s>>>(d, fstride);
     k_gen_bbox_finish<<<B, 32, 0, s>>>(d);
     g_launches.fetch_add(most > 0 ? 4 : 3);
+    bool slab_xr = false;
+    for (int b = 0; b < B; ++b) slab_xr |= (h[b].gmm_xr && h[b].x_count > 0);
+    if (slab_xr) {
+        k_gen_slab_xr_init<<<B, 32, 0, s>>>(d);
+        k_gen_slab_xr<<<dim3(full_blocks, B), kRowWarps * 32, smem, s>>>(d, fstride);
+        k_gen_slab_xr_finish<<<B, 32, 0, s>>>(d);
+        g_launches.fetch_add(3);
+    }
     return check_launch("bfm_gen_bbox");
 }
 

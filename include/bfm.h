@@ -27,7 +27,7 @@ extern "C" {
 #define BFM_E_UNSUPPORTED (-2)  /* valid in the reference but not implemented here */
 #define BFM_E_CUDA (-3)         /* CUDA runtime error; see bfm_last_error() */
 
-#define BFM_ABI_VERSION 7
+#define BFM_ABI_VERSION 8
 
 int bfm_abi_version(void);
 const char *bfm_last_error(void);
@@ -263,6 +263,12 @@ typedef struct bfm_gen_sample {
        (k_gen_warp_pk: half the load requests of the two-volume gather, packed f32x2 arithmetic).  Results are
        identical to the unpaired path. */
     int syn_pair_ok;
+    /* Slab mode, optional: 2 ints of device scratch.  With x_count > 0, bfm_gen_bbox also reduces the source x range
+       [gmm_xr[0], gmm_xr[1]) that the OWNED output planes gather from (same clamped coordinates as the bounding box,
+       floor(min) .. 1 + ceil(max)), and bfm_gen_gmm only synthesises those planes of the crop: the bounding box --
+       the origin of the crop-relative coordinates -- stays the whole volume's, so results do not depend on the
+       decomposition, but a rank no longer runs the GMM stage over the whole replicated label map.  NULL: whole crop. */
+    int *gmm_xr;
 } bfm_gen_sample;
 
 /* Each stage launches over samples [0,B).  `s_dev` is the device copy of the descriptor array,

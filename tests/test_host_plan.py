@@ -63,7 +63,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.exported_symbols())
-    assert L.bfm_abi_version() == _lib.ABI_VERSION == 7
+    assert L.bfm_abi_version() == _lib.ABI_VERSION == 8
 
 
 @pytest.mark.parametrize("seed", range(6))
