@@ -53,8 +53,10 @@ def run(size=512, steps=5, rank=0, world=1, local=0):
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(steps):
         out = generate_slab(ds, 0, rank, world)
+    host_ms = 1e3 * (time.perf_counter() - h0) / steps          # time to ENQUEUE a volume (incl. waits for arena slots)
     e1.record()
     sync()
     ms = par.all_reduce_max(e0.elapsed_time(e1) / steps, device=dev)
@@ -65,7 +67,8 @@ def run(size=512, steps=5, rank=0, world=1, local=0):
     return {"workload": "one %d^3 BaseGen sample (input + bias_field_log), slab mode" % size,
             "n_gpus": world, "ms_per_volume": ms, "volumes_per_s": 1e3 / ms,
             "Mvoxels_per_s": size ** 3 / ms / 1e3, "slab_planes_rank0": list(out["x_range"]),
-            "checksum": float(chk.item()), "steps": steps}
+            "checksum": float(chk.item()), "steps": steps,
+            "host_enqueue_ms_per_volume": par.all_reduce_max(host_ms, device=dev)}
 
 
 def main():
