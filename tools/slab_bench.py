@@ -60,6 +60,24 @@ def run(size=512, steps=5, rank=0, world=1, local=0):
     e1.record()
     sync()
     ms = par.all_reduce_max(e0.elapsed_time(e1) / steps, device=dev)
+    prof_txt = None
+    if os.environ.get("SLAB_PROFILE") == "1":
+        # rank 0: how busy is the GPU?  (sum of kernel / memcpy durations over the wall time of `steps` volumes)
+        from torch.profiler import profile, ProfilerActivity
+        sync()
+        w0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                generate_slab(ds, 0, rank, world)
+            torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        if rank == 0:
+            ev = [e for e in prof.key_averages()]
+            tot = sum(e.device_time_total for e in ev) * 1e-3
+            rows = sorted(ev, key=lambda e: -e.device_time_total)[:14]
+            prof_txt = "GPU busy %.3f ms of %.3f ms wall per volume (rank 0, under the profiler)\n" % (tot / steps, 1e3 * wall / steps)
+            prof_txt += "\n".join("%8.1f us x%-3d %s" % (e.device_time_total / steps, e.count // steps, e.key[:90]) for e in rows)
+        sync()
     chk = out["input"].double().sum().reshape(1)
     if world > 1:
         dist.all_reduce(chk)
@@ -68,7 +86,7 @@ def run(size=512, steps=5, rank=0, world=1, local=0):
             "n_gpus": world, "ms_per_volume": ms, "volumes_per_s": 1e3 / ms,
             "Mvoxels_per_s": size ** 3 / ms / 1e3, "slab_planes_rank0": list(out["x_range"]),
             "checksum": float(chk.item()), "steps": steps,
-            "host_enqueue_ms_per_volume": par.all_reduce_max(host_ms, device=dev)}
+            "host_enqueue_ms_per_volume": par.all_reduce_max(host_ms, device=dev), "profile": prof_txt}
 
 
 def main():
@@ -78,7 +96,10 @@ def main():
     torch.cuda.set_device(local)
     res = run(size, steps, rank, world, local)
     if rank == 0:
+        prof_txt = res.pop("profile", None)
         print(json.dumps(res), flush=True)
+        if prof_txt:
+            print(prof_txt, file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
