@@ -530,7 +530,8 @@ def main():
                 extras["brainid_stream"] = cb.brainid_cfg()   # configs[4]a
             else:
                 import slab_bench as sb                       # configs[4]b: one 512^3 volume in x-slabs over the ranks
-                extras["slab512"] = sb.run(512, 3, rank, world, local)
+                extras["slab512"] = sb.run(512, 6, rank, world, local)
+                extras["slab512"].pop("profile", None)
         except Exception as e:                                # never lose the bench line over an extra
             extras["error"] = repr(e)[:300]
 

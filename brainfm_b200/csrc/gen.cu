@@ -279,6 +279,56 @@ __global__ void k_gen_slab_xr_init(const bfm_gen_sample *__restrict__ S) {
     if (s.gmm_xr && s.x_count > 0 && threadIdx.x < 2) s.gmm_xr[threadIdx.x] = threadIdx.x ? 0 : 0x7f7fffff;
 }
 
+// Candidate form (same argument as k_gen_bbox_cand): between two kinks of the zoom weights the clamped source coordinate
+// is affine in the voxel index, so over the slab [c0, c1) x all j x all k its extrema sit on the candidate voxels with
+// i in (candidates of axis 0 inside the slab) + {c0, c1 - 1}: ~10^4 evaluations instead of the slab's voxels.  The
+// range only has to be a superset, so k_gen_slab_xr_finish widens it by the evaluation-error bound instead of
+// falling back to a scan.  SVF-integrated fields / missing candidate lists take the scan (k_gen_slab_xr).
+__global__ void __launch_bounds__(256) k_gen_slab_xr_cand(const bfm_gen_sample *__restrict__ S) {
+    __shared__ bfm_gen_sample sd;
+    __shared__ float red[8][2];
+    {
+        const bfm_gen_sample &s0 = S[blockIdx.y];
+        if (!s0.gmm_xr || s0.x_count <= 0 || s0.d.F_full || s0.d.ncand[0] <= 0) return;
+        const int total0 = (s0.d.ncand[0] + 2) * s0.d.ncand[1] * s0.d.ncand[2];
+        if ((int)(blockIdx.x * blockDim.x) >= total0) return;
+    }
+    stage_desc(&sd, S + blockIdx.y);
+    const bfm_deform &d = sd.d;
+    const int n0 = d.ncand[0] + 2, n1 = d.ncand[1], n2 = d.ncand[2];
+    const int total = n0 * n1 * n2;
+    const DefRegs g = load_def(d);
+    const int c0 = sd.x_begin, c1 = sd.x_begin + sd.x_count;
+    float lo = INFINITY, hi = 0.f;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < total) {
+        const int c = p % n2, b = (p / n2) % n1, a = p / (n1 * n2);
+        const int i = a < n0 - 2 ? __ldg(d.cand[0] + a) : (a == n0 - 2 ? c0 : c1 - 1);
+        if (i >= c0 && i < c1) {
+            const int j = __ldg(d.cand[1] + b), k = __ldg(d.cand[2] + c);
+            float x1 = __fsub_rn((float)i, g.ctr0), y1 = __fsub_rn((float)j, g.ctr1), z1 = __fsub_rn((float)k, g.ctr2);
+            if (d.fsmall) {
+                float f0, f1, f2;
+                field_direct(d, i, j, k, f0, f1, f2);
+                x1 = __fadd_rn(x1, f0); y1 = __fadd_rn(y1, f1); z1 = __fadd_rn(z1, f2);
+            }
+            float px, py, pz;
+            affine_clamp(g, x1, y1, z1, px, py, pz);
+            lo = hi = px;
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    lo = warp_min(lo); hi = warp_max(hi);
+    if (lane == 0) { red[warp][0] = lo; red[warp][1] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float v = red[0][threadIdx.x];
+        for (int w = 1; w < nw; ++w) v = threadIdx.x ? fmaxf(v, red[w][1]) : fminf(v, red[w][0]);
+        if (threadIdx.x) atomicMax(sd.gmm_xr + 1, __float_as_int(v));
+        else atomicMin(sd.gmm_xr, __float_as_int(v));
+    }
+}
+
 __global__ void __launch_bounds__(kRowWarps * 32) k_gen_slab_xr(const bfm_gen_sample *__restrict__ S, int fstride) {
     extern __shared__ float smem[];
     __shared__ bfm_gen_sample sd;
@@ -286,6 +336,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_slab_xr(const bfm_gen_sa
     {
         const bfm_gen_sample &s0 = S[blockIdx.y];
         if (!s0.gmm_xr || s0.x_count <= 0) return;
+        if (!s0.d.F_full && s0.d.ncand[0] > 0) return;          // k_gen_slab_xr_cand covers it
     }
     stage_desc(&sd, S + blockIdx.y);
     const bfm_deform &d = sd.d;
@@ -318,8 +369,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_gen_slab_xr(const bfm_gen_sa
 __global__ void k_gen_slab_xr_finish(const bfm_gen_sample *__restrict__ S) {
     const bfm_gen_sample &s = S[blockIdx.x];
     if (!s.gmm_xr || s.x_count <= 0) return;
-    if (threadIdx.x == 0) s.gmm_xr[0] = (int)floorf(__int_as_float(s.gmm_xr[0]));
-    else if (threadIdx.x == 1) s.gmm_xr[1] = 1 + (int)ceilf(__int_as_float(s.gmm_xr[1]));
+    // 2 * kBoxDelta: bound on |candidate extremum - true extremum| (bounding box); a superset is harmless
+    if (threadIdx.x == 0) s.gmm_xr[0] = max(0, (int)floorf(__int_as_float(s.gmm_xr[0]) - 2.f * kBoxDelta));
+    else if (threadIdx.x == 1) s.gmm_xr[1] = 1 + (int)ceilf(__int_as_float(s.gmm_xr[1]) + 2.f * kBoxDelta);
 }
 
 __global__ void k_gen_bbox_finish(const bfm_gen_sample *__restrict__ S) {
@@ -1772,13 +1824,23 @@ int bfm_gen_bbox(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void *
     k_gen_bbox_full<<<dim3(full_blocks, B), kRowWarps * 32, smem, s>>>(d, fstride);
     k_gen_bbox_finish<<<B, 32, 0, s>>>(d);
     g_launches.fetch_add(most > 0 ? 4 : 3);
-    bool slab_xr = false;
-    for (int b = 0; b < B; ++b) slab_xr |= (h[b].gmm_xr && h[b].x_count > 0);
-    if (slab_xr) {
+    bool slab_scan = false, slab_cand = false;
+    int64_t most_slab = 0;
+    for (int b = 0; b < B; ++b) {
+        if (!h[b].gmm_xr || h[b].x_count <= 0) continue;
+        if (!h[b].d.F_full && h[b].d.ncand[0] > 0) {
+            slab_cand = true;
+            most_slab = max(most_slab, (int64_t)(h[b].d.ncand[0] + 2) * h[b].d.ncand[1] * h[b].d.ncand[2]);
+        } else {
+            slab_scan = true;
+        }
+    }
+    if (slab_scan || slab_cand) {
         k_gen_slab_xr_init<<<B, 32, 0, s>>>(d);
-        k_gen_slab_xr<<<dim3(full_blocks, B), kRowWarps * 32, smem, s>>>(d, fstride);
+        if (slab_cand) k_gen_slab_xr_cand<<<dim3((unsigned)((most_slab + 255) / 256), B), 256, 0, s>>>(d);
+        if (slab_scan) k_gen_slab_xr<<<dim3(full_blocks, B), kRowWarps * 32, smem, s>>>(d, fstride);
         k_gen_slab_xr_finish<<<B, 32, 0, s>>>(d);
-        g_launches.fetch_add(3);
+        g_launches.fetch_add(2 + (slab_cand ? 1 : 0) + (slab_scan ? 1 : 0) - 1);
     }
     return check_launch("bfm_gen_bbox");
 }

@@ -234,6 +234,30 @@ __global__ void k_shift_scale_flip(const float *__restrict__ x, float *__restric
     }
 }
 
+// 128-bit form: blockIdx.y = plane, no 64-bit divisions (plane % 4 == 0, 16-byte aligned pointers)
+__global__ void __launch_bounds__(256) k_shift_scale_flip4(const float4 *__restrict__ x, float4 *__restrict__ out,
+                                                           int nx, int plane4, const float *sub_dev,
+                                                           const float *div_dev, float post, int flip) {
+    const float sub = sub_dev ? *sub_dev : 0.f;
+    float div = div_dev ? *div_dev : 1.f;
+    if (sub_dev && div_dev) div = __fsub_rn(div, sub);
+    for (int i = blockIdx.y; i < nx; i += gridDim.y) {
+        const float4 *src = x + (int64_t)i * plane4;
+        float4 *dst = out + (int64_t)(flip ? nx - 1 - i : i) * plane4;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < plane4; r += gridDim.x * blockDim.x) {
+            float4 v = __ldg(src + r);
+            float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (sub_dev) a[c] = __fsub_rn(a[c], sub);
+                if (div_dev) a[c] = __fdiv_rn(a[c], div);
+                if (post != 1.f) a[c] = __fmul_rn(a[c], post);
+            }
+            dst[r] = make_float4(a[0], a[1], a[2], a[3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // deformation-driven kernels (warp per output row)
 // ------------------------------------------------------------------------------------------------
@@ -661,6 +685,14 @@ int bfm_shift_scale_flip(const float *x, float *out, int nx, int64_t plane, cons
                          const float *div_dev, float post_scale, int flip, void *stream) {
     BFM_REQUIRE(x && out && nx > 0 && plane > 0, "bfm_shift_scale_flip: bad argument");
     BFM_REQUIRE(!(flip && x == out), "bfm_shift_scale_flip: in-place flip is not supported");
+    if ((plane & 3) == 0 && plane / 4 < (1LL << 30) && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+        const int plane4 = (int)(plane / 4);
+        const unsigned gx = (unsigned)min((int64_t)64, ((int64_t)plane4 + 255) / 256);
+        const unsigned gy = (unsigned)min(nx, 65535);
+        k_shift_scale_flip4<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (float4 *)out, nx, plane4,
+                                                                            sub_dev, div_dev, post_scale, flip);
+        return check_launch("bfm_shift_scale_flip");
+    }
     k_shift_scale_flip<<<grid_for((int64_t)nx * plane), 256, 0, (cudaStream_t)stream>>>(x, out, nx, plane, sub_dev,
                                                                                         div_dev, post_scale, flip);
     return check_launch("bfm_shift_scale_flip");

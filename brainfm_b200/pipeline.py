@@ -77,7 +77,9 @@ class DevicePipeline:
             from .plan import Arena
             ds.arena = Arena(ds.device, capacity=ds.arena.capacity, slots=want)
 
-    def submit(self, indices, timers=None):
+    def submit(self, indices=None, timers=None, call=None):
+        """Generate `indices` (ds.generate_batch) -- or run `call()` (anything that enqueues generator work on the
+        current stream with the dataset's scratch, e.g. `lambda: generate_slab(ds, idx)`) -- on the next lane."""
         ds = self.ds
         lane = self.lanes[self._k % len(self.lanes)]
         self._k += 1
@@ -87,7 +89,7 @@ class DevicePipeline:
         ds._ws = lane["ws"]
         try:
             with torch.cuda.stream(lane["stream"]):
-                items = ds.generate_batch(list(indices), timers=timers)
+                items = call() if call is not None else ds.generate_batch(list(indices), timers=timers)
                 ev = torch.cuda.Event()
                 ev.record(lane["stream"])
         finally:
