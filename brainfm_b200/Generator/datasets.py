@@ -484,7 +484,7 @@ class BaseGen(Dataset):
             self._ws['syn_stride'] = src_pad
         i_bf_ws = self._workspace('i_bf', B * N)
         tmp_ws = self._workspace('tmp', B * 2 * N)
-        low_ws = self._workspace('lowres', B * N)
+        low_ws = self._workspace('lowres', B * N + 16)     # + slack: bulk copies end on a 16-byte boundary
         raw_ws = self._workspace('aux_raw', n_aux * N) if n_aux else None
         p_syn, p_ibf, p_tmp, p_low = syn_ws.data_ptr(), i_bf_ws.data_ptr(), tmp_ws.data_ptr(), low_ws.data_ptr()
         keep = [out, bfl_all, res_all, aux_all]

@@ -244,7 +244,7 @@ class NativePlanner:
             ds._ws['syn_stride'] = src_pad
         p_ibf = ds._workspace('i_bf', total * N).data_ptr()
         p_tmp = ds._workspace('tmp', total * 2 * N).data_ptr()
-        p_low = ds._workspace('lowres', total * N).data_ptr()
+        p_low = ds._workspace('lowres', total * N + 16).data_ptr()     # + slack: bulk copies end on a 16-byte boundary
         p_raw = ds._workspace('aux_raw', n_aux_total * N).data_ptr() if n_aux_total else 0
         outs = (_lib.PlanOut * total)()
         o_np = np.frombuffer(outs, dtype=np.uint64).reshape(total, 9)

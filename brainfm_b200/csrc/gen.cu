@@ -1714,6 +1714,105 @@ __global__ void __launch_bounds__(160, UPS_MINB) k_gen_upsample(const bfm_gen_sa
     }
 }
 
+// Persistent form of k_gen_upsample with the low-res rows prefetched by the bulk-copy engine (opt-in, BFM_UPSAMPLE_BULK=1:
+// parity-green but slower than the plain kernel on B200, see bfm_gen_finish).  A block walks items
+// (x plane i, kUB output rows); while it computes item n from shared memory, one elected thread has already queued the
+// two contiguous row blocks of item n + 1 (low-res planes lo(i) and hi(i), rows y0 .. y1) as cp.async.bulk copies that
+// complete on an mbarrier -- the loads that left k_gen_upsample long-scoreboard bound (profiles/
+// r2_ncu_upsample_v2_summary.csv: 4.7 stalled warps per issue) are off the critical path and cost no registers.
+// Bulk copies need 16-byte aligned addresses and sizes: a row block starts at an arbitrary float of the low-res volume,
+// so the copy starts at the aligned float below it (offset kept per item) and ends at the aligned float above its end;
+// `lowres` must therefore be followed by >= 3 readable floats (bfm.h).  Arithmetic and results: identical to
+// k_gen_upsample.
+constexpr int kUB = 16;           // output rows per item
+struct UpsItem { int oa, ob, y0, ny, i, j0; float wl, wh; };
+
+__global__ void __launch_bounds__(160, 3) k_gen_upsample_bulk(const bfm_gen_sample *__restrict__ S, int cap) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ alignas(8) unsigned long long full[2];
+    __shared__ UpsItem item[2];
+    __shared__ float red[8];
+    __shared__ int ylo_s[kUB], yhi_s[kUB];
+    __shared__ float ywl_s[kUB], ywh_s[kUB];
+    const bfm_gen_sample &s = S[blockIdx.y];
+    if (is_identity_sample(s)) return;                  // k_gen_identity (resample stage) already wrote `out`
+    const int s0 = s.d.size[0], s1 = s.d.size[1], s2 = s.d.size[2];
+    const int ly = s.new_size[1], lz = s.new_size[2];
+    const int n_rg = (s1 + kUB - 1) / kUB, n_items = s0 * n_rg;
+    if ((int)blockIdx.x >= n_items) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    float *raw = smem, *t1 = smem + 4 * cap;            // raw[stage][plane lo / hi][cap], t1[cap]
+    const bfm_zoom_tab &u = s.utab;
+    const float *__restrict__ lowres = s.lowres;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    __syncthreads();
+    auto issue = [&](int t, int st) {                   // one thread: describe item t and queue its two copies
+        UpsItem it;
+        it.i = t / n_rg;
+        it.j0 = (t - it.i * n_rg) * kUB;
+        const int j1 = min(it.j0 + kUB, s1);
+        it.y0 = __ldg(u.lo[1] + it.j0);
+        it.ny = __ldg(u.hi[1] + j1 - 1) - it.y0 + 1;
+        const int lo = __ldg(u.lo[0] + it.i), hi = __ldg(u.hi[0] + it.i);
+        it.wl = __ldg(u.wl[0] + it.i); it.wh = __ldg(u.wh[0] + it.i);
+        const int64_t a = ((int64_t)lo * ly + it.y0) * lz, b = ((int64_t)hi * ly + it.y0) * lz;
+        it.oa = (int)(a & 3); it.ob = (int)(b & 3);
+        const int n = it.ny * lz;
+        const uint32_t ba = (uint32_t)((it.oa + n + 3) & ~3) * 4u, bb = (uint32_t)((it.ob + n + 3) & ~3) * 4u;
+        item[st] = it;
+        mbar_arrive_expect_tx(&full[st], ba + bb);
+        bulk_g2s(raw + (st * 2 + 0) * cap, lowres + (a - it.oa), ba, &full[st]);
+        bulk_g2s(raw + (st * 2 + 1) * cap, lowres + (b - it.ob), bb, &full[st]);
+    };
+    if (tid == 0) issue(blockIdx.x, 0);
+    __syncthreads();
+    float *__restrict__ outp = s.out;
+    const int flip = s.flip;
+    float hi = 0.f;
+    int n = 0;
+    for (int t = blockIdx.x; t < n_items; t += gridDim.x, ++n) {
+        const int st = n & 1;
+        if (tid == 0 && t + (int)gridDim.x < n_items) issue(t + gridDim.x, st ^ 1);   // raw[st ^ 1] was consumed before barrier A of item n - 1
+        const UpsItem it = item[st];
+        const int rows = min(kUB, s1 - it.j0);
+        if (tid < rows) {
+            const int j = it.j0 + tid;
+            ylo_s[tid] = (__ldg(u.lo[1] + j) - it.y0) * lz; yhi_s[tid] = (__ldg(u.hi[1] + j) - it.y0) * lz;
+            ywl_s[tid] = __ldg(u.wl[1] + j); ywh_s[tid] = __ldg(u.wh[1] + j);
+        }
+        mbar_wait(&full[st], (uint32_t)((n >> 1) & 1));
+        {   // first zoom pass (axis 0): shared -> shared
+            const float *ra = raw + (st * 2 + 0) * cap + it.oa, *rb = raw + (st * 2 + 1) * cap + it.ob;
+            const int cnt = it.ny * lz;
+            for (int q = tid; q < cnt; q += blockDim.x) t1[q] = lerp_rn(it.wl, ra[q], it.wh, rb[q]);
+        }
+        __syncthreads();                                                         // barrier A
+        const int plane_out = (flip ? s0 - 1 - it.i : it.i) * s1;
+        for (int k = tid; k < s2; k += blockDim.x) {
+            const int zlo = __ldg(u.lo[2] + k), zhi = __ldg(u.hi[2] + k);
+            const float zwl = __ldg(u.wl[2] + k), zwh = __ldg(u.wh[2] + k);
+            float *__restrict__ o = outp + (size_t)(plane_out + it.j0) * s2 + k;
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                const float *a = t1 + ylo_s[r], *b = t1 + yhi_s[r];
+                const float wl = ywl_s[r], wh = ywh_s[r];
+                const float vl = lerp_rn(wl, a[zlo], wh, b[zlo]), vh = lerp_rn(wl, a[zhi], wh, b[zhi]);
+                const float v = lerp_rn(zwl, vl, zwh, vh);
+                o[(size_t)r * s2] = v;
+                hi = fmaxf(hi, v);
+            }
+        }
+        __syncthreads();                                                         // barrier B: t1 / row tables reusable
+    }
+    hi = warp_max(hi);
+    if (lane == 0) red[warp] = hi;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) hi = fmaxf(hi, red[w]);
+        atomicMax((int *)s.maxval, __float_as_int(hi));               // values >= 0: bit order == float order
+    }
+}
+
 // I / max(I), optional high_res_residual (datasets.py:342-347) and the real-image targets'
 // `Idef -= min; Idef /= max; flip` (utils.py:326-329).  One thread = VEC consecutive z voxels of one x plane.
 template <int VEC>
@@ -2126,6 +2225,17 @@ int bfm_gen_finish(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void
     }
     const size_t smem = (size_t)ny * lz * sizeof(float);
     if (smem > 200 * 1024) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: low-res rows too long for shared memory");
+    // bulk form: 2 stages x 2 planes of raw rows + the first-pass buffer, each `cap` floats
+    int nyb = 1;
+    for (int b = 0; b < B; ++b)
+        nyb = max(nyb, min(h[b].new_size[1], (int)((int64_t)kUB * h[b].new_size[1] / h[b].d.size[1]) + 3));
+    const int cap = ((nyb * lz + 8) + 3) & ~3;
+    const size_t smem_bulk = (size_t)5 * cap * sizeof(float);
+    // opt-in: measured 21.6 instead of 18.4 us per sample for the finish stage (3 persistent blocks of 5 warps per SM,
+    // two barriers + one mbarrier wait per item, the first pass re-read from shared memory) -- the plain kernel's many
+    // small blocks hide the row loads better than the prefetch does
+    static const int bulk_env = getenv("BFM_UPSAMPLE_BULK") ? atoi(getenv("BFM_UPSAMPLE_BULK")) : 0;
+    const bool bulk = bulk_env != 0 && smem_bulk <= 72 * 1024;
     if (s0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: grid too large");
     if (smem > 40 * 1024)
         cudaFuncSetAttribute(k_gen_upsample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2139,7 +2249,18 @@ int bfm_gen_finish(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void
     if (G <= 0 || G > B) G = B;
     for (int b0 = 0; b0 < B; b0 += G) {
         const int n = B - b0 < G ? B - b0 : G;
-        k_gen_upsample<<<dim3((s1 + kUR - 1) / kUR, s0, n), threads, smem, st>>>(d + b0, lz, ny);
+        if (bulk) {
+            static size_t attr = 0;
+            if (smem_bulk > attr) {
+                cudaFuncSetAttribute(k_gen_upsample_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk);
+                attr = smem_bulk;
+            }
+            const int items = s0 * ((s1 + kUB - 1) / kUB);
+            const int per = min(items, max(8, (3 * 148 + n - 1) / n));          // ~3 persistent blocks per SM over the group
+            k_gen_upsample_bulk<<<dim3(per, n), threads, smem_bulk, st>>>(d + b0, cap);
+        } else {
+            k_gen_upsample<<<dim3((s1 + kUR - 1) / kUR, s0, n), threads, smem, st>>>(d + b0, lz, ny);
+        }
         rc = check_launch("bfm_gen_finish");
         if (rc) return rc;
         if (vec) {

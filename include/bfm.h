@@ -220,7 +220,7 @@ typedef struct bfm_gen_sample {
     float noise_std;
     const float *eps_noise; /* injected, low-res shaped, or NULL => Philox */
     float *tmp[2];          /* ping-pong scratch, each >= prod(size) floats */
-    float *lowres;          /* (new_size) */
+    float *lowres;          /* (new_size), 16-byte aligned, followed by >= 3 readable floats (bulk copies of row blocks) */
     int new_size[3];
     /* back to the training grid + normalise */
     bfm_zoom_tab utab;      /* tables of myzoom_torch(lowres, 1/factors), lengths size[d] */
