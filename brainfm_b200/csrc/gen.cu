@@ -1391,8 +1391,15 @@ __host__ __device__ __forceinline__ bool is_identity_sample(const bfm_gen_sample
 }
 
 // ---------------------------------------------------------------------------------------------- resample
+#ifndef BAND_UNROLL
+#define BAND_UNROLL 4
+#endif
 // One banded pass.  Axis 0/1: a thread owns VEC consecutive z outputs (128-bit loads when VEC == 4); the tap
 // weight is uniform across the warp.  Axis 2: a thread owns one output, taps are contiguous.
+#ifndef BAND_UNROLL
+#define BAND_UNROLL 4
+#endif
+constexpr int kBandUnroll = BAND_UNROLL;
 template <int VEC>
 __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restrict__ S, int pass, int zk_cap) {
     // persistent blocks: a few hundred per sample, each thread walks its outputs with carry arithmetic; only
@@ -1441,7 +1448,7 @@ __global__ void __launch_bounds__(256) k_gen_band(const bfm_gen_sample *__restri
 #pragma unroll
         for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
         const float *__restrict__ src = in + base;
-#pragma unroll 4
+#pragma unroll kBandUnroll
         for (int t = t0; t < t1; ++t) {
             const float w = __ldg(wr + t);
             if (VEC == 4) {
@@ -2234,7 +2241,8 @@ int bfm_gen_finish(const bfm_gen_sample *h, const bfm_gen_sample *d, int B, void
     // opt-in: measured 21.6 instead of 18.4 us per sample for the finish stage (3 persistent blocks of 5 warps per SM,
     // two barriers + one mbarrier wait per item, the first pass re-read from shared memory) -- the plain kernel's many
     // small blocks hide the row loads better than the prefetch does
-    static const int bulk_env = getenv("BFM_UPSAMPLE_BULK") ? atoi(getenv("BFM_UPSAMPLE_BULK")) : 0;
+    const char *be = getenv("BFM_UPSAMPLE_BULK");                 // read per call: tests toggle it
+    const int bulk_env = be ? atoi(be) : 0;
     const bool bulk = bulk_env != 0 && smem_bulk <= 72 * 1024;
     if (s0 > 65535 || B > 65535) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_gen_finish: grid too large");
     if (smem > 40 * 1024)

@@ -111,6 +111,21 @@ def test_svf_integration_is_bit_exact(name):
     assert [int(v) for v in grid[3:]] == orc.deform["lo"] + orc.deform["hi"]
 
 
+@pytest.mark.parametrize("name", ["g64_s0", "g64_s2", "g160_s0", "g64_s5_lowres", "g64_s3"])
+def test_bulk_prefetched_upsample_is_identical(name, monkeypatch):
+    """k_gen_upsample_bulk (persistent blocks, low-res row blocks prefetched with cp.async.bulk + mbarrier, unaligned
+    row blocks copied from the 16-byte boundary below; BFM_UPSAMPLE_BULK=1) against k_gen_upsample: bit-identical."""
+    _, orc = oracle_case(name)
+    monkeypatch.setenv("BFM_UPSAMPLE_BULK", "1")
+    got_b, _, _ = cuda_case(name, orc.log)
+    monkeypatch.setenv("BFM_UPSAMPLE_BULK", "0")
+    got_p, _, _ = cuda_case(name, orc.log)
+    a, b = mg.flatten(got_b), mg.flatten(got_p)
+    for k, v in a.items():
+        if isinstance(v, torch.Tensor):
+            assert torch.equal(v, b[k]), k
+
+
 @pytest.mark.parametrize("tile", ["1", "0", "tiny-bricks"])
 @pytest.mark.parametrize("name", ["g64_s0", "g64_s2", "g160_s0", "g64_s5_lowres"])
 def test_pair_mode_is_identical_to_the_unpaired_gather(name, tile, monkeypatch):
