@@ -4,6 +4,8 @@ resample_resolution (utils.py:74-94, 591-609), and a pinned-host/device arena th
 small arrays to the GPU in one asynchronous copy."""
 import ctypes as C
 
+import time
+
 import numpy as np
 import torch
 
@@ -125,12 +127,16 @@ class Arena:
         self.cur = -1
         self.used = 0
         self.committed = 0
+        self.wait_s = 0.0                # host time spent waiting for a free slot (= for the GPU), cumulative
 
     def begin(self):
         self.cur = (self.cur + 1) % len(self.slots)
         s = self.slots[self.cur]
         if s["event"] is not None:
-            s["event"].synchronize()
+            if not s["event"].query():                   # the GPU is behind: the host waits here (and only here)
+                t0 = time.perf_counter()
+                s["event"].synchronize()
+                self.wait_s += time.perf_counter() - t0
         self.used = 0
         self.committed = 0
         self.base = s["dev"].data_ptr()
