@@ -135,6 +135,7 @@ _PROTOS = {
     "bfm_interpol_pull_fast": (c_i, [c_p, C.POINTER(c_i64), c_p, c_i64, c_p, c_i, C.POINTER(c_i), c_i, C.POINTER(c_i),
                                      c_i, c_i, c_i, c_i64, c_p]),
     "bfm_compose_step": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, C.POINTER(c_i), c_i, c_p]),
+    "bfm_exp_velocity": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, C.POINTER(c_i), c_i, c_p, c_p]),
     "bfm_add_identity_grid": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "bfm_spline_filter": (c_i, [c_p, c_i, c_i64, c_i, c_i64, c_i, C.POINTER(C.c_double), c_i, c_p]),
     "bfm_perlin3d": (c_i, [c_p, C.POINTER(c_i), C.POINTER(c_i), c_p, c_p]),

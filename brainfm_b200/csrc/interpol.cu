@@ -407,6 +407,10 @@ __global__ void __launch_bounds__(256) k_pull_fast(const float *__restrict__ inp
 // disp, out: (B, X, Y, Z, 3) float32.  Same operations in the same order as k_add_identity followed by
 // k_pull_fast<1, 3> and the final add -- identical bits -- but the grid and the pulled field never exist in HBM:
 // 24 bytes per voxel and step instead of ~100.
+// CS = floats per voxel record: 3 (the caller's layout) or 4 ({d0, d1, d2, 0}: one 128-bit load per trilinear tap
+// instead of three 32-bit loads whose 12-byte stride spreads a warp's request over 3-4 cache lines -- 93 -> ~40 L1
+// wavefronts per 32 voxels; bfm_exp_velocity keeps the field in this layout between its steps).
+template <int CS>
 __global__ void __launch_bounds__(256) k_compose_linear3(const float *__restrict__ disp, float *__restrict__ out,
                                                          const PullFastArgs a) {
     const int64_t total = (int64_t)a.B * a.P;
@@ -420,13 +424,19 @@ __global__ void __launch_bounds__(256) k_compose_linear3(const float *__restrict
     const int y = (int)(r % Y);
     const int x = (int)(r / Y);
     (void)X;
-    const float *dp = disp + q * 3;
-    const float d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    float d0, d1, d2;
+    if (CS == 4) {
+        const float4 v = __ldg((const float4 *)disp + q);
+        d0 = v.x; d1 = v.y; d2 = v.z;
+    } else {
+        const float *dp = disp + q * 3;
+        d0 = __ldg(dp); d1 = __ldg(dp + 1); d2 = __ldg(dp + 2);
+    }
     const float g[3] = {d0 + (float)x, d1 + (float)y, d2 + (float)z};
     int off[3][2];
     float w[3][2];
     bool inb = true;
-    const int strides[3] = {Y * Z * 3, Z * 3, 3};
+    const int strides[3] = {Y * Z * CS, Z * CS, CS};
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const float xx = g[d];
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(256) k_compose_linear3(const float *__restrict
         }
     }
     const float m = inb ? 1.f : 0.f;
-    const float *src = disp + (int64_t)b * a.P * 3;
+    const float *src = disp + (int64_t)b * a.P * CS;
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int kx = 0; kx < 2; ++kx)
@@ -458,12 +468,36 @@ __global__ void __launch_bounds__(256) k_compose_linear3(const float *__restrict
             for (int kz = 0; kz < 2; ++kz) {
                 const float ww = wxy * w[2][kz];
                 const float *t = src + oxy + off[2][kz];
-                acc[0] = fmaf(__ldg(t), ww, acc[0]); acc[1] = fmaf(__ldg(t + 1), ww, acc[1]);
-                acc[2] = fmaf(__ldg(t + 2), ww, acc[2]);
+                if (CS == 4) {
+                    const float4 v = __ldg((const float4 *)t);
+                    acc[0] = fmaf(v.x, ww, acc[0]); acc[1] = fmaf(v.y, ww, acc[1]); acc[2] = fmaf(v.z, ww, acc[2]);
+                } else {
+                    acc[0] = fmaf(__ldg(t), ww, acc[0]); acc[1] = fmaf(__ldg(t + 1), ww, acc[1]);
+                    acc[2] = fmaf(__ldg(t + 2), ww, acc[2]);
+                }
             }
         }
-    float *o = out + q * 3;
-    o[0] = d0 + acc[0] * m; o[1] = d1 + acc[1] * m; o[2] = d2 + acc[2] * m;
+    if (CS == 4) {
+        ((float4 *)out)[q] = make_float4(d0 + acc[0] * m, d1 + acc[1] * m, d2 + acc[2] * m, 0.f);
+    } else {
+        float *o = out + q * 3;
+        o[0] = d0 + acc[0] * m; o[1] = d1 + acc[1] * m; o[2] = d2 + acc[2] * m;
+    }
+}
+
+// (n, 3) * scale -> (n, 4) records {x, y, z, 0} and back
+__global__ void __launch_bounds__(256) k_pack34(const float *__restrict__ src, float4 *__restrict__ dst, int64_t n, float scale) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float *p = src + q * 3;
+    dst[q] = make_float4(__ldg(p) * scale, __ldg(p + 1) * scale, __ldg(p + 2) * scale, 0.f);
+}
+__global__ void __launch_bounds__(256) k_unpack43(const float4 *__restrict__ src, float *__restrict__ dst, int64_t n) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float4 v = __ldg(src + q);
+    float *p = dst + q * 3;
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
 
 // out = disp + identity grid, (B, X, Y, Z, 3) float32 (add_identity_grid, utils/interpol/api.py:480-521)
@@ -783,8 +817,40 @@ int bfm_compose_step(const float *disp, float *out, int B, int X, int Y, int Z, 
     a.sB = a.P * 3; a.sC = 1; a.sX = Y * Z * 3; a.sY = Z * 3; a.sZ = 3; a.gB = 0; a.out_chlast = 1;
     const int64_t nblocks = ((int64_t)B * a.P + 255) / 256;
     if (nblocks >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_compose_step: too many points");
-    k_compose_linear3<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(disp, out, a);
+    k_compose_linear3<3><<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(disp, out, a);
     return check_launch("bfm_compose_step");
+}
+
+int bfm_exp_velocity(const float *svf, float *out, int B, int X, int Y, int Z, int steps, const int *bound,
+                     int extrapolate, float *scratch, void *stream) {
+    BFM_REQUIRE(svf && out && bound && scratch && B > 0 && X > 0 && Y > 0 && Z > 0 && steps >= 0 && steps < 31,
+                "bfm_exp_velocity: bad argument");
+    BFM_REQUIRE(extrapolate >= 0 && extrapolate <= 2, "bfm_exp_velocity: extrapolate must be 0, 1 or 2");
+    BFM_REQUIRE(((uintptr_t)scratch % 16) == 0, "bfm_exp_velocity: scratch must be 16-byte aligned");
+    PullFastArgs a;
+    a.ishape[0] = X; a.ishape[1] = Y; a.ishape[2] = Z;
+    for (int d = 0; d < 3; ++d) {
+        if (bound[d] < 0 || bound[d] > 6) return fail(BFM_E_INVALID, "%s", "bfm_exp_velocity: bound must be 0..6");
+        a.bound[d] = bound[d];
+    }
+    a.extrapolate = extrapolate; a.B = B; a.C = 3; a.P = (int64_t)X * Y * Z;
+    if (a.P * 4 >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_exp_velocity: field too large for 32-bit offsets");
+    a.sB = a.P * 4; a.sC = 1; a.sX = Y * Z * 4; a.sY = Z * 4; a.sZ = 4; a.gB = 0; a.out_chlast = 1;
+    const int64_t n = (int64_t)B * a.P;
+    const int64_t nblocks = (n + 255) / 256;
+    if (nblocks >= (1LL << 31)) return fail(BFM_E_UNSUPPORTED, "%s", "bfm_exp_velocity: too many points");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *cur = scratch, *nxt = scratch + n * 4;
+    float scale = 1.f;
+    for (int q = 0; q < steps; ++q) scale *= 0.5f;                      // svf / 2**steps, exact
+    k_pack34<<<(unsigned)nblocks, 256, 0, st>>>(svf, (float4 *)cur, n, scale);
+    for (int q = 0; q < steps; ++q) {
+        k_compose_linear3<4><<<(unsigned)nblocks, 256, 0, st>>>(cur, nxt, a);
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    k_unpack43<<<(unsigned)nblocks, 256, 0, st>>>((const float4 *)cur, out, n);
+    g_launches.fetch_add(steps + 1);
+    return check_launch("bfm_exp_velocity");
 }
 
 int bfm_add_identity_grid(const float *disp, float *out, int B, int X, int Y, int Z, void *stream) {

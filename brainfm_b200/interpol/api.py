@@ -524,6 +524,18 @@ def compose_step(disp, bound='dct2', extrapolate=True):
 
 def exp_velocity(svf, steps=7, bound='dct2', extrapolate=True):
     """Scaling and squaring: the displacement of exp(svf), `disp = svf / 2**steps`, then `steps` compose_step calls."""
+    if (svf.is_cuda and svf.dtype == torch.float32 and svf.shape[-1] == 3 and svf.dim() >= 4 and svf.is_contiguous()
+            and not _wants_grad(svf) and svf.numel() > 0 and 0 <= int(steps) < 31
+            and int(math.prod(svf.shape[-4:-1])) * 4 < 2 ** 31):
+        # one library call: the field stays in {x, y, z, 0} records between the steps (bfm_exp_velocity)
+        X, Y, Z = svf.shape[-4:-1]
+        Bn = int(math.prod(svf.shape[:-4]))
+        out = torch.empty_like(svf)
+        scratch = torch.empty(2 * Bn * X * Y * Z * 4, dtype=torch.float32, device=svf.device)
+        _lib.check(_lib.lib().bfm_exp_velocity(svf.data_ptr(), out.data_ptr(), Bn, X, Y, Z, int(steps),
+                                               (C.c_int * 3)(*_bounds(bound, 3)), _extrap(extrapolate),
+                                               scratch.data_ptr(), _stream()))
+        return out
     disp = svf / 2 ** steps
     for _ in range(steps):
         disp = compose_step(disp, bound=bound, extrapolate=extrapolate)

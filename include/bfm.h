@@ -430,6 +430,12 @@ int bfm_add_identity_grid(const float *disp, float *out, int B, int X, int Y, in
  * or the pulled field. */
 int bfm_compose_step(const float *disp, float *out, int B, int X, int Y, int Z, const int *bound, int extrapolate,
                      void *stream);
+/* Scaling and squaring: out = displacement of exp(svf): disp = svf / 2**steps, then `steps` bfm_compose_step
+ * compositions, with the field kept as 16-byte {x, y, z, 0} records between the steps (one 128-bit load per tap).
+ * svf, out: (B, X, Y, Z, 3) float32; scratch: 2 * B*X*Y*Z*4 floats, 16-byte aligned.  Bit-identical to the step-wise
+ * form.                                                       BASELINE configs[2]; Generator/datasets.py:214-223 */
+int bfm_exp_velocity(const float *svf, float *out, int B, int X, int Y, int Z, int steps, const int *bound,
+                     int extrapolate, float *scratch, void *stream);
 
 /* spline_coeff: in-place recursive prefilter along one axis of a tensor viewed as (outer, n, inner)
  * utils/interpol/coeff.py:35-316.  bound: 0 zero (=dct1), 1 replicate (=dct2), 2 dct1, 3 dct2, 6 dft. */

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c 'import torch' >/dev/null 2>&1
+timeout 900 python -m pytest tests/test_interpol_gpu.py tests/test_configs_gpu.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3 | cut -c1-250
+timeout 600 python - <<'PY'
+import sys, json
+sys.path.insert(0, 'tools')
+import config_bench as cb
+r = cb.interpol_cfg(256)
+print(json.dumps(r))
+PY
+for i in 1 2; do timeout 300 python bench.py --steps 30 --warmup 5 --quick 2>/dev/null | cut -c1-150; done
