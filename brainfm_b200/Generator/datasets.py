@@ -275,6 +275,14 @@ class BaseGen(Dataset):
     def _integrate_svf(self, F):
         n = self.synth_args.n_steps_svf_integration
         L = _lib.lib()
+        F = F.contiguous()
+        if F.dtype == torch.float32 and F.is_cuda:
+            # one library call; the field stays in 16-byte records between the steps (bfm_svf_integrate)
+            out = torch.empty_like(F)
+            scratch = torch.empty(2 * 4 * int(np.prod(self.size)), dtype=torch.float32, device=F.device)
+            _lib.check(L.bfm_svf_integrate(F.data_ptr(), out.data_ptr(), *[int(v) for v in self.size], int(n),
+                                           float(1.0 / (2.0 ** n)), scratch.data_ptr(), _stream()))
+            return out
         cur = (F * (1.0 / (2.0 ** n))).contiguous()
         nxt = torch.empty_like(cur)
         for _ in range(n):

@@ -119,6 +119,7 @@ _PROTOS = {
     "bfm_warp_volume": (c_i, [C.POINTER(Deform), c_p, c_p, c_f, c_f, c_i, c_p, c_p, c_p, c_p]),
     "bfm_label_warp_onehot": (c_i, [C.POINTER(Deform), c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
     "bfm_svf_step": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "bfm_svf_integrate": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     "bfm_gen_plan": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_bbox": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_gen_gmm": (c_i, [c_p, c_p, c_i, c_p]),

@@ -23,6 +23,9 @@ __device__ __forceinline__ int64_t floordiv(int64_t a, int64_t n) {
 
 // Bound.index (bounds.py:30-60)
 __device__ __forceinline__ int bound_index(int type, int64_t i, int n) {
+    // every bound maps an in-range index to itself: the 64-bit modulo arithmetic below (~100 instructions per call,
+    // six calls per voxel of a linear pull) only runs for the taps that actually leave the volume
+    if ((uint64_t)i < (uint64_t)n) return (int)i;
     switch (type) {
         case 0: case 1: return (int)(i < 0 ? 0 : (i > n - 1 ? n - 1 : i));
         case 3: case 5: {
@@ -63,6 +66,7 @@ __device__ __forceinline__ int bound_sign(int type, int64_t i, int n) {
             return pymod(i, 2) > 0 ? -x : x;
         }
         case 5: {
+            if ((uint64_t)i < (uint64_t)n) return 1;
             i = i < 0 ? n - 1 - i : i;
             i = floordiv(i, n);
             return pymod(i, 2) > 0 ? -1 : 1;

@@ -168,6 +168,11 @@ int bfm_label_warp_onehot(const bfm_deform *d_host, const int *bbox_dev, const i
 /* random_nonlinear_transform SVF integration step                     Generator/datasets.py:214-223
  * out = Fin + trilerp(Fin, id + Fin)  for a (sx,sy,sz,3) field. */
 int bfm_svf_step(const float *Fin, float *Fout, int sx, int sy, int sz, void *stream);
+/* The whole integration: out = F * scale, then n_steps bfm_svf_step compositions, with the field kept as 16-byte
+ * {f0, f1, f2, 0} records between the steps (one 128-bit load per tap; identical arithmetic).  F, out: (sx,sy,sz,3)
+ * float32; scratch: 2 * sx*sy*sz*4 floats, 16-byte aligned.              Generator/datasets.py:214-223 */
+int bfm_svf_integrate(const float *F, float *out, int sx, int sy, int sz, int n_steps, float scale, float *scratch,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused batched synthesis chain:  BaseGen.generate_sample + augment_sample with the stock steps
