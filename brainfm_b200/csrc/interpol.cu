@@ -637,39 +637,84 @@ __global__ void __launch_bounds__(128) k_spline_filter_tile(float *__restrict__ 
     for (int e = tid; e < a.npoles * (2 * n + 2); e += blockDim.x) {
         const int k = e / (2 * n + 2), r = e - k * (2 * n + 2);
         const double pole = a.poles[k];
+        // |pole|^j rounds to (+-)0 in float32 beyond j = cut: skip the float64 pow there (same value, the sign of a
+        // zero does not reach the sums)
+        const int cut = (int)ceil(-151.0 / log2(fabs(pole)));
+        auto powf_ = [&](int j) { return j > cut ? 0.f : (float)pow(pole, (double)j); };
         float v = 0.f;
         if (r < n) {
-            if (a.bound == 1 || a.bound == 3) v = (float)pow(pole, (double)r) + (float)pow(pole, (double)(2 * n - 1 - r));
+            if (a.bound == 1 || a.bound == 3) v = powf_(r) + powf_(2 * n - 1 - r);
         } else if (a.bound == 6) {
-            v = (float)pow(pole, (double)(r - n));
+            v = powf_(r - n);
         }
         wt[e] = v;
     }
+    // The element loops keep 8 independent global loads in flight per thread (one load per iteration left the stage
+    // long-scoreboard bound: 8.8-12 stalled warps per issue, 0.8 TB/s; profiles/r2_ncu_prefilter_summary.csv) and index
+    // with shifts (L == 32) / carry arithmetic instead of divisions.
+    constexpr int kU = 8;
     if (CONTIG) {                      // inner == 1: lines [q0, q0+L) are one contiguous run of L*n floats
         const int64_t q0 = (int64_t)blockIdx.x * L;
         const int nl = (int)min((int64_t)L, a.outer - q0);
         float *base = data + q0 * n;
         const int total = nl * n;
-        for (int e = tid; e < total; e += blockDim.x) tile[(e / n) * pitch + (e % n)] = base[e];
+        const int dr = blockDim.x / n, dc = blockDim.x - dr * n;
+        {
+            int row = tid / n, col = tid - row * n;
+            for (int e0 = tid; e0 < total; e0 += kU * blockDim.x) {
+                float v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    v[u] = e < total ? __ldg(base + e) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (e0 + u * (int)blockDim.x < total) tile[row * pitch + col] = v[u];
+                    row += dr; col += dc;
+                    if (col >= n) { col -= n; ++row; }
+                }
+            }
+        }
         __syncthreads();
         if (tid < nl) filter_line<float>(tile + tid * pitch, 1, a, wt);
         __syncthreads();
-        for (int e = tid; e < total; e += blockDim.x) base[e] = tile[(e / n) * pitch + (e % n)];
+        {
+            int row = tid / n, col = tid - row * n;
+            for (int e = tid; e < total; e += blockDim.x) {
+                base[e] = tile[row * pitch + col];
+                row += dr; col += dc;
+                if (col >= n) { col -= n; ++row; }
+            }
+        }
     } else {                           // lines (o, in0 .. in0+L): element i of line t at data[o*n*inner + i*inner + in0 + t]
         const int64_t per_o = (a.inner + L - 1) / L;
         const int64_t o = blockIdx.x / per_o, in0 = (blockIdx.x % per_o) * L;
         const int nl = (int)min((int64_t)L, a.inner - in0);
         float *base = data + o * (int64_t)n * a.inner + in0;
-        for (int e = tid; e < n * L; e += blockDim.x) {
-            const int i = e / L, t = e - i * L;
-            if (t < nl) tile[e] = base[(int64_t)i * a.inner + t];
+        const int t = tid & 31, i0 = tid >> 5, di = blockDim.x >> 5;        // L == 32 (host): one row per warp and step
+        if (t < nl) {
+            const float *src = base + t;
+            for (int i = i0; i < n; i += kU * di) {
+                float v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int ii = i + u * di;
+                    v[u] = ii < n ? __ldg(src + (int64_t)ii * a.inner) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int ii = i + u * di;
+                    if (ii < n) tile[ii * 32 + t] = v[u];
+                }
+            }
         }
         __syncthreads();
         if (tid < nl) filter_line<float>(tile + tid, L, a, wt);
         __syncthreads();
-        for (int e = tid; e < n * L; e += blockDim.x) {
-            const int i = e / L, t = e - i * L;
-            if (t < nl) base[(int64_t)i * a.inner + t] = tile[e];
+        if (t < nl) {
+            float *dst = base + t;
+            for (int i = i0; i < n; i += di) dst[(int64_t)i * a.inner] = tile[i * 32 + t];
         }
     }
 }
