@@ -154,6 +154,7 @@ _PROTOS = {
     "bfm_rk_error_fused": (c_i, [C.POINTER(c_p), C.POINTER(c_f), c_i, c_p, c_p, c_i, c_i64, C.c_double, C.c_double, c_p,
                                  c_p, c_p]),
     "bfm_rk_error_sum": (c_i, [c_p, c_p, c_p, c_i, c_i64, C.c_double, C.c_double, c_p, c_p]),
+    "bfm_dopri5_interp": (c_i, [c_p, c_p, c_p, c_p, c_p, C.c_double, C.c_double, c_i64, c_p, c_p]),
 }
 
 

@@ -266,42 +266,46 @@ __global__ void __launch_bounds__(256) k_rk_error4(const RkArgs a, const T *__re
     }
 }
 
-// advection right-hand side, one block per (x plane, chunk of the plane): 32-bit index arithmetic
+// advection right-hand side.  Block = 64 (k) x 4 (j) voxels of one x plane: no index division, one 32-bit centre
+// offset per voxel and six neighbour offsets that are +-1 / +-n2 / +-plane except where the Neumann clamp or the
+// volume's edge folds them (the first version spent 347 warp instructions per 32 voxels, mostly 64-bit address
+// arithmetic, and ran at 85 % instruction issue: profiles/r2_ncu_advect_summary.csv).  All ten loads are issued
+// before anything depends on them; the six neighbours are other threads' centres (L1 / L2 hits).
 template <typename T>
 __global__ void __launch_bounds__(256) k_advect_rhs_p(const T *__restrict__ C, const float *__restrict__ Vx,
                                                       const float *__restrict__ Vy, const float *__restrict__ Vz, int n0,
                                                       int n1, int n2, int neumann, float sp0, float sp1, float sp2,
                                                       float *__restrict__ out) {
-    const int i = blockIdx.y;
+    const int i = blockIdx.z;
+    const int j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.x * 64 + threadIdx.x;
+    if (j >= n1 || k >= n2) return;
     const int plane = n1 * n2;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= plane) return;
-    const int j = q / n2, k = q - j * n2;
     const int lo = neumann ? 1 : 0;
     const int hi0 = neumann ? n0 - 2 : n0 - 1, hi1 = neumann ? n1 - 2 : n1 - 1, hi2 = neumann ? n2 - 2 : n2 - 1;
-    auto cl = [&](int v, int hi) { return neumann ? min(max(v, lo), hi) : v; };
-    // clamped coordinates of the centre and of the six neighbours (set_BC: replicate-padded interior)
-    const int ic = cl(i, hi0), jc = cl(j, hi1), kc = cl(k, hi2);
-    const int64_t s0 = plane;
-    auto at = [&](int a, int b, int c) -> T { return __ldg(C + (int64_t)a * s0 + b * n2 + c); };
-    const T c0 = at(ic, jc, kc);
-    const int64_t p = (int64_t)i * s0 + q;
+    // clamped coordinates of the centre and of the six neighbours (set_BC: replicate-padded interior); a neighbour
+    // index outside the volume is only ever formed for the side that is not selected below
+    const int ic = min(max(i, lo), hi0), jc = min(max(j, lo), hi1), kc = min(max(k, lo), hi2);
+    const int im = min(max(max(i - 1, 0), lo), hi0), ip = min(max(min(i + 1, n0 - 1), lo), hi0);
+    const int jm = min(max(max(j - 1, 0), lo), hi1), jp = min(max(min(j + 1, n1 - 1), lo), hi1);
+    const int km = min(max(max(k - 1, 0), lo), hi2), kp = min(max(min(k + 1, n2 - 1), lo), hi2);
+    const int ctr = (ic * n1 + jc) * n2 + kc;                     // < 2^31 (checked on the host)
+    const T *__restrict__ Cc = C + ctr;
+    const T c0 = __ldg(Cc);
+    const T xm = __ldg(Cc + (im - ic) * plane), xp = __ldg(Cc + (ip - ic) * plane);
+    const T ym = __ldg(Cc + (jm - jc) * n2), yp = __ldg(Cc + (jp - jc) * n2);
+    const T zm = __ldg(Cc + (km - kc)), zp = __ldg(Cc + (kp - kc));
+    const int p = (i * n1 + j) * n2 + k;
     const float vx = __ldg(Vx + p), vy = __ldg(Vy + p), vz = __ldg(Vz + p);
     // forward difference at the last index falls back to the backward one and vice versa (gradient_f / gradient_b)
-    float dx, dy, dz;
-    {
-        const bool fwd = (vx > 0.f) ? (i == 0) : (i != n0 - 1);
-        dx = fwd ? (float)(at(cl(i + 1, hi0), jc, kc) - c0) : (float)(c0 - at(cl(i - 1, hi0), jc, kc));
-    }
-    {
-        const bool fwd = (vy > 0.f) ? (j == 0) : (j != n1 - 1);
-        dy = fwd ? (float)(at(ic, cl(j + 1, hi1), kc) - c0) : (float)(c0 - at(ic, cl(j - 1, hi1), kc));
-    }
-    {
-        const bool fwd = (vz > 0.f) ? (k == 0) : (k != n2 - 1);
-        dz = fwd ? (float)(at(ic, jc, cl(k + 1, hi2)) - c0) : (float)(c0 - at(ic, jc, cl(k - 1, hi2)));
-    }
-    const float cx = __fdiv_rn(dx, sp0), cy = __fdiv_rn(dy, sp1), cz = __fdiv_rn(dz, sp2);
+    const bool fx = (vx > 0.f) ? (i == 0) : (i != n0 - 1);
+    const bool fy = (vy > 0.f) ? (j == 0) : (j != n1 - 1);
+    const bool fz = (vz > 0.f) ? (k == 0) : (k != n2 - 1);
+    const float dx = fx ? (float)(xp - c0) : (float)(c0 - xm);
+    const float dy = fy ? (float)(yp - c0) : (float)(c0 - ym);
+    const float dz = fz ? (float)(zp - c0) : (float)(c0 - zm);
+    // x / 1 == x exactly: skip the IEEE division for unit spacing (uniform branch)
+    const float cx = sp0 == 1.f ? dx : __fdiv_rn(dx, sp0), cy = sp1 == 1.f ? dy : __fdiv_rn(dy, sp1),
+                cz = sp2 == 1.f ? dz : __fdiv_rn(dz, sp2);
     out[p] = -__fadd_rn(__fadd_rn(__fmul_rn(vx, cx), __fmul_rn(vy, cy)), __fmul_rn(vz, cz));
 }
 
@@ -440,10 +444,11 @@ int bfm_advect_rhs(const void *C, int is_double, const float *Vx, const float *V
     const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t plane = (int64_t)shape[1] * shape[2];
-    if (plane < (1LL << 30) && shape[0] <= 65535) {
-        const dim3 grid((unsigned)((plane + 255) / 256), (unsigned)shape[0]);
-        if (is_double) k_advect_rhs_p<double><<<grid, 256, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
-        else k_advect_rhs_p<float><<<grid, 256, 0, s>>>((const float *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
+    if (n < (1LL << 31) && shape[0] <= 65535 && (shape[1] + 3) / 4 <= 65535) {
+        const dim3 grid((unsigned)((shape[2] + 63) / 64), (unsigned)((shape[1] + 3) / 4), (unsigned)shape[0]);
+        const dim3 block(64, 4);
+        if (is_double) k_advect_rhs_p<double><<<grid, block, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
+        else k_advect_rhs_p<float><<<grid, block, 0, s>>>((const float *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
         return check_launch("bfm_advect_rhs");
     }
     if (is_double) k_advect_rhs<double><<<g1d(n), 256, 0, s>>>((const double *)C, Vx, Vy, Vz, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], out);
@@ -463,6 +468,53 @@ int bfm_diffuse_rhs(const void *C, int is_double, const float *D, float D_const,
     if (is_double) k_diffuse_rhs<double><<<grid, 256, 0, s>>>((const double *)C, D, D_const, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], accumulate, out);
     else k_diffuse_rhs<float><<<grid, 256, 0, s>>>((const float *)C, D, D_const, shape[0], shape[1], shape[2], neumann, spacing[0], spacing[1], spacing[2], accumulate, out);
     return check_launch("bfm_diffuse_rhs");
+}
+
+}  // extern "C" (reopened below)
+
+namespace bfm {
+// Dense output of dopri5 (interp.py:5-65): the quartic through y0, y1, y_mid, f0, f1 evaluated at x in [0, 1], with
+// the reference's tensor expressions and dtype promotions for a float64 state and float32 stages:
+//   a = (-2dt)*f0 + (2dt)*f1 + -8*y0 + -8*y1 + 16*y_mid      ((f32 + f32) promoted to f64 by the first f64 term)
+//   b = (5dt)*f0 + (-3dt)*f1 + 18*y0 + 14*y1 + -32*y_mid
+//   c = (-4dt)*f0 + dt*f1 + -11*y0 + -5*y1 + 16*y_mid
+//   d = dt*f0 (f32),  e = y0
+//   out = a*x^4 + b*x^3 + c*x^2 + d*x + e*1                   (d*x in f32: a 0-dim f64 factor does not promote)
+// fifteen element-wise passes over 7-10 tensors in the reference's formulation, one here.
+__global__ void __launch_bounds__(256) k_dopri5_interp(const double *__restrict__ y0, const double *__restrict__ y1,
+                                                       const double *__restrict__ ym, const float *__restrict__ f0,
+                                                       const float *__restrict__ f1, double dt, double x, int64_t n,
+                                                       double *__restrict__ out) {
+    const float m2 = (float)(-2 * dt), p2 = (float)(2 * dt), p5 = (float)(5 * dt), m3 = (float)(-3 * dt),
+                m4 = (float)(-4 * dt), p1 = (float)dt, xf = (float)x;
+    const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const double a0 = y0[q], a1 = y1[q], am = ym[q];
+        const float g0 = f0[q], g1 = f1[q];
+        const double a = __dadd_rn(__dadd_rn(__dadd_rn((double)__fadd_rn(__fmul_rn(m2, g0), __fmul_rn(p2, g1)),
+                                                       __dmul_rn(-8.0, a0)), __dmul_rn(-8.0, a1)), __dmul_rn(16.0, am));
+        const double b = __dadd_rn(__dadd_rn(__dadd_rn((double)__fadd_rn(__fmul_rn(p5, g0), __fmul_rn(m3, g1)),
+                                                       __dmul_rn(18.0, a0)), __dmul_rn(14.0, a1)), __dmul_rn(-32.0, am));
+        const double c = __dadd_rn(__dadd_rn(__dadd_rn((double)__fadd_rn(__fmul_rn(m4, g0), __fmul_rn(p1, g1)),
+                                                       __dmul_rn(-11.0, a0)), __dmul_rn(-5.0, a1)), __dmul_rn(16.0, am));
+        const float d = __fmul_rn(p1, g0);
+        double r = __dadd_rn(__dmul_rn(a, x4), __dmul_rn(b, x3));
+        r = __dadd_rn(r, __dmul_rn(c, x2));
+        r = __dadd_rn(r, (double)__fmul_rn(d, xf));
+        out[q] = __dadd_rn(r, __dmul_rn(a0, 1.0));
+    }
+}
+}  // namespace bfm
+
+extern "C" {
+
+int bfm_dopri5_interp(const double *y0, const double *y1, const double *y_mid, const float *f0, const float *f1,
+                      double dt, double x, int64_t n, double *out, void *stream) {
+    BFM_REQUIRE(y0 && y1 && y_mid && f0 && f1 && out && n > 0, "bfm_dopri5_interp: bad argument");
+    const int64_t g = (n + 255) / 256;
+    k_dopri5_interp<<<(unsigned)(g < 148 * 32 ? g : 148 * 32), 256, 0, (cudaStream_t)stream>>>(y0, y1, y_mid, f0, f1, dt, x,
+                                                                                              n, out);
+    return check_launch("bfm_dopri5_interp");
 }
 
 int bfm_rk_combine(const void *y0, int is_double, const float *const *k_host, const float *coef_host, int n_terms,

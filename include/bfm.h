@@ -489,6 +489,12 @@ int bfm_rk_error_fused(const float *const *k_host, const float *coef_host, int n
                        int is_double, int64_t n, double rtol, double atol, float *err_scratch, double *result_dev,
                        void *stream);
 
+/* Dense output of dopri5 for a float64 state with float32 stages: the quartic through y0, y1, y_mid, f0, f1 at
+ * x = (t - t0) / (t1 - t0), evaluated with the reference's tensor expressions and dtype promotions in ONE pass.
+ * ShapeID/DiffEqs/interp.py:5-65 */
+int bfm_dopri5_interp(const double *y0, const double *y1, const double *y_mid, const float *f0, const float *f1,
+                      double dt, double x, int64_t n, double *out, void *stream);
+
 /* ---- pathology branch of generate_sample / augment_sample (op-level) ------------------------------------------- */
 /* SYN = clamp(mus[round(G)] + sigmas[round(G)] * eps, 0) over the crop bbox = {x1,y1,z1,x2,y2,z2} of the label volume
  * (label 77 -> 2); eps: (crop) float32 draws or NULL (counter-based field keyed on the absolute source voxel).

@@ -59,6 +59,14 @@ def main(n=192):
     torch.cuda.synchronize()
     print("dopri5: %.2f ms, %d steps, %d rhs" % (1e3 * (time.perf_counter() - t0), len(solver.trace), solver.n_rhs))
     pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        odeint_adjoint(pde, y, t, dt, method='dopri5')
+        torch.cuda.synchronize()
+    ev = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    print("GPU busy %.2f ms" % (sum(e.device_time_total for e in ev) * 1e-3))
+    for e in ev[:16]:
+        print("%9.1f us x%-4d %s" % (e.device_time_total, e.count, e.key[:100]))
 
 
 if __name__ == "__main__":
