@@ -519,18 +519,9 @@ def main():
         sampler.stop()
         clocks = sampler.summary(t0, t1, load_t0, load_t1)
 
-    # ---------------- CPU baseline (oracle port), rank 0 at N=1 only ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        gens = oracle_generator(subs[:2], threads)
-        time_oracle(gens, 1, seed=5)
-        n = 12
-        dt = time_oracle(gens, n, seed=6)
-        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d samples of 160^3 (same label maps, same parameter ranges), torch %d threads" % (n, threads)}
-
     # ---------------- the other BASELINE.json configurations, on the record (extra keys, not bench values) ----------------
+    # (before the CPU baseline: after ~4 s of 16 busy host threads the host-paced ShapeID solver loop was measured at
+    # twice its time)
     extras = {}
     if not args.no_extras:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -550,6 +541,17 @@ def main():
                 extras["slab512"].pop("profile", None)
         except Exception as e:                                # never lose the bench line over an extra
             extras["error"] = repr(e)[:300]
+
+    # ---------------- CPU baseline (oracle port), rank 0 at N=1 only ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        gens = oracle_generator(subs[:2], threads)
+        time_oracle(gens, 1, seed=5)
+        n = 12
+        dt = time_oracle(gens, n, seed=6)
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d samples of 160^3 (same label maps, same parameter ranges), torch %d threads" % (n, threads)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
