@@ -51,7 +51,10 @@ def run(size=512, steps=5, rank=0, world=1, local=0):
     # volumes in flight: each on its own stream with its own scratch (DevicePipeline), so that one volume's rendezvous
     # waits (two plane exchanges, one all-reduce) are filled with the other's kernels.  Every rank issues the same
     # sequence of NCCL operations, whatever the lane.
-    lanes = int(os.environ.get("SLAB_LANES", "2"))
+    # (measured, same 20 volumes: 2.43 -> 2.28 ms on 1 GPU, 1.47 -> 1.31 on 2, 0.89 on 4; on 8 GPUs the host side -- 8
+    # Python processes and their NCCL proxy threads on the box's 32 vCPUs -- is the limit and a second volume in flight
+    # costs more host time than it hides: 1.32 ms against 0.96 with one)
+    lanes = int(os.environ.get("SLAB_LANES", "2" if world <= 4 else "1"))
     from brainfm_b200.pipeline import DevicePipeline
     pipe = DevicePipeline(ds, depth=lanes)
     job = lambda: generate_slab(ds, 0, rank, world)
