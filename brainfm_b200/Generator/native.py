@@ -39,6 +39,7 @@ class NativePlanner:
         self._fp = self.fingerprint()
         self.last = None
         self._prep = {}
+        self._prep_version = -1
         self._other_targets = None
 
     _KEYS = ('photo_prob', 'pathology_prob', 'random_shape_prob', 'flip_prob', 'max_rotation', 'max_shear',
@@ -156,8 +157,11 @@ class NativePlanner:
         order + eviction epoch).  Saves ~0.15 ms of ctypes stores and dictionary look-ups per batch of 8."""
         ds = self.ds
         key = tuple(int(i) for i in indices)
-        ent = self._prep.get(key)
         cache = ds.cache
+        if self._prep_version != cache.version:
+            self._prep.clear()               # entries hold references to cached tensors: drop them with the old set
+            self._prep_version = cache.version
+        ent = self._prep.get(key)
         if use_cache and ent is not None and ent['version'] == cache.version:
             cache.touch(ent['keys'])
             return ent
@@ -195,8 +199,9 @@ class NativePlanner:
         ent = dict(items=items, metas=metas, n_aux_total=n_aux_total, src_pad=src_pad, keys=keys,
                    version=cache.version, ok=None)
         if use_cache:
-            if len(self._prep) > 256:
+            if len(self._prep) > 256 or self._prep_version != cache.version:      # volumes were loaded while preparing
                 self._prep.clear()
+                self._prep_version = cache.version
             self._prep[key] = ent
         return ent
 
