@@ -1003,6 +1003,23 @@ class BaseGen(Dataset):
             items.append(self._finish_item(ctx, target, sample))
         return items
 
+    def generate_batch_fast(self, indices):
+        """generate_batch through `NativePlanner.run_fast` (one library call per batch, lazily built result tuples), or
+        None when the configuration / batch needs the general path.  BFM_FAST_SUBMIT=0 disables it."""
+        if os.environ.get("BFM_FAST_SUBMIT", "1") == "0" or self.planner == 'python':
+            return None
+        self.cache.begin_batch()
+        from .native import NativePlanner
+        if not (NativePlanner.config_ok(self) and (self.planner == 'native' or type(self.rng) is HostDraws)):
+            return None
+        if self._native is None:
+            self._native = NativePlanner(self)
+        else:
+            self._native.refresh()
+        if not self._native.fast_ok():
+            return None
+        return self._native.run_fast(indices)
+
     def _slow_item(self, ctx):
         """Op-by-op path: real-image inputs, custom augmentation sequences, pathology."""
         self.arena.commit()

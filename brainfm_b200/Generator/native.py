@@ -40,6 +40,8 @@ class NativePlanner:
         self.last = None
         self._prep = {}
         self._prep_version = -1
+        self._items = {}
+        self._item_version = -1
         self._other_targets = None
 
     _KEYS = ('photo_prob', 'pathology_prob', 'random_shape_prob', 'flip_prob', 'max_rotation', 'max_shear',
@@ -212,6 +214,114 @@ class NativePlanner:
         if ent['ok'] is None:
             ent['ok'] = all(self.item_ok(ds.idx_to_path(m[0])[1], m[4]) for m in ent['metas'])
         return ent['ok']
+
+    # ---- one batch, lean path ------------------------------------------------------------------------------
+    def fast_ok(self):
+        """run_fast covers native draws with every requested target riding on the fused gather (no op-wise target
+        readers, no replay, no stage timers)."""
+        ds = self.ds
+        if getattr(ds.rng, 'replay', False):
+            return False
+        other = self._other_targets
+        if other is None:
+            other = self._other_targets = any(t in K.processing_funcs and t not in ('T1', 'T2', 'FLAIR')
+                                              for t in ds.tasks)
+        return not other
+
+    def _item_entry(self, idx):
+        """Per-INDEX cached PlanItem bytes + metadata (valid while the device cache holds the same tensors)."""
+        ds, cache = self.ds, self.ds.cache
+        if self._item_version != cache.version:
+            self._items.clear()
+            self._item_version = cache.version
+        ent = self._items.get(idx)
+        if ent is not None:
+            return ent
+        prep = self._prepare([idx], use_cache=False)
+        meta = prep['metas'][0]
+        ent = dict(raw=bytes(prep['items']), meta=meta, keys=prep['keys'], n_aux=len(meta[5]),
+                   src_pad=prep['src_pad'], ok=self.item_ok(ds.idx_to_path(idx)[1], meta[4]),
+                   needs_plan=len(meta[5]) < sum(1 for k in ('T1', 'T2', 'FLAIR') if k in meta[4]),
+                   case_name=_case_name(meta[2]))
+        if self._item_version != cache.version:              # volumes were loaded while preparing
+            self._items.clear()
+            self._item_version = cache.version
+        self._items[idx] = ent
+        return ent
+
+    def run_fast(self, indices):
+        """generate_batch for the common case in ONE library call (bfm_plan_run: buffer lay-out, planning, descriptor
+        upload, every stage launch) and a few dozen microseconds of Python: per-index cached PlanItems are copied into
+        the batch array, the output tensors are allocated, and the per-item result tuples are built only when somebody
+        indexes the returned sequence (`LazyItems`; `.input` / `.bias_field_log` / `.targets` are the collated batch
+        tensors a trainer consumes).  Returns None when the batch needs the general path (`run`)."""
+        ds, L = self.ds, _lib.lib()
+        B = len(indices)
+        ns = self.n_samples
+        total = B * ns
+        ents = []
+        for idx in indices:
+            e = self._item_entry(int(idx))
+            if not e['ok'] or e['needs_plan']:
+                return None
+            ents.append(e)
+        if self.seed is None:
+            self.seed = int(np.random.randint(0, 2 ** 62))
+        ds.hemis_mask = None
+        size, N, dev = self.size, self.N, self.device
+        items = (_lib.PlanItem * B)()
+        isz = C.sizeof(_lib.PlanItem)
+        base = C.addressof(items)
+        touch = ds.cache.touch
+        n_aux_total, src_pad = 0, 0
+        for n, e in enumerate(ents):
+            C.memmove(base + n * isz, e['raw'], isz)
+            touch(e['keys'])
+            n_aux_total += e['n_aux']
+            if e['src_pad'] > src_pad:
+                src_pad = e['src_pad']
+        src_pad = (src_pad + 3) // 4 * 4 * 2                 # float2 {synthetic, target} pairs (syn_pair_ok)
+        want_bflog = ds._want_bflog('synth')
+        want_res = 'super_resolution' in ds.tasks
+        out = torch.empty((total, 1, *size), dtype=torch.float32, device=dev)
+        bfl = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_bflog else None
+        res = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_res else None
+        aux_all = torch.empty((n_aux_total, 1, *size), dtype=torch.float32, device=dev) if n_aux_total else None
+        syn_ws = ds._workspace('syn', total * src_pad, zero=True)
+        if ds._ws.get('syn_stride') != src_pad:
+            if 'syn_stride' in ds._ws:
+                syn_ws.zero_()
+            ds._ws['syn_stride'] = src_pad
+        bufs = _lib.StepBufs()
+        bufs.out = out.data_ptr()
+        bufs.bflog_out = bfl.data_ptr() if bfl is not None else None
+        bufs.residual = res.data_ptr() if res is not None else None
+        bufs.syn = syn_ws.data_ptr()
+        bufs.syn_stride = src_pad
+        bufs.i_bf = ds._workspace('i_bf', total * N).data_ptr()
+        bufs.tmp = ds._workspace('tmp', total * 2 * N).data_ptr()
+        bufs.lowres = ds._workspace('lowres', total * N + 16).data_ptr()
+        if n_aux_total:
+            bufs.aux_out = aux_all.data_ptr()
+            bufs.aux_raw = ds._workspace('aux_raw', n_aux_total * N).data_ptr()
+        bufs.pair_ok = 1 if ds.pair_mode else 0
+        arena = ds.arena.begin()
+        slot = arena.slots[arena.cur]
+        descs = (_lib.GenSample * total)()
+        descs_dev = C.c_void_p(0)
+        info = (_lib.PlanInfo * B)()
+        used = C.c_int64(0)
+        _lib.check(L.bfm_plan_run(C.addressof(self.cfg), B, base, C.addressof(bufs), self.seed, self.counter,
+                                  slot["host"].data_ptr(), slot["dev"].data_ptr(), arena.capacity, arena.used,
+                                  C.byref(used), C.addressof(descs), C.byref(descs_dev), C.addressof(info), _stream()))
+        self.counter += B
+        arena.used = arena.committed = used.value
+        arena.mark_done()
+        self.last = dict(descs=descs, descs_dev=descs_dev.value, info=info, total=total,
+                         keep=(out, bfl, res, aux_all, items), arena_slot=arena.cur)
+        ds._last_descs = (descs, descs_dev.value, total)
+        ds._last_out = out
+        return LazyItems(ds, ents, info, ns, out, bfl, res, aux_all)
 
     # ---- one batch ---------------------------------------------------------------------------------------
     def run(self, indices, timers=None, patch=None, plan_only=False):
@@ -471,3 +581,73 @@ _INPUT_MODES = ('synth', 'T1', 'T2', 'FLAIR', 'CT')
 def _case_name(t1_path):
     import os
     return os.path.basename(t1_path).split('.T1w.nii')[0]
+
+
+class LazyItems:
+    """What `run_fast` returns: the batch as collated device tensors (`input`: (B * n_samples, 1, *size), `bias_field_log`,
+    `high_res_residual`, `targets[key]`: (B, 1, *size)) and, on demand, the reference-shaped per-item tuples
+    `(datasets_num, dataset_name, input_mode, target, sample)` -- a sequence: len(), indexing and iteration build
+    them exactly as `NativePlanner.run` does."""
+
+    def __init__(self, ds, ents, info, ns, out, bfl, res, aux_all):
+        self._ds, self._ents, self._info, self._ns = ds, ents, info, ns
+        self.input, self.bias_field_log, self.high_res_residual = out, bfl, res
+        self._aux = aux_all
+        self._built = None
+
+    @property
+    def targets(self):
+        """{key: (n_items_with_that_target, 1, *size)} of the fused real-image targets, in item order."""
+        out, k = {}, 0
+        for e in self._ents:
+            for key, _ in e['meta'][5]:
+                out.setdefault(key, []).append(self._aux[k])
+                k += 1
+        return {key: torch.stack(v) for key, v in out.items()}
+
+    def _build(self):
+        if self._built is not None:
+            return self._built
+        ds, ns, info = self._ds, self._ns, self._info
+        out_v = self.input.unbind(0)
+        bfl_v = self.bias_field_log.unbind(0) if self.bias_field_log is not None else None
+        res_v = self.high_res_residual.unbind(0) if self.high_res_residual is not None else None
+        aux_v = self._aux.unbind(0) if self._aux is not None else ()
+        tuples, k_aux = [], 0
+        for n, e in enumerate(self._ents):
+            idx, dataset_name, t1_path, age, mods, aux, src = e['meta']
+            inf = info[n]
+            target = defaultdict(ds._default_target)
+            target['name'] = e['case_name']
+            fused = {}
+            for key, _ in aux:
+                fused[key] = aux_v[k_aux]
+                k_aux += 1
+            for key in ('T1', 'T2', 'FLAIR'):
+                target[key] = fused[key] if key in fused else 0.
+            target['pathology'] = 0.
+            target['pathology_prob'] = 0.
+            if age is not None:
+                target['age'] = age
+            results = []
+            for q in range(n * ns, (n + 1) * ns):
+                smp = {}
+                if res_v is not None:
+                    smp['high_res_residual'] = res_v[q]
+                smp['input'] = out_v[q]
+                if bfl_v is not None and inf.input_mode != 4:          # no bias field on CT inputs
+                    smp['bias_field_log'] = bfl_v[q]
+                results.append(smp)
+            sample = results if ds._list_samples else results[0]
+            tuples.append((ds.datasets_num, dataset_name, _INPUT_MODES[inf.input_mode], target, sample))
+        self._built = tuples
+        return tuples
+
+    def __len__(self):
+        return len(self._ents)
+
+    def __getitem__(self, n):
+        return self._build()[n]
+
+    def __iter__(self):
+        return iter(self._build())

@@ -86,6 +86,11 @@ class PlanOut(C.Structure):
                 ("lowres", c_p), ("syn_pair_ok", c_i64)]
 
 
+class StepBufs(C.Structure):
+    _fields_ = [("out", c_p), ("bflog_out", c_p), ("residual", c_p), ("syn", c_p), ("syn_stride", c_i64),
+                ("i_bf", c_p), ("tmp", c_p), ("lowres", c_p), ("aux_out", c_p), ("aux_raw", c_p), ("pair_ok", c_i64)]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [("input_mode", c_i), ("photo_mode", c_i), ("flip", c_i), ("spac", c_d), ("resolution", c_d * 3), ("thickness", c_d * 3),
                 ("scaling_factor_distances", c_d), ("A", c_f * 9), ("c2", c_f * 3), ("fs", c_i * 3),
@@ -129,6 +134,8 @@ _PROTOS = {
     "bfm_gen_run": (c_i, [c_p, c_p, c_i, c_p]),
     "bfm_plan_batch": (c_i, [c_p, c_i, c_p, c_p, c_u64, c_u64, c_p, c_p, c_i64, C.POINTER(c_i64), C.POINTER(c_i64),
                              c_p, C.POINTER(c_p), c_p, c_p, c_i64, C.POINTER(c_i64)]),
+    "bfm_plan_run": (c_i, [c_p, c_i, c_p, c_p, c_u64, c_u64, c_p, c_p, c_i64, c_i64, C.POINTER(c_i64), c_p,
+                           C.POINTER(c_p), c_p, c_p]),
     "bfm_interpol": (c_i, [c_i, c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_i, c_i, c_i,
                            c_i, c_i, c_i, c_i64, c_p]),
     "bfm_interpol_grad_backward": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i),

@@ -89,7 +89,14 @@ class DevicePipeline:
         ds._ws = lane["ws"]
         try:
             with torch.cuda.stream(lane["stream"]):
-                items = call() if call is not None else ds.generate_batch(list(indices), timers=timers)
+                if call is not None:
+                    items = call()
+                else:
+                    items = None
+                    if timers is None:
+                        items = ds.generate_batch_fast(indices)          # one library call when the batch allows it
+                    if items is None:
+                        items = ds.generate_batch(list(indices), timers=timers)
                 ev = torch.cuda.Event()
                 ev.record(lane["stream"])
         finally:

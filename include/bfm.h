@@ -386,6 +386,25 @@ int bfm_plan_batch(const bfm_plan_cfg *cfg, int n_items, const bfm_plan_item *it
                    int64_t *arena_used, int64_t *upload_bytes, bfm_gen_sample *descs_host, void **descs_dev,
                    bfm_plan_info *info, const double *replay, int64_t n_replay, int64_t *replay_used);
 
+/* Base pointers of a batch's buffers, per-sample strides implied: out / bflog_out / residual / i_bf / lowres advance by
+ * prod(size) floats per sample, tmp by 2 * prod(size), syn by syn_stride; aux_out / aux_raw by prod(size) per fused
+ * real-image target, in item order. */
+typedef struct bfm_step_bufs {
+    float *out, *bflog_out, *residual;
+    float *syn;
+    int64_t syn_stride;
+    float *i_bf, *tmp, *lowres;
+    float *aux_out, *aux_raw;
+    int64_t pair_ok;
+} bfm_step_bufs;
+
+/* bfm_plan_batch (native draws) + bfm_upload_pinned of the host-written arena prefix + bfm_gen_run, with the per-sample
+ * buffers laid out from `bufs`: ONE call per batch.  items[n].aux_out / aux_raw are filled in.  arena_used_in: bytes of
+ * the arena already reserved; *arena_used_out: after planning. */
+int bfm_plan_run(const bfm_plan_cfg *cfg, int n_items, bfm_plan_item *items, const bfm_step_bufs *bufs, uint64_t seed,
+                 uint64_t counter, void *arena_host, void *arena_dev, int64_t arena_capacity, int64_t arena_used_in,
+                 int64_t *arena_used_out, bfm_gen_sample *descs_host, void **descs_dev, bfm_plan_info *info, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * utils/interpol (vendored torch-interpol 0.2.3): spline resampling, forward semantics
  * ---------------------------------------------------------------------------------------------- */

@@ -116,6 +116,31 @@ def test_device_pipeline_two_lanes_equals_one_stream():
         assert torch.isfinite(t).all() and float(t.min()) == 0.0 and float(t.max()) == 1.0
 
 
+def test_one_call_batches_equal_the_general_path():
+    """generate_batch_fast (bfm_plan_run: one library call per batch, lazily built tuples) against generate_batch with
+    the same planner state: every tensor of every item bit for bit, same tuple structure; arbitrary index order."""
+    ds, subs = _dataset()
+    for idx in ([0, 1, 2, 3], [3, 1], [2, 2, 0]):
+        ref = _run(ds, lambda: ds.generate_batch(idx))
+        ref = [(a, b, c, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()},
+                {k: v.clone() for k, v in e.items()}) for a, b, c, d, e in ref]
+        got = _run(ds, lambda: ds.generate_batch_fast(idx))
+        assert got is not None and len(got) == len(idx)
+        torch.cuda.synchronize()
+        assert got.input.shape[0] == len(idx) and set(got.targets) == {'T1'}
+        for n, (r, g) in enumerate(zip(ref, got)):
+            assert r[:3] == g[:3]
+            assert set(r[4]) == set(g[4]) and {k for k in r[3]} == {k for k in g[3]}
+            for k in r[4]:
+                assert torch.equal(r[4][k], g[4][k]), (n, k)
+            for k, v in r[3].items():
+                if torch.is_tensor(v):
+                    assert torch.equal(v, g[3][k]), (n, k)
+                else:
+                    assert v == g[3][k], (n, k)
+            assert torch.equal(got.input[n], g[4]['input']) and torch.equal(got.targets['T1'][n], g[3]['T1'])
+
+
 def test_cache_eviction_is_lru_and_spares_the_batch_in_flight():
     from brainfm_b200 import io as bio
     bio.clear_registry()
