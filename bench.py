@@ -33,6 +33,25 @@ METRIC = "synthetic 160^3 samples/sec (BaseGen default chain, batch 8)"
 UNIT = "samples/s"
 
 
+class quiet_gc:
+    """Timed regions run with Python's cyclic collector off (what `timeit` does): a generation-2 collection over the
+    heap of an imported torch takes 5-200 ms and lands deterministically inside a 20-step region (measured: ONE step
+    of 206 ms among 0.3 ms steps; profiles/README.md, 'host-side stalls').  The current heap is frozen first so that
+    later collections stay cheap."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        gc.enable()
+        return False
+
+
 def make_inputs(n_subjects):
     """Subjects of the bench: label map = the 160^3 crop of round(files/gca.mgz) SURVEY.md 8d names (committed as
     tests/golden/atlas_gca_L160_u8.npz -- the reference tree does not exist on the GPU box), shifted by a few voxels per
@@ -385,27 +404,56 @@ def main():
     from brainfm_b200.pipeline import DevicePipeline
     dpipe = DevicePipeline(ds, depth=args.lanes)
     tickets = []
-    for _ in range(2 * args.lanes):
+    # untimed: the pipeline's own warm-up, in the same submit / wait rhythm as the timed loop (a one-off host stall of
+    # 1.5-200 ms was measured at the pipeline's 8th submit whatever the path -- see profiles/README.md)
+    for _ in range(max(2 * args.lanes, int(os.environ.get("BFM_PIPE_WARMUP", "16")))):
         tickets.append(dpipe.submit(idxs))
+        if len(tickets) > args.lanes:
+            tickets.pop(0).wait()
     for t in tickets:
         t.wait()
+    tickets = []
+    t = None          # the loop variable would keep the last warm-up batch's outputs alive through the timed loop: one
+    #                   more live set than the warm-up ever had => three cudaMallocs (1.3-200 ms) at the third timed step
     barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gcq = quiet_gc().__enter__()
+    barrier()
     e0.record()
     wait0 = ds.arena.wait_s
     t0 = time.perf_counter()
     tickets = []
+    trace = [] if os.environ.get("BFM_BENCH_TRACE") == "1" else None
+    if trace is not None:
+        ds._trace = []
     for k in range(args.steps):
+        if trace is not None:
+            ts = time.perf_counter()
         tickets.append(dpipe.submit(idxs))
         if len(tickets) > args.lanes:
             tickets.pop(0).wait()                # the consumer's stream takes the batch (stream wait, no host sync)
+        if trace is not None:
+            trace.append(round(1e3 * (time.perf_counter() - ts), 3))
+            tr = getattr(ds, '_trace', None)
+            if rank == 0 and k < 6:
+                ms_ = torch.cuda.memory_stats()
+                print("step %d: segments %d, cudaMalloc retries %d, reserved %.2f GB, active %.2f GB, host %.3f ms" %
+                      (k, ms_.get("segment.all.current", -1), ms_.get("num_alloc_retries", -1),
+                       ms_.get("reserved_bytes.all.current", 0) / 1e9, ms_.get("active_bytes.all.current", 0) / 1e9,
+                       trace[-1]), file=sys.stderr, flush=True)
+            if tr and trace[-1] > 1.0 and rank == 0:
+                print("slow step %d: %s (whole step %.3f ms)" % (k, [(a, round(1e3 * (b - tr[0][1]), 3)) for a, b in tr],
+                                                                 trace[-1]), file=sys.stderr, flush=True)
     for t in tickets:
         t.wait()
     e1.record()
     barrier()
     t1 = time.perf_counter()
+    gcq.__exit__()
     host_s = t1 - t0
+    if trace is not None and rank == 0:
+        print("per-step host ms: %s" % trace, file=sys.stderr, flush=True)
     host_wait_s = ds.arena.wait_s - wait0        # of which: waiting for a free plan-arena slot, i.e. for the GPU
     launches = _lib.launch_count() - l0
     dev_ms = e0.elapsed_time(e1)
@@ -504,10 +552,11 @@ def main():
         print("e2e warm-up ms/step per block of 8: %s" % series, file=sys.stderr, flush=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    e2e_run(args.steps)
-    torch.cuda.synchronize()
-    f1.record()
+    with quiet_gc():
+        f0.record()
+        e2e_run(args.steps)
+        torch.cuda.synchronize()
+        f1.record()
     barrier()
     el2 = torch.tensor([f0.elapsed_time(f1)], device=device, dtype=torch.float64)
     if world > 1:
@@ -525,6 +574,7 @@ def main():
     extras = {}
     if not args.no_extras:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
+        gcx = quiet_gc().__enter__()
         try:
             if world == 1:
                 import config_bench as cb
@@ -541,6 +591,7 @@ def main():
                 extras["slab512"].pop("profile", None)
         except Exception as e:                                # never lose the bench line over an extra
             extras["error"] = repr(e)[:300]
+        gcx.__exit__()
 
     # ---------------- CPU baseline (oracle port), rank 0 at N=1 only ----------------
     cpu = None

@@ -256,6 +256,11 @@ class NativePlanner:
         indexes the returned sequence (`LazyItems`; `.input` / `.bias_field_log` / `.targets` are the collated batch
         tensors a trainer consumes).  Returns None when the batch needs the general path (`run`)."""
         ds, L = self.ds, _lib.lib()
+        tr = getattr(ds, '_trace', None)           # development aid: host time stamps of the last call
+        if tr is not None:
+            import time as _t
+            tr.clear()
+            tr.append(('start', _t.perf_counter()))
         B = len(indices)
         ns = self.n_samples
         total = B * ns
@@ -281,12 +286,27 @@ class NativePlanner:
             if e['src_pad'] > src_pad:
                 src_pad = e['src_pad']
         src_pad = (src_pad + 3) // 4 * 4 * 2                 # float2 {synthetic, target} pairs (syn_pair_ok)
+        if tr is not None:
+            tr.append(('items', _t.perf_counter()))
         want_bflog = ds._want_bflog('synth')
         want_res = 'super_resolution' in ds.tasks
+        # Outputs come from the CALLER's stream pool when a pipeline set one (DevicePipeline): the caching allocator keeps
+        # one pool of free blocks per stream, and with the outputs in the lanes' pools a lane was measured to run out of
+        # free 131 MB blocks and cudaMalloc three new ones (1.3-200 ms) while a dozen sat free in the other pools.  Safe:
+        # every submit() orders the lane after the caller's stream, so a block the consumer freed is only rewritten
+        # after the consumer's work on it (see pipeline._DeviceTicket.wait).
+        als = getattr(ds, '_alloc_stream', None)
+        if als is not None:
+            lane_stream = torch.cuda.current_stream(dev)
+            torch.cuda.set_stream(als)
         out = torch.empty((total, 1, *size), dtype=torch.float32, device=dev)
         bfl = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_bflog else None
         res = torch.empty((total, 1, *size), dtype=torch.float32, device=dev) if want_res else None
         aux_all = torch.empty((n_aux_total, 1, *size), dtype=torch.float32, device=dev) if n_aux_total else None
+        if als is not None:
+            torch.cuda.set_stream(lane_stream)
+        if tr is not None:
+            tr.append(('outputs', _t.perf_counter()))
         syn_ws = ds._workspace('syn', total * src_pad, zero=True)
         if ds._ws.get('syn_stride') != src_pad:
             if 'syn_stride' in ds._ws:
@@ -305,7 +325,11 @@ class NativePlanner:
             bufs.aux_out = aux_all.data_ptr()
             bufs.aux_raw = ds._workspace('aux_raw', n_aux_total * N).data_ptr()
         bufs.pair_ok = 1 if ds.pair_mode else 0
+        if tr is not None:
+            tr.append(('workspaces', _t.perf_counter()))
         arena = ds.arena.begin()
+        if tr is not None:
+            tr.append(('arena', _t.perf_counter()))
         slot = arena.slots[arena.cur]
         descs = (_lib.GenSample * total)()
         descs_dev = C.c_void_p(0)
@@ -314,11 +338,15 @@ class NativePlanner:
         _lib.check(L.bfm_plan_run(C.addressof(self.cfg), B, base, C.addressof(bufs), self.seed, self.counter,
                                   slot["host"].data_ptr(), slot["dev"].data_ptr(), arena.capacity, arena.used,
                                   C.byref(used), C.addressof(descs), C.byref(descs_dev), C.addressof(info), _stream()))
+        if tr is not None:
+            tr.append(('plan_run', _t.perf_counter()))
         self.counter += B
         arena.used = arena.committed = used.value
         arena.mark_done()
         self.last = dict(descs=descs, descs_dev=descs_dev.value, info=info, total=total,
                          keep=(out, bfl, res, aux_all, items), arena_slot=arena.cur)
+        if tr is not None:
+            tr.append(('done', _t.perf_counter()))
         ds._last_descs = (descs, descs_dev.value, total)
         ds._last_out = out
         return LazyItems(ds, ents, info, ns, out, bfl, res, aux_all)

@@ -87,6 +87,7 @@ class DevicePipeline:
         lane["stream"].wait_stream(cur)               # volumes uploaded / refreshed on the caller's stream are visible
         saved = ds._ws
         ds._ws = lane["ws"]
+        ds._alloc_stream = cur                         # output tensors: the caller's pool (see NativePlanner.run_fast)
         try:
             with torch.cuda.stream(lane["stream"]):
                 if call is not None:
@@ -101,6 +102,7 @@ class DevicePipeline:
                 ev.record(lane["stream"])
         finally:
             ds._ws = saved
+            ds._alloc_stream = None
         return _DeviceTicket(items, ev, lane["stream"])
 
 
