@@ -197,13 +197,40 @@ def _generate_slab_native(ds, native, idx, rank, world, group):
     sample = {'input': fin[None], 'x_range': (x0, x1)}
     if plan['bfl'] is not None and s.bflog_out:
         sample['bias_field_log'] = plan['bfl'][0][:, x0:x1]
+    # ---- real-image targets that ride on the gather (read_and_deform_image, Generator/utils.py:324-343): the warp
+    # wrote this rank's planes of the raw warped volume and reduced ITS min / max; `Idef -= min; Idef /= max` needs the
+    # volume's: one all-reduce of 2 * n_aux order-preserving ints (MAX of {-min, max}), then the normalise + flip pass
+    n_aux = int(s.n_aux)
+    if n_aux:
+        arena = plan['arena']
+        base = arena.slots[arena.cur]["dev"].data_ptr()
+        mm = arena.view(s.aux_mm - base, 2 * n_aux, torch.int32).clone()
+        mm[0::2] = -mm[0::2]
+        if world > 1:
+            if dist.get_backend(group) == "gloo":
+                h_mm = mm.cpu()
+                dist.all_reduce(h_mm, op=dist.ReduceOp.MAX, group=group)
+                mm = h_mm.to(dev)
+            else:
+                dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+        mm[0::2] = -mm[0::2]
+        mmf = torch.where(mm >= 0, mm, mm ^ 0x7fffffff).view(torch.float32)         # ord2f (csrc/common.cuh)
+        keys = [k for k, _ in plan['metas'][0][5]]
+        for a in range(n_aux):
+            raw = ds._ws['aux_raw'][a * N:(a + 1) * N].view(s0, s1, s2)[c0:c1]
+            tgt = torch.empty((c1 - c0, s1, s2), dtype=torch.float32, device=dev)
+            _lib.check(L.bfm_shift_scale_flip(raw.data_ptr(), tgt.data_ptr(), c1 - c0, s1 * s2,
+                                              mmf[2 * a:2 * a + 1].data_ptr(), mmf[2 * a + 1:2 * a + 2].data_ptr(), 1.0,
+                                              1 if flip else 0, st))
+            sample[keys[a]] = tgt[None]
     plan['arena'].mark_done()
     return sample
 
 
 def generate_slab(ds, idx, rank=None, world=None, group=None):
     """This rank's x-slab of sample `idx` of dataset `ds` (BaseGen): {'input': (1, nx, s1, s2),
-    'bias_field_log': (1, nx, s1, s2) or absent, 'x_range': (x0, x1)} with x0:x1 the owned planes of the final
+    'bias_field_log': (1, nx, s1, s2) or absent, 'T1' / 'T2' / 'FLAIR': (1, nx, s1, s2) for the real-image targets that
+    ride on the fused gather (library planner), 'x_range': (x0, x1)} with x0:x1 the owned planes of the final
     (flipped) output volume.  Every rank must call this with the same generator seeds."""
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0

@@ -60,11 +60,18 @@ def main():
         if os.environ.get("BFM_SLAB_PLANNER") == "native":
             assert ds._native is not None and ds._last_descs[0][0].gen_small != 0      # planned by the library
         solo = seeded(lambda: generate_slab(ds, 0, 0, 1), seed, ds)
-        fused = seeded(lambda: ds.generate_batch([0])[0][4]['input'], seed, ds)
+        item = seeded(lambda: ds.generate_batch([0])[0], seed, ds)
+        fused = item[4]['input']
         torch.cuda.synchronize()
         x0, x1 = mine["x_range"]
         same = torch.equal(mine["input"], solo["input"][:, x0:x1])
         close = np.allclose(solo["input"].cpu().numpy(), fused.cpu().numpy(), rtol=1e-5, atol=1e-4)
+        if os.environ.get("BFM_SLAB_PLANNER") == "native":
+            # the real-image target that rides on the gather is sharded too: every rank's planes equal the single-rank
+            # run's and the fused chain's target bit for bit (same gathers, the volume's min / max all-reduced)
+            assert "T1" in mine and torch.is_tensor(item[3]["T1"])
+            same = same and torch.equal(mine["T1"], solo["T1"][:, x0:x1]) and \
+                torch.equal(solo["T1"], item[3]["T1"])
         if "bias_field_log" in mine:
             same = same and torch.equal(mine["bias_field_log"], solo["bias_field_log"][:, x0:x1])
         if rank == 0:
