@@ -128,7 +128,8 @@ class ClockSampler:
     def start(self):
         if os.environ.get("BFM_CLOCK_MS") == "0":       # development switch: no sampler at all
             return
-        self.period = float(os.environ.get("BFM_CLOCK_MS", "20")) * 1e-3
+        # in-process NVML: 5 ms period, so that a timed region of ~14 ms (20 steps) holds 2-3 samples
+        self.period = float(os.environ.get("BFM_CLOCK_MS", "5")) * 1e-3
         self._stop = False
         # in-process NVML (three queries per sample) when pynvml is importable; an `nvidia-smi -lms` child otherwise.
         # The child re-queries a dozen fields per line through the driver and was measured to cost the two-stream
