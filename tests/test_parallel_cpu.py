@@ -108,3 +108,33 @@ def test_by_sample_mode_gloo():
     assert sorted(out[0][0] + out[1][0]) == list(range(32))
     assert out[0][1] != out[1][1]
     assert out[0][2] == out[1][2] == 16.0
+
+
+def test_slab_host_ranges_match_the_band_and_zoom_tables():
+    """Generator/slab.py plans its plane exchanges on the host from cached per-axis ranges: the first tap of the banded
+    x pass must be band_host's `start`, the zoom-back ranges the zoom tables' lo / hi -- for every (n_in, n_out) a 64^3
+    or 160^3 volume can draw."""
+    import numpy as np
+    from brainfm_b200.Generator import slab
+    from brainfm_b200.plan import band_host, zoom_tables_host
+    for n_in, n_out, sigma in [(64, 64, 0.0), (64, 23, 1.7), (160, 160, 0.9), (160, 53, 2.4), (160, 18, 4.6), (512, 171, 2.1)]:
+        lo, centre = slab._band_ranges_host(n_in, n_out)
+        start, w, T = band_host(n_in, n_out, sigma)
+        assert np.array_equal(lo - (T - 2) // 2, start)
+        assert centre.min() >= 0 and centre.max() <= n_in - 1 and np.all(np.diff(centre) >= 0)
+        zlo, zhi = slab._zoom_ranges_host(n_out, n_in)
+        t = zoom_tables_host(n_out, 1 / (n_out / n_in), n_in)
+        assert np.array_equal(zlo, t[0]) and np.array_equal(zhi, t[1])
+        assert np.all(np.diff(zlo) >= 0) and zhi.max() <= n_out - 1
+    # every plane a rank's low-res outputs read lies inside the range the exchange asks for
+    n_in, n_out, sigma, world = 160, 41, 3.3, 4
+    lo, centre = slab._band_ranges_host(n_in, n_out)
+    start, w, T = band_host(n_in, n_out, sigma)
+    from brainfm_b200 import parallel as par
+    for r in range(world):
+        b, e = par.slab_bounds(n_in, r, world)
+        o = np.nonzero((centre >= b) & (centre < e))[0]
+        if o.size:
+            need = (max(0, start[o[0]:o[-1] + 1].min()), min(n_in, start[o[0]:o[-1] + 1].max() + T))
+            taps = np.concatenate([np.arange(max(0, s), min(n_in, s + T)) for s in start[o[0]:o[-1] + 1]])
+            assert taps.min() >= need[0] and taps.max() < need[1]
